@@ -1,0 +1,156 @@
+/*
+ * scan3d_oracle.h -- CPU ORACLE for the 3dscan per-pixel reconstruction hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product.  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker / the timed CPU baseline.
+ *
+ * It is a plain-C restatement (no OpenCV, no PCL) of the reference's loops:
+ *   3/wrapped_phase.cpp          -> o3d_check_roi, o3d_wrapped_phase, o3d_mask_recurrence
+ *   4/phase_unwrap.cpp           -> o3d_decode_gray, o3d_unwrap, o3d_unwrapped_image
+ *   5/compute_correspondance.cpp -> o3d_compute_c_p_map
+ *   6/system_calibration.cpp     -> o3d_rodrigues, o3d_compose_relative (KAT only)
+ *   7/triangulation.cpp          -> o3d_undistort_lut, o3d_compute_A, o3d_triangulate
+ *   8/save_point_cloud.cpp       -> o3d_compact
+ * The reference itself cannot be compiled here (OpenCV 2.4 C API, PCL 1.6, V4L2,
+ * hard-coded /home/pranav paths), so the OpenCV arithmetic on the path
+ * (cvUndistortPoints, cvRodrigues2, cvMatMul, cvInvert 3x3) is restated from the
+ * published OpenCV 2.4 algorithm and cross-checked against cv2 4.13 in this
+ * container (tools/make_golden.py -> tests/golden/opencv_kat.npz).
+ *
+ * Pinning status:
+ *   stages 3+4 : PINNED bit-for-bit by the reference's stored Wrapped_phase_image.bmp /
+ *                Unwrapped_phase_*.bmp (tests/test_oracle_golden.py).
+ *   Rodrigues + extrinsic composition : PINNED by Relative_geometry XML files (1e-15).
+ *   undistort / normal-equation solve / c_p_map / XYZ / PLY : "parity unpinned" by any
+ *                reference output (those blobs are missing from the reference tree);
+ *                pinned only against cv2 4.13 + numpy restatements.
+ *
+ * Layout: every image-sized plane here is ROW-MAJOR [H][W] (the reference uses
+ * [col][row]; layout does not change any value).  c_p_map is [H*W][2] like the reference.
+ *
+ * Parity-critical quirks kept on purpose:
+ *   Pi = 22.0/7.0 textual macro; 3-step uses pi/2 shifts without sqrt(3); N=3,4 use
+ *   double atan2, N=5 uses atanf2; Gray threshold is pattern-vs-inverse, tie -> 1;
+ *   bit 0 = MSB; no code range reject; "+= Pi" is stored back into wrapped phase;
+ *   unwrap skips col 0/W-1 (vertical) and row 0/H-1 (horizontal); lrint half-even;
+ *   mask "erosion" is a sequential raster recurrence, one pass; undistort runs 5 fixed
+ *   iterations on already-undistorted captures; method-3 LS triangulation in the world
+ *   frame; raster-order compaction with (float) casts.
+ * Policies where the reference reads uninitialised memory: all output planes are
+ * zero-filled before a stage writes them.
+ */
+#ifndef SCAN3D_ORACLE_H
+#define SCAN3D_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- stage 3 : 3/wrapped_phase.cpp ---- */
+/* check_I_mod_criteria :64-143 (live part :78-82,106-115): valid0 = (roi != 0). */
+void o3d_check_roi(const uint8_t *roi, int W, int H, int32_t *valid);
+
+/* create_wrapped_phase :151-238.  fringe = [N][H][W] u8.  wrapped / dbg are written only
+ * where valid==1 (caller zero-fills).  N in {3,4,5} follow the reference; N==8 and other
+ * N >= 3 are this project's extension (see .c).  dbg may be NULL. */
+void o3d_wrapped_phase(const uint8_t *fringe, int N, int W, int H, const int32_t *valid,
+                       float *wrapped, uint8_t *dbg, int threads);
+
+/* save_wrapped_image :266-279 (== :306-318): the literal sequential raster recurrence. */
+void o3d_mask_recurrence(int32_t *valid, int W, int H, uint8_t *dbg);
+
+/* closed form of the same recurrence -- used only to cross-check. */
+void o3d_mask_closed_form(const int32_t *valid0, int W, int H, int32_t *valid1);
+
+/* ---- stage 4 : 4/phase_unwrap.cpp ---- */
+/* decode_pixels :134-275 (Gray-coded branch).  gray/inv = [M][H][W] u8. */
+void o3d_decode_gray(const uint8_t *gray, const uint8_t *inv, int M, int W, int H,
+                     const int32_t *valid, int32_t *code, int threads);
+
+/* unwrap :278-316.  dir 0 = vertical (skips col 0, W-1), 1 = horizontal (skips row 0, H-1).
+ * wrapped is modified in place (+= Pi) like the reference. */
+void o3d_unwrap(int dir, float *wrapped, const int32_t *code, const int32_t *valid, int W,
+                int H, float *unwrapped, int threads);
+
+/* save_unwrap_phase_image :321-364: (uchar)((float)(Phi/(2.0*Pi*codes))*255). */
+void o3d_unwrapped_image(const float *unwrapped, const int32_t *valid, int W, int H,
+                         int number_of_codes, uint8_t *img);
+
+/* ---- stage 5 : 5/compute_correspondance.cpp ---- */
+/* merge_valid_maps :60-77 + compute_c_p_map :630-679.  cpmap = [H*W][2] int64. */
+void o3d_compute_c_p_map(const float *unw_v, const float *unw_h, const int32_t *valid_v,
+                         const int32_t *valid_h, int fw_v, int fw_h, int PW, int PH, int W,
+                         int H, int64_t *cpmap, int32_t *valid, int threads);
+
+/* ---- stage 6/7 : calibration algebra ---- */
+void o3d_rodrigues(const double rvec[3], double R[9]);           /* cvRodrigues2 (vec->mat) */
+/* 6/system_calibration.cpp:1489-1504: R = Rc*Rp^T ; T = Tc - R*Tp */
+void o3d_compose_relative(const double rc[3], const double tc[3], const double rp[3],
+                          const double tp[3], double R[9], double T[3]);
+/* cvUndistortPoints (OpenCV 2.4, 5 fixed iterations, no R/P) on n points (x,y pairs). */
+void o3d_undistort_points(const double *src_xy, int n, const double K[9], const double d[5],
+                          double *dst_xy);
+/* 7/triangulation.cpp:252-307 / :352-378: undistorted *pixel* coordinates of every pixel:
+ * lut[0][i] = u', lut[1][i] = v' for i = row*W+col. */
+void o3d_undistort_lut(const double K[9], const double d[5], int W, int H, double *lut,
+                       int threads);
+/* compute_A :1061-1126: A = K*[R(rvec)|t], 3x4 row-major. */
+void o3d_compute_A(const double K[9], const double rvec[3], const double tvec[3],
+                   double A[12]);
+/* compute_P/compute_F/compute_X_Y_Z :1134-1218 for one correspondence. */
+void o3d_triangulate_point(const double A_cam[12], const double A_proj[12], double uc,
+                           double vc, double up, double vp, double xyz[3]);
+/* compute_depth_method_3 :1223-1247.  xyz = [H][W][3] f64, written where valid==1. */
+void o3d_triangulate(const double A_cam[12], const double A_proj[12], const double *cam_lut,
+                     const double *proj_lut, const int64_t *cpmap, const int32_t *valid, int W,
+                     int H, int PW, int PH, double *xyz, int threads);
+
+/* ---- stage 8 : 8/save_point_cloud.cpp:33-39,85-136 ---- */
+/* texture = [H][W][3] BGR u8 or NULL.  Returns count; writes raster-ordered
+ * xyz_f32[count][3], rgb[count][3] (r,g,b) and pix[count] = row*W+col. Outputs may be NULL
+ * (count only). */
+int64_t o3d_compact(const double *xyz, const int32_t *valid, const uint8_t *texture, int W,
+                    int H, float *out_xyz, uint8_t *out_rgb, uint32_t *out_pix);
+
+/* ---- whole path, used as the timed CPU baseline and by the end-to-end parity tests ---- */
+typedef struct {
+    int W, H, PW, PH;   /* camera / projector resolution */
+    int N;              /* phase steps */
+    int M_v, M_h;       /* Gray bit planes per direction */
+    int fw_v, fw_h;     /* fringe width in projector pixels */
+    int dirs;           /* 1 = vertical only (stages 3+4), 2 = both (+ stages 5,7,8) */
+} o3d_config;
+
+typedef struct {
+    double Kc[9], dc[5], Kp[9], dp[5];
+    double rc[3], tc[3], rp[3], tp[3];
+} o3d_calib;
+
+typedef struct {            /* all row-major [H][W]; caller allocates, oracle zero-fills */
+    float *wrapped_v, *wrapped_h;   /* AFTER the in-place += Pi of stage 4 */
+    float *unwrapped_v, *unwrapped_h;
+    int32_t *code_v, *code_h;
+    int32_t *valid_v, *valid_h, *valid;
+    int64_t *cpmap;                 /* [H*W][2] */
+    double *xyz;                    /* [H][W][3] */
+    float *pts;                     /* [count][3] (capacity H*W) */
+    uint32_t *pix;                  /* [count] */
+    int64_t count;
+} o3d_outputs;
+
+/* stack layout: fringe_v [N][H][W], gray_v [M_v][H][W], inv_v [M_v][H][W], then the same
+ * for the horizontal direction.  Runs 3 -> 4 -> 5 -> 7 (incl. LUT build) -> 8. */
+void o3d_reconstruct(const o3d_config *cfg, const o3d_calib *cal, const uint8_t *fringe_v,
+                     const uint8_t *gray_v, const uint8_t *inv_v, const uint8_t *fringe_h,
+                     const uint8_t *gray_h, const uint8_t *inv_h, const uint8_t *roi,
+                     o3d_outputs *out, int threads);
+
+int o3d_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,138 @@
+"""Pins the CPU oracle against everything the reference tree holds for the path
+(SURVEY.md 8c): the stored wrapped / unwrapped phase images of its own scan (bit-for-bit),
+the Relative_geometry XML (Rodrigues + composition), and cv2 4.13 known answers for the
+OpenCV arithmetic (undistort, Rodrigues, gemm/invert triangulation chain)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_ffi as o
+from helpers import GOLDEN, REF, have_reference, load_c1_crop, load_calib_c1, read_bmp8
+
+
+def _stage34(fr, g, gi, gw, direction):
+    valid = (gw != 0).astype(np.int32)          # post-recurrence mask stored by the reference
+    w, dbg = o.wrapped_phase(fr, valid)
+    code = o.decode_gray(g, gi, valid)
+    w2, unw = o.unwrap(direction, w, code, valid)
+    return valid, w, dbg, code, w2, unw
+
+
+@pytest.mark.parametrize("key,direction,codes", [("v", 0, 40), ("h", 1, 23)])
+def test_c1_crop_matches_reference_images(key, direction, codes):
+    d = load_c1_crop()
+    valid, w, dbg, code, w2, unw = _stage34(d[f"fringe_{key}"], d[f"gray_{key}"], d[f"inv_{key}"],
+                                            d[f"golden_wrapped_{key}"], direction)
+    assert valid.sum() > 50000
+    m = valid == 1
+    assert np.array_equal(dbg[m], d[f"golden_wrapped_{key}"][m])
+    img = o.unwrapped_image(unw, valid, codes)
+    # the crop's first/last column (vertical) or row (horizontal) is skipped by unwrap()
+    inner = m.copy()
+    if direction == 0:
+        inner[:, 0] = inner[:, -1] = False
+    else:
+        inner[0, :] = inner[-1, :] = False
+    assert np.array_equal(img[inner], d[f"golden_unwrapped_{key}"][inner])
+    assert (code[~m] == -1).all() and (code[m] >= 0).all()
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference tree not mounted")
+@pytest.mark.parametrize("name,M,direction,codes", [("Vertical", 6, 0, 40), ("Horizontal", 5, 1, 23)])
+def test_full_frame_matches_reference_images(name, M, direction, codes):
+    base = REF + "Captured_patterns/"
+    fr = np.stack([read_bmp8(f"{base}Fringe_patterns/{name}/Undistorted/Gray_captured_image_{i}.bmp") for i in range(3)])
+    g = np.stack([read_bmp8(f"{base}Coded_patterns/Gray_coded/{name}/Undistorted/Gray_captured_image_{i}.bmp") for i in range(M)])
+    gi = np.stack([read_bmp8(f"{base}Coded_patterns/Gray_coded/{name}/Undistorted/inverse_Gray_captured_image_{i}.bmp") for i in range(M)])
+    gw = read_bmp8(REF + f"Wrapped_phase_images/{name}/Wrapped_phase_image.bmp")
+    gu = read_bmp8(REF + f"Unwrapped_phase_images/Gray_coded/{name}/Unwrapped_phase_{name.lower()}.bmp")
+    valid, w, dbg, code, w2, unw = _stage34(fr, g, gi, gw, direction)
+    assert int(valid.sum()) == 358580
+    m = valid == 1
+    assert np.array_equal(dbg[m], gw[m])
+    img = o.unwrapped_image(unw, valid, codes)
+    assert np.array_equal(img[m], gu[m])
+    assert (gu[~m] == 0).all()
+
+
+def test_relative_geometry_kat():
+    c = load_calib_c1()
+    R, T = o.compose_relative(c["rc"], c["tc"], c["rp"], c["tp"])
+    assert np.abs(R - c["rel_R"].reshape(3, 3)).max() <= 1e-15
+    assert np.abs(T - c["rel_T"]).max() <= 1e-13
+
+
+def test_opencv_known_answers_bit_exact():
+    k = np.load(os.path.join(GOLDEN, "opencv_kat.npz"))
+    for dist, want in zip(k["und_dists"], k["und_out"]):
+        got = o.undistort_points(k["und_pts"], k["und_K"], dist)
+        assert np.array_equal(got, want)
+    for r, want in zip(k["rod_in"], k["rod_out"]):
+        assert np.array_equal(o.rodrigues(r), want)
+    c = load_calib_c1()
+    Ac = o.compute_A(c["Kc"], c["rc"], c["tc"])
+    Ap = o.compute_A(c["Kp"], c["rp"], c["tp"])
+    assert np.array_equal(Ac, k["A_cam"]) and np.array_equal(Ap, k["A_proj"])
+    for (uc, vc, up, vp), want in zip(k["tri_in"][:1024], k["tri_out"][:1024]):
+        assert np.array_equal(o.triangulate_point(Ac, Ap, uc, vc, up, vp), want)
+
+
+def test_undistort_lut_matches_pointwise():
+    c = load_calib_c1()
+    W, H = 64, 48
+    lut = o.undistort_lut(c["Kc"], c["dc"], W, H)
+    yy, xx = np.mgrid[0:H, 0:W]
+    pts = np.stack([xx.ravel(), yy.ravel()], 1).astype(np.float64)
+    n = o.undistort_points(pts, c["Kc"], c["dc"])
+    K = c["Kc"].reshape(3, 3)
+    u = (K[0, 0] * n[:, 0] + K[0, 1] * n[:, 1]) + K[0, 2]
+    v = (K[1, 0] * n[:, 0] + K[1, 1] * n[:, 1]) + K[1, 2]
+    assert np.array_equal(lut[0].ravel(), u) and np.array_equal(lut[1].ravel(), v)
+    # zero distortion: identity up to the (x-cx)*ifx*fx+cx round trip
+    lutp = o.undistort_lut(c["Kp"], c["dp"], W, H)
+    assert np.abs(lutp[0] - xx).max() < 1e-9 and np.abs(lutp[1] - yy).max() < 1e-9
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_mask_closed_form_equals_sequential(seed):
+    rng = np.random.default_rng(seed)
+    H, W = int(rng.integers(3, 40)), int(rng.integers(3, 40))
+    p = [0.5, 0.8, 0.95, 0.99, 0.2, 1.0][seed]
+    v0 = (rng.random((H, W)) < p).astype(np.int32)
+    assert np.array_equal(o.mask_recurrence(v0), o.mask_closed_form(v0))
+
+
+def test_mask_edge_shapes():
+    for H, W in ((1, 1), (1, 7), (7, 1), (2, 2), (3, 3), (2, 9)):
+        v0 = np.ones((H, W), np.int32)
+        v0.flat[0] = 0
+        assert np.array_equal(o.mask_recurrence(v0), o.mask_closed_form(v0))
+
+
+def test_quirks():
+    # tie in Gray threshold decodes as 1; bit 0 is the MSB; code is not range-limited
+    g = np.array([[[7]], [[9]], [[3]]], np.uint8)
+    gi = np.array([[[7]], [[9]], [[200]]], np.uint8)
+    code = o.decode_gray(g, gi, np.ones((1, 1), np.int32))
+    # G = 1,1,0 -> B = 1,0,0 -> code = 4
+    assert code[0, 0] == 4
+    assert o.decode_gray(g, gi, np.zeros((1, 1), np.int32))[0, 0] == -1
+    # unwrap: Pi is 22/7 and is stored back into the wrapped plane; border col skipped
+    w = np.full((3, 4), 0.5, np.float32)
+    c = np.full((3, 4), 3, np.int32)
+    w2, u = o.unwrap(0, w, c, np.ones((3, 4), np.int32))
+    want_w = np.float32(np.float64(np.float32(0.5)) + 22.0 / 7.0)
+    want_u = np.float32(np.float64(want_w) + 3 * 2.0 * 22.0 / 7.0)
+    assert (w2[:, 1:3] == want_w).all() and (u[:, 1:3] == want_u).all()
+    assert (w2[:, [0, 3]] == np.float32(0.5)).all() and (u[:, [0, 3]] == 0).all()
+    w2, u = o.unwrap(1, w, c, np.ones((3, 4), np.int32))
+    assert (u[1, :] == want_u).all() and (u[[0, 2], :] == 0).all()
+    # lrint half-to-even + bounds reject keeps the computed value
+    unw = np.array([[np.float32(0.5 * 44.0 / 7.0 / 1.0)]], np.float32)
+    cp, valid = o.compute_c_p_map(unw * 0 + np.float32(2.5 * (44.0 / 7.0)), unw * 0, np.ones((1, 1), np.int32),
+                                  np.ones((1, 1), np.int32), 1, 1, 10, 10)
+    assert cp[0, 0] in (2, 3) and valid[0, 0] == 1
+    cp, valid = o.compute_c_p_map(unw * 0 + 1000.0, unw * 0, np.ones((1, 1), np.int32),
+                                  np.ones((1, 1), np.int32), 4, 4, 10, 10)
+    assert valid[0, 0] == 0 and cp[0, 0] == int(np.rint(4 * (1000.0 / (44.0 / 7.0))))
