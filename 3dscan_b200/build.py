@@ -1,0 +1,88 @@
+"""Builds the in-tree native libraries of the package (sm_100a only, no JIT cache):
+
+  3dscan_b200/lib/libscan3d.so       CUDA kernels + the C ABI of include/scan3d.h
+  3dscan_b200/lib/libscan3d_host.so  C++ host side (image / calibration / PLY I/O, synthetic
+                                     pattern generator, reference-named stage functions)
+
+nvcc cross-compiles without a GPU, so this also runs in the CPU-only build container.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+HOST = os.path.join(HERE, "host")
+LIB = os.path.join(HERE, "lib")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "--use_fast_math=false" if False else "-DSCAN3D_BUILD",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-Wall", "-Xptxas", "-v",
+    "-cudart", "static", "-ccbin", "/usr/bin/g++",
+]
+CU_SOURCES = ["scan3d_api.cu", "scan3d_stage_kernels.cu", "scan3d_fused_kernel.cu"]
+HOST_SOURCES = ["scan3d_io.cpp", "scan3d_synth.cpp", "scan3d_stages.cpp"]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _deps(folder, extra=()):
+    out = [os.path.join(folder, f) for f in os.listdir(folder)
+           if f.endswith((".cu", ".cuh", ".h", ".cpp", ".hpp"))]
+    out += list(extra)
+    out.append(os.path.abspath(__file__))
+    return out
+
+
+def build_cuda(force=False, verbose=False):
+    os.makedirs(LIB, exist_ok=True)
+    so = os.path.join(LIB, "libscan3d.so")
+    hdr = os.path.join(HERE, "..", "include", "scan3d.h")
+    if not (force or _stale(so, _deps(CSRC, [hdr]))):
+        return so
+    objs = []
+    for src in CU_SOURCES:
+        obj = os.path.join(LIB, src.replace(".cu", ".o"))
+        cmd = [NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        with open(os.path.join(LIB, src + ".ptxas.log"), "w") as f:
+            f.write(r.stderr)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on " + src)
+        objs.append(obj)
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+           "-ccbin", "/usr/bin/g++", "-o", so] + objs
+    subprocess.check_call(cmd)
+    return so
+
+
+def build_host(force=False):
+    os.makedirs(LIB, exist_ok=True)
+    so = os.path.join(LIB, "libscan3d_host.so")
+    srcs = [os.path.join(HOST, s) for s in HOST_SOURCES if os.path.exists(os.path.join(HOST, s))]
+    if not srcs:
+        return None
+    hdr = os.path.join(HERE, "..", "include", "scan3d.h")
+    if not (force or _stale(so, _deps(HOST, [hdr]))):
+        return so
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-ffp-contract=off",
+           "-fopenmp", "-I", os.path.join(HERE, "..", "include"), "-o", so] + srcs + ["-ldl"]
+    subprocess.check_call(cmd)
+    return so
+
+
+def build_all(force=False, verbose=False):
+    return build_cuda(force, verbose), build_host(force)
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,127 @@
+// scan3d_internal.h -- context layout and kernel launcher declarations (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/scan3d.h"
+#include "scan3d_math.cuh"
+
+#define S3D_PLANE_MASK_H 10   // internal: valid_map_horizontal when the stage API is used
+
+struct scan3d_ctx {
+    scan3d_config cfg{};
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // calibration
+    bool has_calib = false;
+    scan3d_calib hcal{};
+    s3d::DeviceCalib dcal{};
+    double2* cam_lut = nullptr;    // [H][W] (u',v') of the local rows, only if the camera is distorted
+    double2* proj_lut = nullptr;   // [PH][PW], only if the projector is distorted
+    double* atan_tab = nullptr;    // hi[33] then lo[33]
+    double* nstep_w = nullptr;     // sin[64] then cos[64] (generic-N extension)
+
+    // planes (row-major [H][W])
+    float* wrapped[2] = {nullptr, nullptr};
+    float* unwrapped[2] = {nullptr, nullptr};
+    int16_t* code[2] = {nullptr, nullptr};
+    uint8_t* mask[2] = {nullptr, nullptr};
+    uint8_t* valid = nullptr;
+    int2* cpmap = nullptr;
+    double* xyz = nullptr;         // lazily allocated by scan3d_triangulate
+
+    // compacted points
+    float* pts = nullptr;          // [H*W][3]
+    uint32_t* pix = nullptr;       // [H*W]   (only with SCAN3D_FLAG_POINT_PIXELS / stage API)
+    uint8_t* rgb = nullptr;        // [H*W][3] (only when a texture is set)
+    uint8_t* texture = nullptr;    // [H][W][3] BGR
+    uint32_t* d_count = nullptr;   // [1]
+    uint32_t* block_counts = nullptr;  // stage-API compaction scratch
+    unsigned long long* tile_state = nullptr;  // fused kernel decoupled look-back
+    uint32_t epoch = 0;
+
+    // staging for the host-buffer entries
+    uint8_t* d_stack = nullptr;
+    uint8_t* d_roi = nullptr;
+
+    // stage bookkeeping
+    bool have_wrapped[2] = {false, false};
+    bool have_unwrapped[2] = {false, false};
+    bool have_cpmap = false, have_xyz = false, have_points = false;
+};
+
+namespace s3d {
+
+struct Shape {
+    int W, H;         // local frame
+    int row0, H_total;
+    int PW, PH;
+};
+
+inline Shape shape_of(const scan3d_config& c)
+{
+    Shape s;
+    s.W = c.W; s.H = c.H; s.row0 = c.row0;
+    s.H_total = c.H_total > 0 ? c.H_total : c.H;
+    s.PW = c.PW; s.PH = c.PH;
+    return s;
+}
+
+// ---- stage-wise kernels (any W, H) ----
+cudaError_t launch_mask(const Shape& s, const uint8_t* roi_full, uint8_t* mask, cudaStream_t st);
+cudaError_t launch_wrapped(const Shape& s, int N, const uint8_t* fringe, const uint8_t* roi_full,
+                           float* wrapped, const double* atan_tab, const double* nstep_w,
+                           bool libdevice, cudaStream_t st);
+cudaError_t launch_unwrap(const Shape& s, int dir, int M, const uint8_t* gray, const uint8_t* inv,
+                          float* wrapped, const uint8_t* mask, int16_t* code, float* unwrapped,
+                          cudaStream_t st);
+cudaError_t launch_cpmap(const Shape& s, int fw_v, int fw_h, const float* unw_v, const float* unw_h,
+                         const uint8_t* mask_v, const uint8_t* mask_h, int2* cpmap, uint8_t* valid,
+                         cudaStream_t st);
+cudaError_t launch_triangulate(const Shape& s, const DeviceCalib& cal, const double2* cam_lut,
+                               const double2* proj_lut, const int2* cpmap, const uint8_t* valid,
+                               double* xyz, cudaStream_t st);
+cudaError_t launch_undistort_lut(const double* K9_k5_dev_unused, const DeviceCalib& cal, bool projector,
+                                 int W, int H, int row0, double2* lut, cudaStream_t st);
+// 3 launches: count, scan, scatter.  pix / rgb / texture may be null.
+cudaError_t launch_compact(const Shape& s, const double* xyz, const uint8_t* valid,
+                           const uint8_t* texture, uint32_t* block_counts, float* pts, uint32_t* pix,
+                           uint8_t* rgb, uint32_t* d_count, cudaStream_t st, int* n_launches);
+
+// ---- fused single-pass kernel (W % 16 == 0, N in {3,4,5,8}) ----
+struct FusedArgs {
+    const uint8_t* stack;   // [NF][H][W]
+    const uint8_t* roi;     // [H_total][W]
+    float* unw_v; float* unw_h;
+    int16_t* code_v; int16_t* code_h;
+    uint8_t* valid;         // final valid (dirs==2) or mask (dirs==1)
+    int2* cpmap;
+    float* pts; uint32_t* pix; uint8_t* rgb; const uint8_t* texture;
+    uint32_t* d_count;
+    unsigned long long* tile_state;
+    const double2* cam_lut; const double2* proj_lut;
+    const double* atan_tab;
+    uint32_t epoch;
+    int W, H, row0, H_total, PW, PH;
+    int N, M_v, M_h, fw_v, fw_h;
+    int n_tiles, tiles_per_row;
+};
+bool fused_supported(const scan3d_config& c, int* stages_out, size_t* smem_out);
+int fused_num_tiles(const scan3d_config& c);
+cudaError_t launch_fused(const scan3d_config& c, const FusedArgs& a, const DeviceCalib& cal,
+                         int sm_count, cudaStream_t st);
+
+// ---- debug / self-test ----
+cudaError_t launch_debug_atan2(const double* y, const double* x, float* out, int n, int mode,
+                               const double* atan_tab, cudaStream_t st);
+
+void fill_atan_table(double* hi33_lo33);
+
+}  // namespace s3d

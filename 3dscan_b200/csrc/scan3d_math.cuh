@@ -1,0 +1,317 @@
+// scan3d_math.cuh -- per-pixel arithmetic of the 3dscan reconstruction path, written so that
+// every value that feeds an integer decision (fringe order, lrint correspondence, validity)
+// follows the reference's IEEE operation sequence exactly.  All double arithmetic that must
+// match goes through __dmul_rn/__dadd_rn/__dsub_rn/__ddiv_rn so nvcc never contracts it to FMA
+// (the reference was an SSE2 build: separate multiply and add roundings).
+//
+// Reference expressions (paths relative to the reference tree):
+//   3/wrapped_phase.cpp:171-175,195-198,217-220   wrapped phase
+//   4/phase_unwrap.cpp:183-193                    Gray threshold / Gray->binary / code
+//   4/phase_unwrap.cpp:290-291                    += Pi ; + code*2.0*Pi
+//   5/compute_correspondance.cpp:648,659,671      lrint correspondences + bounds
+//   7/triangulation.cpp:290-307,1152-1211         undistorted pixel, P, F, (P^T P)^-1 P^T F
+//   PROJECT_GLOBAL/global_cv.h:62                 #define Pi 22.0/7.0 (textual)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace s3d {
+
+// "Pi" as the reference's macro expands inside each expression.
+#define S3D_PI_REF (22.0 / 7.0)              // x += Pi            -> x + 22.0/7.0
+#define S3D_TWO_PI_REF (2.0 * 22.0 / 7.0)    // (2.0*Pi)           -> (2.0*22.0)/7.0
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// ---------------------------------------------------------------------------------------
+// atan2 evaluated in double and rounded to float: (float)atan2((double)t1,(double)t2) of
+// 3/wrapped_phase.cpp:175.  Accuracy ~1 double ulp, so the float result differs from a
+// correctly rounded libm only when the true value lies within ~2^-52 of a float rounding
+// boundary (probability ~1e-8 per pixel; tests count and bound these).
+//
+// Method: reduce to a = min/max in [0,1]; pick c = i/32 nearest to a (float estimate);
+// atan(a) = atan(c) + atan(t), t = (mn - c*mx)/(mx + c*mn), |t| <= 1/64, so a degree-9 odd
+// polynomial is exact to 2^-60; one division (reciprocal seed + Newton) instead of libm's two
+// range-reduction divisions and degree-19 polynomial.
+// ---------------------------------------------------------------------------------------
+struct AtanTable {
+    double hi[33];
+    double lo[33];
+};
+
+__device__ __forceinline__ double fast_div(double num, double den)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(r, fma(-den, r, 1.0), r);
+    r = fma(r, fma(-den, r, 1.0), r);
+    double t = num * r;
+    return fma(fma(-den, t, num), r, t);
+}
+
+// y, x: exact doubles; yf, xf: any float approximations of them (only select the table row).
+__device__ __forceinline__ float atan2_to_float(double y, double x, float yf, float xf,
+                                                const double* __restrict__ tab_hi,
+                                                const double* __restrict__ tab_lo)
+{
+    const double ax = fabs(x), ay = fabs(y);
+    const bool swap = ay > ax;
+    const double mx = swap ? ay : ax, mn = swap ? ax : ay;
+    const float axf = fabsf(xf), ayf = fabsf(yf);
+    const float mxf = fmaxf(axf, ayf), mnf = fminf(axf, ayf);
+    int i = __float2int_rn(__fdividef(mnf, mxf) * 32.0f);
+    i = mxf > 0.0f ? min(max(i, 0), 32) : 0;
+    const double c = (double)i * 0.03125;
+    const double num = fma(-c, mx, mn);
+    const double den = fma(c, mn, mx);
+    double res;
+    if (mx == 0.0) {
+        res = 0.0;
+    } else {
+        const double t = fast_div(num, den);
+        const double s = t * t;
+        double p = fma(s, 1.0 / 9.0, -1.0 / 7.0);
+        p = fma(s, p, 1.0 / 5.0);
+        p = fma(s, p, -1.0 / 3.0);
+        p = fma(t * s, p, t);
+        res = tab_hi[i] + (tab_lo[i] + p);
+    }
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+    const double pi_hi = 3.14159265358979311600e+00, pi_lo = 1.22464679914735317720e-16;
+    if (swap) res = (pio2_hi - res) + pio2_lo;
+    if (x < 0.0) res = (pi_hi - res) + pi_lo;
+    res = y < 0.0 ? -res : res;
+    return __double2float_rn(res);
+}
+
+// ---------------------------------------------------------------------------------------
+// wrapped phase (3/wrapped_phase.cpp:151-238).  I[k] are the pixel's N fringe samples.
+// USE_LIBDEVICE selects CUDA's own double atan2 (reference implementation for A/B tests).
+// ---------------------------------------------------------------------------------------
+template <bool USE_LIBDEVICE>
+__device__ __forceinline__ float phase_from_terms(double d1, double d2, float f1, float f2,
+                                                  const double* tab_hi, const double* tab_lo)
+{
+    if (USE_LIBDEVICE) return __double2float_rn(atan2(d1, d2));
+    return atan2_to_float(d1, d2, f1, f2, tab_hi, tab_lo);
+}
+
+template <int N, bool USE_LIBDEVICE>
+__device__ __forceinline__ float wrapped_phase(const int* I, const double* __restrict__ wsin,
+                                               const double* __restrict__ wcos, int n_runtime,
+                                               const double* tab_hi, const double* tab_lo)
+{
+    if (N == 3) {            // :171-175   t1 = I0 - I2 ; t2 = 2*I1 - I0 - I2   (exact)
+        const int t1 = I[0] - I[2], t2 = 2 * I[1] - I[0] - I[2];
+        return phase_from_terms<USE_LIBDEVICE>((double)t1, (double)t2, (float)t1, (float)t2, tab_hi, tab_lo);
+    } else if (N == 4) {     // :195-198   t1 = I3 - I1 ; t2 = I0 - I2
+        const int t1 = I[3] - I[1], t2 = I[0] - I[2];
+        return phase_from_terms<USE_LIBDEVICE>((double)t1, (double)t2, (float)t1, (float)t2, tab_hi, tab_lo);
+    } else if (N == 5) {     // :217-220   t1 = 2(I1 - I3) ; t2 = 2*I2 - I0 - I4 ; atan2f
+        const int t1 = 2 * (I[1] - I[3]), t2 = 2 * I[2] - I[0] - I[4];
+        return phase_from_terms<USE_LIBDEVICE>((double)t1, (double)t2, (float)t1, (float)t2, tab_hi, tab_lo);
+    } else if (N == 8) {     // extension: shifts k*pi/4, phase origin of the 4-step formula
+        const int a1 = I[6] - I[2], b1 = I[5] + I[7] - I[1] - I[3];
+        const int a2 = I[0] - I[4], b2 = I[1] + I[7] - I[3] - I[5];
+        const double r = 0.70710678118654752440;
+        const double d1 = dadd((double)a1, dmul((double)b1, r));
+        const double d2 = dadd((double)a2, dmul((double)b2, r));
+        const float f1 = fmaf((float)b1, 0.70710678f, (float)a1);
+        const float f2 = fmaf((float)b2, 0.70710678f, (float)a2);
+        return phase_from_terms<USE_LIBDEVICE>(d1, d2, f1, f2, tab_hi, tab_lo);
+    } else {                 // extension: generic N, sequential double sums (k ascending)
+        double S = 0.0, C = 0.0;
+        for (int k = 0; k < n_runtime; k++) {
+            const double v = (double)I[k];
+            S = dadd(S, dmul(v, wsin[k]));
+            C = dadd(C, dmul(v, wcos[k]));
+        }
+        const double d1 = dsub(0.0, S);
+        return phase_from_terms<USE_LIBDEVICE>(d1, C, (float)d1, (float)C, tab_hi, tab_lo);
+    }
+}
+
+// 4/phase_unwrap.cpp:290 :  wrapped += Pi          (float <- double sum)
+__device__ __forceinline__ float add_pi(float wrapped)
+{
+    return __double2float_rn(dadd((double)wrapped, S3D_PI_REF));
+}
+// 4/phase_unwrap.cpp:291 :  unwrapped = wrapped + code*2.0*Pi   == w + ((code*2.0)*22.0)/7.0
+__device__ __forceinline__ float unwrap_abs(float wrapped_plus_pi, int code)
+{
+    const double k = ddiv(dmul(dmul((double)code, 2.0), 22.0), 7.0);
+    return __double2float_rn(dadd((double)wrapped_plus_pi, k));
+}
+// 5/compute_correspondance.cpp:648 : lrint(fw * (Phi / (2.0*Pi))), round-half-even; FE_INVALID
+// (NaN/inf/out of range) rejects the pixel.  Returns false on FE_INVALID.
+__device__ __forceinline__ bool correspond(float phi_abs, int fw, long long* out)
+{
+    const double v = dmul((double)fw, ddiv((double)phi_abs, S3D_TWO_PI_REF));
+    if (!(v == v) || v >= 9223372036854775808.0 || v < -9223372036854775808.0) return false;
+    *out = __double2ll_rn(v);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// calibration algebra on the device
+// ---------------------------------------------------------------------------------------
+struct DeviceCalib {
+    double Ac[12];      // K_cam * [R|t]   (3x4 row-major)   7/triangulation.cpp:1090-1101
+    double Ap[12];      // K_proj * [R|t]                     :1104-1116
+    double Kc[9], dc[5], Kp[9], dp[5];
+    int cam_distorted;  // any camera distortion coefficient non-zero
+    int proj_distorted; // any projector distortion coefficient non-zero
+};
+
+// One pixel of cvUndistortPoints (5 fixed iterations, 5-coefficient model) followed by
+// K*[xn;yn;1] and the divide by the third row (7/triangulation.cpp:290-307 / :363-378).
+__device__ __forceinline__ void undistorted_pixel(const double* __restrict__ K,
+                                                  const double* __restrict__ k, double u, double v,
+                                                  double* ou, double* ov)
+{
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    const double ifx = ddiv(1.0, fx), ify = ddiv(1.0, fy);
+    double x, y, x0, y0;
+    x0 = x = dmul(dsub(u, cx), ifx);
+    y0 = y = dmul(dsub(v, cy), ify);
+#pragma unroll 1
+    for (int j = 0; j < 5; j++) {
+        const double r2 = dadd(dmul(x, x), dmul(y, y));
+        const double poly = dmul(dadd(dmul(dadd(dmul(k[4], r2), k[1]), r2), k[0]), r2);
+        const double icdist = ddiv(1.0, dadd(1.0, poly));
+        // deltaX = 2*k[2]*x*y + k[3]*(r2 + 2*x*x)
+        const double dX = dadd(dmul(dmul(dmul(2.0, k[2]), x), y), dmul(k[3], dadd(r2, dmul(dmul(2.0, x), x))));
+        // deltaY = k[2]*(r2 + 2*y*y) + 2*k[3]*x*y
+        const double dY = dadd(dmul(k[2], dadd(r2, dmul(dmul(2.0, y), y))), dmul(dmul(dmul(2.0, k[3]), x), y));
+        x = dmul(dsub(x0, dX), icdist);
+        y = dmul(dsub(y0, dY), icdist);
+    }
+    // cvMatMul(K, [x;y;1]) with sums k ascending from 0, then rows 0,1 divided by row 2
+    const double m0 = dadd(dadd(dadd(0.0, dmul(K[0], x)), dmul(K[1], y)), dmul(K[2], 1.0));
+    const double m1 = dadd(dadd(dadd(0.0, dmul(K[3], x)), dmul(K[4], y)), dmul(K[5], 1.0));
+    const double m2 = dadd(dadd(dadd(0.0, dmul(K[6], x)), dmul(K[7], y)), dmul(K[8], 1.0));
+    *ou = ddiv(m0, m2);
+    *ov = ddiv(m1, m2);
+}
+
+// Zero distortion: the 5 iterations are the exact identity (icdist == 1, deltas == 0), so only
+// the normalise / re-project round trip remains.  Bit-identical to undistorted_pixel() then.
+__device__ __forceinline__ void undistorted_pixel_nodist(const double* __restrict__ K, double u,
+                                                         double v, double* ou, double* ov)
+{
+    const double ifx = ddiv(1.0, K[0]), ify = ddiv(1.0, K[4]);
+    const double x = dmul(dsub(u, K[2]), ifx);
+    const double y = dmul(dsub(v, K[5]), ify);
+    const double m0 = dadd(dadd(dadd(0.0, dmul(K[0], x)), dmul(K[1], y)), dmul(K[2], 1.0));
+    const double m1 = dadd(dadd(dadd(0.0, dmul(K[3], x)), dmul(K[4], y)), dmul(K[5], 1.0));
+    const double m2 = dadd(dadd(dadd(0.0, dmul(K[6], x)), dmul(K[7], y)), dmul(K[8], 1.0));
+    *ou = ddiv(m0, m2);
+    *ov = ddiv(m1, m2);
+}
+
+// sum_k a_k*b_k, k ascending, accumulator starts at 0 (OpenCV GEMM order)
+__device__ __forceinline__ double dot4(double a0, double b0, double a1, double b1, double a2,
+                                       double b2, double a3, double b3)
+{
+    return dadd(dadd(dadd(dmul(a0, b0), dmul(a1, b1)), dmul(a2, b2)), dmul(a3, b3));
+}
+__device__ __forceinline__ double dot3(double a0, double b0, double a1, double b1, double a2,
+                                       double b2)
+{
+    return dadd(dadd(dmul(a0, b0), dmul(a1, b1)), dmul(a2, b2));
+}
+
+// compute_P / compute_F / compute_X_Y_Z (7/triangulation.cpp:1134-1218) for one correspondence:
+// V = ((P^T P)^-1 P^T) F with cvInvert's closed-form 3x3 and the reference's product order.
+__device__ __forceinline__ void triangulate_point(const double* __restrict__ Ac,
+                                                  const double* __restrict__ Ap, double uc,
+                                                  double vc, double up, double vp, double* X)
+{
+    double P[4][3], F[4];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        P[0][j] = dsub(Ac[0 * 4 + j], dmul(uc, Ac[2 * 4 + j]));
+        P[1][j] = dsub(Ac[1 * 4 + j], dmul(vc, Ac[2 * 4 + j]));
+        P[2][j] = dsub(Ap[0 * 4 + j], dmul(up, Ap[2 * 4 + j]));
+        P[3][j] = dsub(Ap[1 * 4 + j], dmul(vp, Ap[2 * 4 + j]));
+    }
+    F[0] = dsub(dmul(Ac[11], uc), Ac[3]);
+    F[1] = dsub(dmul(Ac[11], vc), Ac[7]);
+    F[2] = dsub(dmul(Ap[11], up), Ap[3]);
+    F[3] = dsub(dmul(Ap[11], vp), Ap[7]);
+    // S = P^T P (symmetric bit-for-bit: products commute, same summation order)
+    const double S00 = dot4(P[0][0], P[0][0], P[1][0], P[1][0], P[2][0], P[2][0], P[3][0], P[3][0]);
+    const double S01 = dot4(P[0][0], P[0][1], P[1][0], P[1][1], P[2][0], P[2][1], P[3][0], P[3][1]);
+    const double S02 = dot4(P[0][0], P[0][2], P[1][0], P[1][2], P[2][0], P[2][2], P[3][0], P[3][2]);
+    const double S11 = dot4(P[0][1], P[0][1], P[1][1], P[1][1], P[2][1], P[2][1], P[3][1], P[3][1]);
+    const double S12 = dot4(P[0][1], P[0][2], P[1][1], P[1][2], P[2][1], P[2][2], P[3][1], P[3][2]);
+    const double S22 = dot4(P[0][2], P[0][2], P[1][2], P[1][2], P[2][2], P[2][2], P[3][2], P[3][2]);
+    const double S10 = S01, S20 = S02, S21 = S12;
+    // cvInvert, n == 3, CV_64F: det3 then cofactors times 1/det
+    const double c00 = dsub(dmul(S11, S22), dmul(S12, S21));
+    const double c01 = dsub(dmul(S10, S22), dmul(S12, S20));
+    const double c02 = dsub(dmul(S10, S21), dmul(S11, S20));
+    double d = dadd(dsub(dmul(S00, c00), dmul(S01, c01)), dmul(S02, c02));
+    double T[3][3];
+    if (d != 0.0) {
+        d = ddiv(1.0, d);
+        T[0][0] = dmul(c00, d);
+        T[0][1] = dmul(dsub(dmul(S02, S21), dmul(S01, S22)), d);
+        T[0][2] = dmul(dsub(dmul(S01, S12), dmul(S02, S11)), d);
+        T[1][0] = dmul(dsub(dmul(S12, S20), dmul(S10, S22)), d);
+        T[1][1] = dmul(dsub(dmul(S00, S22), dmul(S02, S20)), d);
+        T[1][2] = dmul(dsub(dmul(S02, S10), dmul(S00, S12)), d);
+        T[2][0] = dmul(dsub(dmul(S10, S21), dmul(S11, S20)), d);
+        T[2][1] = dmul(dsub(dmul(S01, S20), dmul(S00, S21)), d);
+        T[2][2] = dmul(dsub(dmul(S00, S11), dmul(S01, S10)), d);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) T[i][j] = 0.0;
+    }
+    // I2 = T * P^T (3x4), V = I2 * F
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double I2[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) I2[j] = dot3(T[i][0], P[j][0], T[i][1], P[j][1], T[i][2], P[j][2]);
+        X[i] = dot4(I2[0], F[0], I2[1], F[1], I2[2], F[2], I2[3], F[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// closed form of the raster mask recurrence (3/wrapped_phase.cpp:266-279); see DESIGN.md.
+// inv(x,y) must return true for a pixel whose ROI flag != 1; coordinates are GLOBAL.
+// ---------------------------------------------------------------------------------------
+template <class InvFn>
+__device__ __forceinline__ bool mask_trigger(int x, int y, int W, int H, InvFn inv)
+{
+    auto border = [&](int qx, int qy) { return qx == 0 || qy == 0 || qx == W - 1 || qy == H - 1; };
+    // LATE = {R, DL, D, DR}; EARLY = {UL, U, UR, L}
+    auto late_any = [&](int qx, int qy) {
+        return inv(qx + 1, qy) || inv(qx - 1, qy + 1) || inv(qx, qy + 1) || inv(qx + 1, qy + 1);
+    };
+    if (late_any(x, y)) return true;
+    const int ex[4] = {-1, 0, 1, -1}, ey[4] = {-1, -1, -1, 0};
+    bool trig = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int qx = x + ex[k], qy = y + ey[k];
+        if (!inv(qx, qy)) continue;
+        if (border(qx, qy)) { trig = true; continue; }
+        bool E = late_any(qx, qy);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int rx = qx + ex[j], ry = qy + ey[j];
+            E = E || (border(rx, ry) && inv(rx, ry));
+        }
+        trig = trig || !E;
+    }
+    return trig;
+}
+
+}  // namespace s3d

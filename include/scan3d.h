@@ -1,0 +1,179 @@
+/*
+ * scan3d.h -- C ABI of the B200-native reconstruction hot path of pranavkantgaur/3dscan.
+ *
+ * This is the drop-in boundary: one entry point per stage function that the reference's
+ * main() calls between capture and PLY (PROJECT_GLOBAL/intermodule_dependencies.h:10-25,
+ * called at M_tech_project_console/m_tech_project_console.cpp:372-401), plus one fused entry
+ * that runs the whole path in a single pass over the captured pattern stack.
+ *
+ *   reference (C++ linkage, globals)                this library (extern "C", explicit ctx)
+ *   ---------------------------------------------   ------------------------------------------
+ *   void compute_wrapped_phase(int pattern_type)    scan3d_compute_wrapped_phase[_dev]
+ *        3/wrapped_phase.cpp:402
+ *   void unwrap_phase(int pattern_type)             scan3d_unwrap_phase[_dev]
+ *        4/phase_unwrap.cpp:367
+ *   void compute_c_p_map()                          scan3d_compute_c_p_map
+ *        5/compute_correspondance.cpp:630
+ *   void triangulate()                              scan3d_triangulate
+ *        7/triangulation.cpp:1444
+ *   void save_point_cloud(unsigned)                 scan3d_compact_points + scan3d_write_ply
+ *        8/save_point_cloud.cpp:26
+ *   load_matrices() / read_parameters()             scan3d_set_calibration
+ *        6/system_calibration.cpp:1526, 7/triangulation.cpp:149
+ *   (all five calls above, one scan)                scan3d_reconstruct[_dev]
+ *
+ * Data contract
+ *   - Every image-sized plane is ROW-MAJOR [H][W] (the reference's globals are [col][row];
+ *     INTEGRATION.md shows the transposing shim).  pattern_type / dir: 0 = vertical stripes
+ *     (encodes projector x), 1 = horizontal (encodes projector y).
+ *   - The reference passes data between stages through extern globals
+ *     (PROJECT_GLOBAL/common_variables.h:12-62); here the ctx owns the same planes in HBM and
+ *     the getters below copy them out.  The caller owns all host buffers.
+ *   - Pointers named *_host are host memory, *_dev are device memory on the ctx's GPU.
+ *   - All work is ordered on the ctx's stream; entries taking host buffers synchronise before
+ *     they return, *_dev entries are asynchronous (use scan3d_sync).
+ *   - Per-pixel failures are expressed only through the valid planes, as in the reference.
+ *   - Return value: 0 on success, negative scan3d_status otherwise; scan3d_last_error() gives
+ *     a message.  There is no CPU fallback: without a usable CUDA device every compute entry
+ *     fails with SCAN3D_ERR_CUDA.
+ */
+#ifndef SCAN3D_H
+#define SCAN3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCAN3D_VERSION 100
+
+typedef struct scan3d_ctx scan3d_ctx;
+
+typedef enum {
+    SCAN3D_OK = 0,
+    SCAN3D_ERR_CONFIG = -1,      /* bad sizes / unsupported N, M */
+    SCAN3D_ERR_CUDA = -2,        /* CUDA runtime error (message has the detail) */
+    SCAN3D_ERR_STATE = -3,       /* stage called out of order / calibration missing */
+    SCAN3D_ERR_ARG = -4,         /* null pointer, bad enum */
+    SCAN3D_ERR_IO = -5           /* file could not be written */
+} scan3d_status;
+
+/* Compile-time sizes and initialised globals of the reference
+ * (PROJECT_GLOBAL/global_cv.h:49-53, common_variables.h:6-10,23-24) as a runtime struct. */
+typedef struct {
+    int32_t W, H;          /* camera frame held by this ctx (H = local rows when row-sharded) */
+    int32_t PW, PH;        /* projector resolution */
+    int32_t N;             /* number_of_patterns_fringe: 3,4,5 (reference) or 8 / 6..16 (extension) */
+    int32_t M_v, M_h;      /* number_of_patterns_binary_{vertical,horizontal}: 1..15 */
+    int32_t fw_v, fw_h;    /* fringe_width_pixels_{vertical,horizontal} */
+    int32_t dirs;          /* 1 = vertical only (stages 3+4), 2 = both directions (full path) */
+    int32_t row0;          /* row-sharding: global row of local row 0 (0 when not sharded) */
+    int32_t H_total;       /* row-sharding: full frame height (0 or H when not sharded) */
+    uint32_t flags;        /* SCAN3D_FLAG_* */
+} scan3d_config;
+
+#define SCAN3D_FLAG_NONE 0u
+#define SCAN3D_FLAG_POINT_PIXELS 1u  /* also emit pix[count] = global row*W+col of every point */
+
+/* The 8 matrices load_matrices() reads (6/system_calibration.cpp:1526-1554): intrinsics (3x3
+ * row-major), distortion (k1,k2,p1,p2,k3), world->device rotation vectors and translations. */
+typedef struct {
+    double Kc[9], dc[5], Kp[9], dp[5];
+    double rc[3], tc[3], rp[3], tp[3];
+} scan3d_calib;
+
+typedef enum {
+    SCAN3D_PLANE_WRAPPED_V = 0,   /* f32  wrapped_phi_vertical   (stage entries only)        */
+    SCAN3D_PLANE_WRAPPED_H = 1,   /* f32  wrapped_phi_horizontal (stage entries only)        */
+    SCAN3D_PLANE_UNWRAPPED_V = 2, /* f32  unwrapped_phi_vertical                              */
+    SCAN3D_PLANE_UNWRAPPED_H = 3, /* f32  unwrapped_phi_horizontal                            */
+    SCAN3D_PLANE_CODE_V = 4,      /* i16  code_vertical (-1 = invalid)                        */
+    SCAN3D_PLANE_CODE_H = 5,      /* i16  code_horizontal                                     */
+    SCAN3D_PLANE_MASK = 6,        /* u8   valid_map_vertical == valid_map_horizontal          */
+    SCAN3D_PLANE_VALID = 7,       /* u8   valid_map (merged, after the projector-bounds test) */
+    SCAN3D_PLANE_CPMAP = 8,       /* i32[2] c_p_map[row*W+col] = (proj x, proj y)             */
+    SCAN3D_PLANE_XYZ = 9,         /* f64[3] intersection_points (scan3d_triangulate only)     */
+    SCAN3D_PLANE_COUNT_
+} scan3d_plane;
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+int scan3d_version(void);
+int scan3d_create(const scan3d_config *cfg, int device, scan3d_ctx **out);
+void scan3d_destroy(scan3d_ctx *ctx);
+const char *scan3d_last_error(const scan3d_ctx *ctx); /* ctx may be NULL: last create error */
+/* Use an existing cudaStream_t (e.g. the caller's framework stream); NULL = ctx-owned stream. */
+int scan3d_set_stream(scan3d_ctx *ctx, void *cuda_stream);
+int scan3d_sync(scan3d_ctx *ctx);
+
+/* load_matrices / read_parameters / compute_A / assign_3d_coordinates: uploads the calibration,
+ * builds A = K[R|t] for both devices and the undistorted-pixel tables on the GPU (once per
+ * calibration instead of once per triangulate() call, 7/triangulation.cpp:228-439,1061-1126). */
+int scan3d_set_calibration(scan3d_ctx *ctx, const scan3d_calib *cal);
+/* 3x4 row-major A matrices computed above (for diffing against the reference's A_cam/A_proj). */
+int scan3d_get_projection_matrices(scan3d_ctx *ctx, double A_cam[12], double A_proj[12]);
+
+/* Optional texture ("Point_cloud/texture.bmp", 8/save_point_cloud.cpp:59-66): BGR u8 [H][W][3].
+ * NULL clears it (points then carry rgb = 0). */
+int scan3d_set_texture(scan3d_ctx *ctx, const uint8_t *bgr_host);
+
+/* ---- stage entries (mirror the reference's call sequence) ------------------------------ */
+/* compute_wrapped_phase(pattern_type): fringe = [N][H][W] u8 captured phase-shift frames,
+ * roi = selected_region as u8 [H_total][W] (non-zero = selected; row-sharded ctxs pass the FULL
+ * frame's ROI).  Produces WRAPPED_{V,H} and MASK (ROI after the raster mask recurrence). */
+int scan3d_compute_wrapped_phase(scan3d_ctx *ctx, int dir, const uint8_t *fringe_host,
+                                 const uint8_t *roi_host);
+int scan3d_compute_wrapped_phase_dev(scan3d_ctx *ctx, int dir, const uint8_t *fringe_dev,
+                                     const uint8_t *roi_dev);
+/* unwrap_phase(pattern_type): gray / inv = [M][H][W] u8 captured Gray-code frames and their
+ * inverses.  Produces CODE_{V,H}, UNWRAPPED_{V,H}; adds Pi to WRAPPED_{V,H} in place. */
+int scan3d_unwrap_phase(scan3d_ctx *ctx, int dir, const uint8_t *gray_host,
+                        const uint8_t *inv_host);
+int scan3d_unwrap_phase_dev(scan3d_ctx *ctx, int dir, const uint8_t *gray_dev,
+                            const uint8_t *inv_dev);
+/* compute_c_p_map(): produces CPMAP and VALID from UNWRAPPED_{V,H} and MASK. */
+int scan3d_compute_c_p_map(scan3d_ctx *ctx);
+/* triangulate(): produces XYZ (dense f64, allocated on first use) from CPMAP and VALID. */
+int scan3d_triangulate(scan3d_ctx *ctx);
+/* save_point_cloud()'s count + raster-order gather: compacts XYZ/VALID (+texture) into the
+ * ctx's point buffers; *count_out receives the number of points. */
+int scan3d_compact_points(scan3d_ctx *ctx, int64_t *count_out);
+
+/* ---- fused entry: the whole path in one pass ------------------------------------------- */
+/* stack = the captured pattern stack, planes [H][W] u8 in this order:
+ *   fringe_v[N], gray_v[M_v], inv_v[M_v]   (and, when dirs == 2)   fringe_h[N], gray_h[M_h], inv_h[M_h]
+ * Produces UNWRAPPED_*, CODE_*, VALID (MASK when dirs == 1), CPMAP and the compacted points. */
+int64_t scan3d_stack_bytes(const scan3d_config *cfg);
+int scan3d_reconstruct(scan3d_ctx *ctx, const uint8_t *stack_host, const uint8_t *roi_host,
+                       int64_t *count_out);
+int scan3d_reconstruct_dev(scan3d_ctx *ctx, const uint8_t *stack_dev, const uint8_t *roi_dev);
+
+/* ---- results -------------------------------------------------------------------------- */
+int64_t scan3d_plane_bytes(const scan3d_ctx *ctx, int plane);
+int scan3d_get_plane(scan3d_ctx *ctx, int plane, void *dst_host);     /* synchronous D2H */
+void *scan3d_device_plane(scan3d_ctx *ctx, int plane);                /* NULL if not allocated */
+/* code plane widened to the reference's int (common_variables.h:12-13) */
+int scan3d_get_code_i32(scan3d_ctx *ctx, int dir, int32_t *dst_host);
+/* c_p_map widened to the reference's long int [W*H][2] (common_variables.h:15) */
+int scan3d_get_cpmap_i64(scan3d_ctx *ctx, int64_t *dst_host);
+
+int scan3d_point_count(scan3d_ctx *ctx, int64_t *count_out);          /* syncs the stream */
+/* Raster-ordered points: xyz f32[count][3], pix u32[count] (global row*W+col), rgb u8[count][3].
+ * Any destination may be NULL.  max_points bounds the copy. */
+int scan3d_get_points(scan3d_ctx *ctx, float *xyz_host, uint32_t *pix_host, uint8_t *rgb_host,
+                      int64_t max_points);
+void *scan3d_device_points(scan3d_ctx *ctx);        /* f32[capacity][3] */
+void *scan3d_device_point_pixels(scan3d_ctx *ctx);  /* u32[capacity]    */
+void *scan3d_device_point_count(scan3d_ctx *ctx);   /* u32[1] on device (for collectives) */
+
+/* save_point_cloud()'s pcl::io::savePLYFile equivalent: "x y z red green blue" vertices,
+ * ASCII (binary = 0, PCL's default) or binary_little_endian. */
+int scan3d_write_ply(scan3d_ctx *ctx, const char *path, int binary);
+
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+int64_t scan3d_launch_count(const scan3d_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCAN3D_H */

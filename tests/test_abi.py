@@ -1,0 +1,135 @@
+"""CPU-side checks: the C-ABI libraries load without a GPU and export every symbol that
+include/*.h declares; host-side logic (file formats, pattern conventions, synthetic scenes)."""
+import ctypes as C
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_ffi as o
+from helpers import GOLDEN, REF, have_reference, load_calib_c1
+
+s3 = importlib.import_module("3dscan_b200")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(scan3d_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    L = s3.cuda_lib()
+    names = _declared("scan3d.h")
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.scan3d_version() == 100
+
+
+def test_host_library_exports_every_declared_symbol():
+    L = s3.host_lib()
+    for n in _declared("scan3d_host.h"):
+        assert hasattr(L, n), n
+
+
+def test_config_validation_without_gpu():
+    L = s3.cuda_lib()
+    h = C.c_void_p()
+    bad = s3.make_config(0, 10)
+    assert L.scan3d_create(C.byref(bad), 0, C.byref(h)) == -1
+    assert b"W/H" in L.scan3d_last_error(None)
+    bad = s3.make_config(64, 64, 64, 64, N=2, M_v=4, M_h=4)
+    assert L.scan3d_create(C.byref(bad), 0, C.byref(h)) == -1
+    cfg = s3.make_config(4096, 3000, 4096, 3000, 8, 10, 10, 4, 4, 2)
+    assert L.scan3d_stack_bytes(C.byref(cfg)) == 56 * 4096 * 3000
+
+
+def test_no_cpu_fallback_without_gpu():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    with pytest.raises(s3.Scan3DError):
+        s3.Scan3D(s3.make_config(64, 64, 64, 64, 3, 4, 4, 4, 4, 2), 0)
+
+
+def test_pattern_rows_match_reference_generated_patterns():
+    k = np.load(os.path.join(GOLDEN, "pattern_kat.npz"))
+    for i in range(3):
+        assert np.array_equal(s3.synth_pattern_row(0, 3, 32, i, 1280), k["fringe_v_row0"][i])
+        assert np.array_equal(s3.synth_pattern_row(0, 3, 32, i, 720), k["fringe_h_col0"][i])
+    for i in range(6):
+        assert np.array_equal(s3.synth_pattern_row(1, 6, 32, i, 1280), k["gray_v_row0"][i])
+        assert np.array_equal(s3.synth_pattern_row(2, 6, 32, i, 1280), k["inv_v_row0"][i])
+    for i in range(5):
+        assert np.array_equal(s3.synth_pattern_row(1, 5, 32, i, 720), k["gray_h_col0"][i])
+        assert np.array_equal(s3.synth_pattern_row(2, 5, 32, i, 720), k["inv_h_col0"][i])
+
+
+def _cal():
+    c = load_calib_c1()
+    args = [c[k] for k in ("Kc", "dc", "Kp", "dp", "rc", "tc", "rp", "tp")]
+    return s3.make_calib(*args), o.make_calib(*args)
+
+
+def test_synthetic_scene_reconstructs_through_the_oracle():
+    """noise-free stack -> oracle -> the scene comes back (the generator and the decode agree)."""
+    cal, ocal = _cal()
+    cfg = s3.make_config(400, 300, 320, 180, 4, 6, 5, 8, 8, 2)
+    cal2 = s3.scale_calibration(cal, 0.25, 0.25)
+    c2 = s3.calib_to_dict(cal2)
+    ocal2 = o.make_calib(*[c2[k] for k in ("Kc", "dc", "Kp", "dp", "rc", "tc", "rp", "tp")])
+    p = s3.default_synth_params(noise_sigma=0.0, ambient_max=0.0, albedo_lo=1.0)
+    stack, roi, truth = s3.synth_stack(cfg, cal2, p, want_truth=True)
+    d = s3.split_stack(cfg, stack)
+    r = o.reconstruct({k: getattr(cfg, k) for k in ("W", "H", "PW", "PH", "N", "M_v", "M_h", "fw_v", "fw_h", "dirs")},
+                      ocal2, d["fringe_v"], d["gray_v"], d["inv_v"], d["fringe_h"], d["gray_h"], d["inv_h"], roi)
+    assert r.count > 20000
+    err = np.linalg.norm(r.pts - truth.reshape(-1, 3)[r.pix], axis=1)
+    assert np.median(err) < 0.5          # mm; the scene is ~100 mm from the camera
+    assert (err < 2.0).mean() > 0.97
+
+
+def test_synth_is_deterministic_and_row_shardable():
+    cal, _ = _cal()
+    full = s3.make_config(160, 48, 128, 96, 3, 5, 5, 4, 4, 2)
+    a, roi = s3.synth_stack(full, cal)
+    b, _ = s3.synth_stack(full, cal)
+    assert np.array_equal(a, b)
+    part = s3.make_config(160, 20, 128, 96, 3, 5, 5, 4, 4, 2, row0=10, H_total=48)
+    c, roi2 = s3.synth_stack(part, cal)
+    assert np.array_equal(c, a[:, 10:30]) and np.array_equal(roi, roi2)
+    assert 0.6 < roi.mean() < 0.8
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference tree not mounted")
+def test_reference_tree_loaders():
+    cal = s3.load_calibration(REF)
+    c = load_calib_c1()
+    for k in ("Kc", "dc", "Kp", "dp", "rc", "tc", "rp", "tp"):
+        assert np.array_equal(np.array(list(getattr(cal, k))), c[k])
+    cfg = s3.make_config(1600, 1200, 1280, 720, 3, 6, 5, 32, 32, 2)
+    stack = s3.load_captured_set(REF, cfg)
+    assert stack.shape == (28, 1200, 1600)
+    from helpers import read_bmp8
+    want = read_bmp8(REF + "Captured_patterns/Coded_patterns/Gray_coded/Horizontal/Undistorted/inverse_Gray_captured_image_4.bmp")
+    assert np.array_equal(stack[-1], want)
+
+
+def test_bmp_and_ply_roundtrip(tmp_path):
+    img = np.random.default_rng(1).integers(0, 256, (37, 53), dtype=np.uint8)
+    p = str(tmp_path / "a.bmp")
+    assert s3.host_lib().scan3d_write_bmp8(p.encode(), 53, 37, img.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(s3.read_bmp8(p), img)
+    xyz = np.random.default_rng(2).normal(size=(11, 3)).astype(np.float32)
+    q = str(tmp_path / "a.ply")
+    assert s3.host_lib().scan3d_write_ply_points(q.encode(), xyz.ctypes.data_as(C.c_void_p), None, 11, 0) == 0
+    body = open(q).read().split("end_header\n")[1]
+    got = np.loadtxt(body.splitlines())[:, :3].astype(np.float32)
+    assert np.array_equal(got, xyz)

@@ -1,0 +1,268 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded inputs.  Bar (BASELINE.json north_star): Gray codes / fringe orders / validity
+bit-exact; unwrapped phase within 1e-4 rad; 3-D points within 1e-5 relative."""
+import numpy as np
+import pytest
+
+import oracle_ffi as o
+from gpu_common import calibs, compare, run_oracle, s3
+from helpers import load_c1_crop
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(cfg, cal):
+    return s3.Scan3D(cfg, 0, cal)
+
+
+# ---------------------------------------------------------------------------- atan2 numerics
+def test_wrapped_phase_exhaustive_3step():
+    """Every (I0,I1,I2) triple: 2^24 pixels through scan3d_compute_wrapped_phase vs libm."""
+    v = np.arange(256, dtype=np.uint8)
+    fr = np.empty((3, 4096, 4096), np.uint8)
+    fr[0] = np.repeat(v, 16)[:, None]                      # I0 = row // 16
+    fr[1] = (np.arange(4096) % 256).astype(np.uint8)[None, :]   # I1 = col % 256
+    fr[2] = ((np.arange(4096)[:, None] % 16) * 16 + (np.arange(4096)[None, :] // 256)).astype(np.uint8)
+    roi = np.ones((4096, 4096), np.uint8)
+    cfg = s3.make_config(4096, 4096, N=3, M_v=1, dirs=1)
+    ctx = s3.Scan3D(cfg, 0)
+    ctx.compute_wrapped_phase(0, fr, roi)
+    got = ctx.plane(s3.PLANE_WRAPPED_V)
+    want, _ = o.wrapped_phase(fr, np.ones((4096, 4096), np.int32), threads=0, want_dbg=False)
+    bad = int((got.view(np.uint32) != want.view(np.uint32)).sum())
+    print("3-step exhaustive: non-identical wrapped-phase floats:", bad, "of", got.size)
+    assert bad == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("N", [4, 5, 8, 6])
+def test_wrapped_phase_random(N):
+    rng = np.random.default_rng(N)
+    H, W = 2048, 2048
+    fr = rng.integers(0, 256, (N, H, W), dtype=np.uint8)
+    roi = np.ones((H, W), np.uint8)
+    cfg = s3.make_config(W, H, N=N, M_v=1, dirs=1)
+    ctx = s3.Scan3D(cfg, 0)
+    ctx.compute_wrapped_phase(0, fr, roi)
+    got = ctx.plane(s3.PLANE_WRAPPED_V)
+    want, _ = o.wrapped_phase(fr, np.ones((H, W), np.int32), threads=0, want_dbg=False)
+    bad = int((got.view(np.uint32) != want.view(np.uint32)).sum())
+    print(f"N={N}: non-identical wrapped-phase floats: {bad} of {got.size}")
+    assert np.abs(got.astype(np.float64) - want).max() <= 4e-7
+    if N != 5:       # N=5: the reference calls float atan2f (glibc flt-32), see DESIGN.md
+        assert bad <= 2
+    ctx.close()
+
+
+def test_debug_atan2_modes_agree_with_libm():
+    rng = np.random.default_rng(7)
+    y = rng.integers(-510, 511, 1 << 20).astype(np.float64)
+    x = rng.integers(-1020, 1021, 1 << 20).astype(np.float64)
+    y[:8] = [0, 0, 0, 1, -1, 5, -5, 0]
+    x[:8] = [0, 5, -5, 0, 0, 5, -5, 1]
+    cfg = s3.make_config(16, 16, N=3, M_v=1, dirs=1)
+    ctx = s3.Scan3D(cfg, 0)
+    want = np.array([np.float32(np.math.atan2(a, b)) if False else 0 for a, b in ()], np.float32)
+    import math
+    want = np.fromiter((math.atan2(a, b) for a, b in zip(y, x)), np.float64, y.size).astype(np.float32)
+    for mode in (0, 1):
+        got = ctx.debug_atan2(y, x, mode)
+        bad = int((got.view(np.uint32) != want.view(np.uint32)).sum())
+        print("atan2 mode", mode, "non-identical:", bad)
+        assert bad == 0
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------- stage by stage
+@pytest.mark.parametrize("W,H,N,Mv,Mh,fw", [(200, 150, 3, 6, 5, 4), (333, 77, 4, 7, 6, 3), (64, 40, 5, 5, 4, 4),
+                                            (640, 480, 8, 9, 8, 2), (97, 33, 6, 6, 5, 2)])
+def test_stage_entries_match_oracle(W, H, N, Mv, Mh, fw):
+    PW, PH = fw * (1 << Mv) // 2 + 37, fw * (1 << Mh) // 2 + 11
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fw, fw, 2)
+    stack, roi = s3.synth_stack(cfg, cal, s3.default_synth_params(seed=W * 7 + H))
+    ref = run_oracle(cfg, ocal, stack, roi)
+    d = s3.split_stack(cfg, stack)
+    ctx = _ctx(cfg, cal)
+    for k, key in enumerate(("v", "h")):
+        ctx.compute_wrapped_phase(k, d["fringe_" + key], roi)
+        ctx.unwrap_phase(k, d["gray_" + key], d["inv_" + key])
+    # wrapped plane after unwrap's in-place += Pi
+    wv = ctx.plane(s3.PLANE_WRAPPED_V)
+    assert np.abs(wv.astype(np.float64) - ref.wrapped_v).max() <= 4e-7
+    assert np.array_equal(ctx.plane(s3.PLANE_MASK).astype(np.int32), ref.valid_v)
+    assert np.array_equal(ctx.plane(s3.PLANE_MASK_H).astype(np.int32), ref.valid_h)
+    ctx.compute_c_p_map()
+    ctx.triangulate()
+    n = ctx.compact_points()
+    st = compare(cfg, ref, ctx, fused=False)
+    if st["unw_v_nonidentical"] == 0 and st["unw_h_nonidentical"] == 0:
+        xyz = ctx.plane(s3.PLANE_XYZ)
+        m = ref.valid == 1
+        assert np.array_equal(xyz[m], ref.xyz[m]), "dense XYZ not bit-identical"
+        assert n == ref.count
+    print(st)
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------- fused kernel
+FUSED_CASES = [
+    # W, H, PW, PH, N, Mv, Mh, fw_v, fw_h, dirs
+    (1600, 1200, 1280, 720, 3, 6, 5, 32, 32, 2),     # C1 geometry
+    (1920, 1080, 1920, 1080, 3, 8, 8, 8, 8, 1),      # C2: vertical stage only
+    (1040, 64, 1024, 768, 8, 10, 10, 1, 1, 2),       # partial tile at the row end
+    (2048, 96, 2048, 1500, 8, 10, 10, 2, 2, 2),
+    (512, 300, 640, 480, 4, 7, 6, 5, 8, 2),
+    (256, 128, 512, 512, 5, 6, 6, 8, 8, 2),
+    (16, 3, 64, 64, 3, 4, 4, 4, 4, 2),               # degenerate tiny frame
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_fused_matches_oracle(case):
+    W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs = case
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs, flags=s3.FLAG_POINT_PIXELS)
+    stack, roi = s3.synth_stack(cfg, cal, s3.default_synth_params(seed=W + 31 * H))
+    ref = run_oracle(cfg, ocal, stack, roi)
+    ctx = _ctx(cfg, cal)
+    n = ctx.reconstruct(stack, roi)
+    st = compare(cfg, ref, ctx, fused=True)
+    if dirs == 2 and st.get("pts_nonidentical") is not None:
+        assert n == ref.count
+        _, pix = ctx.points(want_pix=True)
+        assert np.array_equal(pix, ref.pix)
+    # a second scan on the same ctx (epoch-tagged look-back state, reused buffers)
+    stack2, roi2 = s3.synth_stack(cfg, cal, s3.default_synth_params(seed=W + 31 * H + 1, roi_fraction=0.4))
+    ref2 = run_oracle(cfg, ocal, stack2, roi2)
+    ctx.reconstruct(stack2, roi2)
+    compare(cfg, ref2, ctx, fused=True)
+    print(case, st)
+    ctx.close()
+
+
+def test_fused_distorted_projector_and_tangential_camera():
+    W, H, PW, PH = 1024, 256, 1024, 768
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0, dc=[0.0813, -0.1102, 0.0013, -0.0007, 0.021],
+                          dp=[-0.05, 0.02, 0.001, -0.0005, 0.0])
+    cfg = s3.make_config(W, H, PW, PH, 8, 10, 10, 1, 1, 2)
+    stack, roi = s3.synth_stack(cfg, cal)
+    ref = run_oracle(cfg, ocal, stack, roi)
+    ctx = _ctx(cfg, cal)
+    ctx.reconstruct(stack, roi)
+    print(compare(cfg, ref, ctx))
+    ctx.close()
+
+
+def test_fused_undistorted_camera():
+    W, H, PW, PH = 1024, 128, 1024, 768
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0, dc=[0, 0, 0, 0, 0])
+    cfg = s3.make_config(W, H, PW, PH, 3, 10, 10, 1, 1, 2)
+    stack, roi = s3.synth_stack(cfg, cal)
+    ref = run_oracle(cfg, ocal, stack, roi)
+    ctx = _ctx(cfg, cal)
+    ctx.reconstruct(stack, roi)
+    print(compare(cfg, ref, ctx))
+    ctx.close()
+
+
+@pytest.mark.parametrize("kind", ["empty", "full", "random", "border"])
+def test_fused_roi_edge_cases(kind):
+    W, H, PW, PH = 1056, 40, 1024, 768
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, 3, 10, 10, 1, 1, 2)
+    stack, roi = s3.synth_stack(cfg, cal)
+    rng = np.random.default_rng(3)
+    if kind == "empty":
+        roi[:] = 0
+    elif kind == "full":
+        roi[:] = 1          # includes the image border: exercises the uninitialised-border policy
+    elif kind == "random":
+        roi[:] = (rng.random(roi.shape) < 0.93)
+    else:
+        roi[:] = 0
+        roi[:3, :] = 1; roi[-2:, :] = 1; roi[:, :3] = 7; roi[:, -3:] = 255
+    ref = run_oracle(cfg, ocal, stack, roi)
+    ctx = _ctx(cfg, cal)
+    n = ctx.reconstruct(stack, roi)
+    st = compare(cfg, ref, ctx)
+    if kind == "empty":
+        assert n == 0
+    print(kind, st)
+    ctx.close()
+
+
+def test_fused_row_shards_concatenate_to_full_frame():
+    W, H, PW, PH = 1024, 90, 1024, 768
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    full = s3.make_config(W, H, PW, PH, 8, 10, 10, 1, 1, 2, flags=s3.FLAG_POINT_PIXELS)
+    stack, roi = s3.synth_stack(full, cal)
+    ref = run_oracle(full, ocal, stack, roi)
+    pts, pix = [], []
+    for r0, r1 in ((0, 31), (31, 32), (32, 90)):
+        cfg = s3.make_config(W, r1 - r0, PW, PH, 8, 10, 10, 1, 1, 2, row0=r0, H_total=H, flags=s3.FLAG_POINT_PIXELS)
+        ctx = _ctx(cfg, cal)
+        ctx.reconstruct(np.ascontiguousarray(stack[:, r0:r1]), roi)
+        p, q = ctx.points(want_pix=True)
+        pts.append(p); pix.append(q)
+        assert np.array_equal(ctx.code_i32(0), ref.code_v[r0:r1])
+        assert np.array_equal(ctx.plane(s3.PLANE_VALID).astype(np.int32), ref.valid[r0:r1])
+        ctx.close()
+    pts, pix = np.concatenate(pts), np.concatenate(pix)
+    assert np.array_equal(pix, ref.pix)
+    assert np.array_equal(pts.view(np.uint32), ref.pts.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------- golden data
+def test_c1_crop_through_gpu_matches_reference_images():
+    d = load_c1_crop()
+    H, W = d["golden_wrapped_v"].shape
+    cal, ocal, _ = calibs()
+    cfg = s3.make_config(W, H, 1280, 720, 3, 6, 5, 32, 32, 2)
+    ctx = _ctx(cfg, cal)
+    roi = (d["golden_wrapped_v"] != 0).astype(np.uint8)   # the reference's post-recurrence mask
+    for k, key, codes in ((0, "v", 40), (1, "h", 23)):
+        ctx.compute_wrapped_phase(k, d["fringe_" + key], roi)
+        w = ctx.plane(s3.PLANE_WRAPPED_V + k)
+        m = roi == 1
+        dbg = (128.0 + 127.0 * (w.astype(np.float64) / (22.0 / 7.0))).astype(np.float32).astype(np.int32).astype(np.uint8)
+        assert np.array_equal(dbg[m], d["golden_wrapped_" + key][m])
+    # full path on the crop against the oracle (real captured data)
+    stack = np.concatenate([d["fringe_v"], d["gray_v"], d["inv_v"], d["fringe_h"], d["gray_h"], d["inv_h"]])
+    ref = run_oracle(cfg, ocal, stack, roi)
+    ctx.reconstruct(stack, roi)
+    st = compare(cfg, ref, ctx)
+    unw = ctx.plane(s3.PLANE_UNWRAPPED_V)
+    m = ref.valid_v == 1
+    m[:, 0] = m[:, -1] = False
+    img = o.unwrapped_image(unw, m.astype(np.int32), 40)
+    assert np.array_equal(img[m], d["golden_unwrapped_v"][m])
+    print(st)
+    ctx.close()
+
+
+def test_ply_writer(tmp_path):
+    W, H, PW, PH = 256, 64, 512, 512
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, 3, 6, 6, 8, 8, 2)
+    stack, roi = s3.synth_stack(cfg, cal)
+    ctx = _ctx(cfg, cal)
+    tex = np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    ctx.set_texture(tex)
+    n = ctx.reconstruct(stack, roi)
+    xyz, rgb = ctx.points(want_rgb=True)
+    valid = ctx.plane(s3.PLANE_VALID).astype(bool)
+    assert np.array_equal(rgb, tex[valid][:, ::-1])
+    for binary in (False, True):
+        path = str(tmp_path / f"cloud_{int(binary)}.ply")
+        ctx.write_ply(path, binary)
+        raw = open(path, "rb").read()
+        head, body = raw.split(b"end_header\n", 1)
+        assert f"element vertex {n}".encode() in head
+        if binary:
+            rec = np.frombuffer(body, np.dtype([("p", "<f4", 3), ("c", "u1", 3)]))
+            assert np.array_equal(rec["p"], xyz) and np.array_equal(rec["c"], rgb)
+        else:
+            rows = np.loadtxt(body.decode().splitlines()) if n else np.empty((0, 6))
+            assert np.array_equal(rows[:, :3].astype(np.float32), xyz)
+    ctx.close()
