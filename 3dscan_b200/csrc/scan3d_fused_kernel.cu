@@ -215,6 +215,7 @@ __device__ __forceinline__ float phase_of(const Terms& T, int j, const double* t
     } else {
         const int t1 = term_of(T, 0, j, N == 5 ? 1024 : 512);
         const int t2 = term_of(T, 1, j, N == 4 ? 512 : 1024);
+        if (N == 5) return atan2f_fdlibm((float)t1, (float)t2);   // 3/wrapped_phase.cpp:220 (float atan2f)
         return atan2_to_float((double)t1, (double)t2, (float)t1, (float)t2, tab, tab + 33);
     }
 }

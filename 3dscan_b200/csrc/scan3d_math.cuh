@@ -88,6 +88,74 @@ __device__ __forceinline__ float atan2_to_float(double y, double x, float yf, fl
 }
 
 // ---------------------------------------------------------------------------------------
+// The 5-step formula calls the FLOAT atan2f (3/wrapped_phase.cpp:220).  glibc's atan2f is the
+// fdlibm routine (sysdeps/ieee754/flt-32/e_atan2f.c + s_atanf.c, unchanged from the eglibc 2.15
+// the reference ran on to the glibc 2.39 of this image): a fixed sequence of float operations.
+// Restated here with explicitly rounded float intrinsics so the result is bit-identical
+// (tests/test_oracle_golden.py pins the same restatement against libm on the CPU).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fd(float a, float b) { return __fdiv_rn(a, b); }
+
+__device__ __forceinline__ float atanf_fdlibm(float x)
+{
+    const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+    const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+    const int hx = __float_as_int(x), ix = hx & 0x7fffffff;
+    int id;
+    if (ix >= 0x4c000000) {
+        if (ix > 0x7f800000) return fa(x, x);
+        return hx > 0 ? fa(atanhi[3], atanlo[3]) : fs(-atanhi[3], atanlo[3]);
+    }
+    if (ix < 0x3ee00000) {
+        if (ix < 0x31000000) return x;
+        id = -1;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000) {
+            if (ix < 0x3f300000) { id = 0; x = fd(fs(fm(2.0f, x), 1.0f), fa(2.0f, x)); }
+            else { id = 1; x = fd(fs(x, 1.0f), fa(x, 1.0f)); }
+        } else {
+            if (ix < 0x401c0000) { id = 2; x = fd(fs(x, 1.5f), fa(1.0f, fm(1.5f, x))); }
+            else { id = 3; x = fd(-1.0f, x); }
+        }
+    }
+    const float z = fm(x, x), w = fm(z, z);
+    const float s1 = fm(z, fa(3.3333334327e-01f, fm(w, fa(1.4285714924e-01f, fm(w, fa(9.0908870101e-02f,
+                     fm(w, fa(6.6610731184e-02f, fm(w, fa(4.9768779427e-02f, fm(w, 1.6285819933e-02f)))))))))));
+    const float s2 = fm(w, fa(-2.0000000298e-01f, fm(w, fa(-1.1111110449e-01f, fm(w, fa(-7.6918758452e-02f,
+                     fm(w, fa(-5.8335702866e-02f, fm(w, -3.6531571299e-02f)))))))));
+    if (id < 0) return fs(x, fm(x, fa(s1, s2)));
+    const float hi = id == 0 ? atanhi[0] : id == 1 ? atanhi[1] : id == 2 ? atanhi[2] : atanhi[3];
+    const float lo = id == 0 ? atanlo[0] : id == 1 ? atanlo[1] : id == 2 ? atanlo[2] : atanlo[3];
+    const float r = fs(hi, fs(fs(fm(x, fa(s1, s2)), lo), x));
+    return hx < 0 ? -r : r;
+}
+
+__device__ __forceinline__ float atan2f_fdlibm(float y, float x)
+{
+    const float tiny = 1.0e-30f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+    const int hx = __float_as_int(x), ix = hx & 0x7fffffff, hy = __float_as_int(y), iy = hy & 0x7fffffff;
+    if (ix > 0x7f800000 || iy > 0x7f800000) return fa(x, y);
+    if (hx == 0x3f800000) return atanf_fdlibm(y);
+    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+    if (iy == 0) return m == 0 || m == 1 ? y : (m == 2 ? fa(pi, tiny) : fs(-pi, tiny));
+    if (ix == 0) return hy < 0 ? fs(-pi_o_2, tiny) : fa(pi_o_2, tiny);
+    // (infinite operands cannot occur: the inputs are differences of 8-bit samples)
+    const int k = (iy - ix) >> 23;
+    float z;
+    if (k > 60) z = fa(pi_o_2, fm(0.5f, pi_lo));
+    else if (hx < 0 && k < -60) z = 0.0f;
+    else z = atanf_fdlibm(fabsf(fd(y, x)));
+    if (m == 0) return z;
+    if (m == 1) return __int_as_float(__float_as_int(z) ^ 0x80000000);
+    if (m == 2) return fs(pi, fs(z, pi_lo));
+    return fs(fs(z, pi_lo), pi);
+}
+
+// ---------------------------------------------------------------------------------------
 // wrapped phase (3/wrapped_phase.cpp:151-238).  I[k] are the pixel's N fringe samples.
 // USE_LIBDEVICE selects CUDA's own double atan2 (reference implementation for A/B tests).
 // ---------------------------------------------------------------------------------------
@@ -112,7 +180,7 @@ __device__ __forceinline__ float wrapped_phase(const int* I, const double* __res
         return phase_from_terms<USE_LIBDEVICE>((double)t1, (double)t2, (float)t1, (float)t2, tab_hi, tab_lo);
     } else if (N == 5) {     // :217-220   t1 = 2(I1 - I3) ; t2 = 2*I2 - I0 - I4 ; atan2f
         const int t1 = 2 * (I[1] - I[3]), t2 = 2 * I[2] - I[0] - I[4];
-        return phase_from_terms<USE_LIBDEVICE>((double)t1, (double)t2, (float)t1, (float)t2, tab_hi, tab_lo);
+        return atan2f_fdlibm((float)t1, (float)t2);
     } else if (N == 8) {     // extension: shifts k*pi/4, phase origin of the 4-step formula
         const int a1 = I[6] - I[2], b1 = I[5] + I[7] - I[1] - I[3];
         const int a2 = I[0] - I[4], b2 = I[1] + I[7] - I[3] - I[5];

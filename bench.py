@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the reconstruction hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torchrun)
+  python bench.py --impl reference ...                    (CPU oracle port, rank 0 only)
+
+Workload: BASELINE.json configs[2] = synthetic 4096x3000 (12 MP) scans, vertical + horizontal,
+8-step phase shift + 10-bit Gray code (56 u8 frames per scan).  A "step" is one pass of the hot
+path over one batch of `--batch` scans per GPU, cycled over a ring of `--ring` distinct stacks
+resident in HBM (ring bytes >> L2).  With N > 1 this is configs[3]: scans are sharded
+frame-parallel, no collective on the data path (weak scaling: per-GPU work is fixed).
+
+Printed JSON (one line, rank 0): value = whole-job Mpix/s with inputs resident in HBM; e2e = the
+same metric through the host-buffer C-ABI entry (pinned host stack -> H2D -> kernel -> D2H of the
+point cloud); roofline for the fused kernel; cpu_baseline = the oracle port on the host cores.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+METRIC = "decoded+triangulated Mpix/s"
+WORKLOADS = {
+    # name: W, H, PW, PH, N, M_v, M_h, fw_v, fw_h, dirs
+    "c3_12mp_8step_10bit_vh": (4096, 3000, 4096, 3000, 8, 10, 10, 4, 4, 2),
+    "c2_1080p_3step_8bit_v": (1920, 1080, 1920, 1080, 3, 8, 8, 8, 8, 1),
+    "c1_1600x1200_3step_6bit_vh": (1600, 1200, 1280, 720, 3, 6, 5, 32, 32, 2),
+}
+
+
+def algorithmic_bytes_per_pixel(N, M_v, M_h, dirs):
+    """every input frame read once + 1 B ROI; per direction 4 B phase + 2 B fringe
+    order; 1 B valid; both directions: 8 B c_p_map + 12 B point (f = 1 upper bound)."""
+    reads = N + 2 * M_v + (N + 2 * M_h if dirs == 2 else 0) + 1
+    writes = dirs * 6 + 1 + (20 if dirs == 2 else 0)
+    return reads + writes
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of the fused kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "fused_kernel_ncu.json")) as f:
+            d = json.load(f)
+        return d.get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15] or [r for _, r in self.rows[-3:]]
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_scan_seconds(cfg, ocal, stack, roi, threads, min_seconds, max_runs):
+    from gpu_common import run_oracle
+    run_oracle(cfg, ocal, stack, roi, threads=threads)          # warm (page faults, thread pool)
+    times = []
+    t_all = time.time()
+    while len(times) < max_runs and (not times or time.time() - t_all < min_seconds):
+        t = time.time()
+        run_oracle(cfg, ocal, stack, roi, threads=threads)
+        times.append(time.time() - t)
+    return float(np.median(times)), len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_12mp_8step_10bit_vh", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=16, help="scans per GPU per step")
+    ap.add_argument("--ring", type=int, default=4, help="distinct resident stacks per GPU")
+    ap.add_argument("--e2e-scans", type=int, default=2, help="scans per e2e step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs = WORKLOADS[args.workload]
+    npix = W * H
+    bpp = algorithmic_bytes_per_pixel(N, Mv, Mh, dirs)
+
+    from gpu_common import calibs, s3
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs)
+    config = {"workload": args.workload, "frame": [W, H], "projector": [PW, PH], "phase_steps": N,
+              "gray_bits": [Mv, Mh][:dirs], "directions": dirs, "frames_per_scan": s3.stack_planes(cfg),
+              "scans_per_gpu_per_step": args.batch, "resident_ring": args.ring,
+              "sharding": "frame-parallel scans, no collective" if world > 1 else "single GPU",
+              "l2_policy": "inputs larger than L2 (ring of distinct stacks, %.2f GB per GPU)"
+                           % (args.ring * s3.stack_planes(cfg) * npix / 1e9),
+              "algorithmic_bytes_per_pixel": bpp}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import oracle_ffi as o
+        threads = o.max_threads()
+        stack, roi = s3.synth_stack(cfg, cal, s3.default_synth_params(seed=0x3D5CA9))
+        from gpu_common import run_oracle
+        for _ in range(args.warmup):
+            run_oracle(cfg, ocal, stack, roi, threads=threads)
+        t0 = time.time()
+        for _ in range(args.steps):
+            run_oracle(cfg, ocal, stack, roi, threads=threads)
+        dt = time.time() - t0
+        val = args.steps * npix / dt / 1e6
+        config["scans_per_gpu_per_step"] = 1
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "scans_per_s": args.steps / dt,
+                "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": threads, "kind": "port",
+                                 "sample": "1 full %dx%d scan per step, stages 3-8 incl. full-frame undistort tables, inputs in RAM, no file I/O" % (W, H)},
+                "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    ctx = s3.Scan3D(cfg, local_rank, cal, stream=stream.cuda_stream)
+    nf = s3.stack_planes(cfg)
+    # resident ring of distinct synthetic scans (scan index = global, so ranks hold different scans)
+    ring, rois = [], []
+    host_stack = torch.empty((nf, H, W), dtype=torch.uint8, pin_memory=True)
+    host_roi = torch.empty((H, W), dtype=torch.uint8, pin_memory=True)
+    for i in range(args.ring):
+        prm = s3.default_synth_params(seed=0x3D5CA9 + rank * args.ring + i,
+                                      sphere_c=(60.0 + 3.0 * i, 40.0 - 2.0 * i, -30.0 - 1.5 * rank))
+        s3.synth_stack(cfg, cal, prm, out=host_stack.numpy(), roi_out=host_roi.numpy())
+        ring.append(host_stack.to("cuda", non_blocking=False))
+        rois.append(host_roi.to("cuda", non_blocking=False))
+    torch.cuda.synchronize()
+
+    def step():
+        for b in range(args.batch):
+            k = b % args.ring
+            ctx.reconstruct_dev(ring[k].data_ptr(), rois[k].data_ptr())
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop(t_wall0, t_wall1)
+    count = ctx.point_count() if dirs == 2 else 0
+    tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    total_pix = world * args.steps * args.batch * npix
+    value = total_pix / (ms_max * 1e-3) / 1e6
+
+    # ---- roofline of the dominant (only) kernel: algorithmic bytes per launch / avg launch time
+    per_launch_s = ms * 1e-3 / max(launches, 1)
+    peak, peak_kind = measured_peak_gbs()
+    achieved = bpp * npix / per_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(args.workload), "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
+                "kernel": "s3d::k_fused<%d,%d>" % (N, dirs), "algorithmic_bytes_per_launch": bpp * npix,
+                "avg_launch_us": per_launch_s * 1e6, "frac_of_8TBs_nominal": achieved / 8000.0}
+
+    # ---- e2e: host-buffer entry, pinned input, H2D + kernel + D2H of the point cloud per scan
+    e2e = None
+    if not args.no_e2e:
+        pts_host = torch.empty((npix, 3), dtype=torch.float32, pin_memory=True) if dirs == 2 else None
+        out_host = torch.empty((H, W), dtype=torch.float32, pin_memory=True)
+        h2d = (nf + 1) * npix
+
+        def e2e_scan():
+            n = ctx.reconstruct(host_stack.numpy(), host_roi.numpy())
+            if dirs == 2:
+                ctx._ck(ctx.L.scan3d_get_points(ctx.h, pts_host.data_ptr(), None, None, n))
+                return n * 12 + 8
+            ctx._ck(ctx.L.scan3d_get_plane(ctx.h, s3.PLANE_UNWRAPPED_V, out_host.data_ptr()))
+            return npix * 4
+
+        d2h = e2e_scan()
+        barrier()
+        t0 = time.time()
+        e_steps = max(1, min(args.steps, 5))
+        for _ in range(e_steps):
+            for _ in range(args.e2e_scans):
+                d2h = e2e_scan()
+        barrier()
+        dt = time.time() - t0
+        te = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * e_steps * args.e2e_scans * npix / float(te.item()) / 1e6, "unit": "Mpix/s",
+               "h2d_bytes_per_step": h2d * args.e2e_scans, "d2h_bytes_per_step": d2h * args.e2e_scans,
+               "scans_per_step": args.e2e_scans, "steps": e_steps,
+               "api": "scan3d_reconstruct(host stack, host roi) + scan3d_get_points"}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 semantics)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        import oracle_ffi as o
+        threads = o.max_threads()
+        sec, runs = oracle_scan_seconds(cfg, ocal, host_stack.numpy(), host_roi.numpy(), threads, 8.0, 4)
+        cpu = {"value": npix / sec / 1e6, "unit": "Mpix/s", "cores": threads, "kind": "port",
+               "sample": "%d full %dx%d scan(s) of the same workload, median; stages 3-8 incl. full-frame undistort tables; inputs in RAM" % (runs, W, H),
+               "seconds_per_scan": sec}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "scans_per_s": world * args.steps * args.batch / (ms_max * 1e-3),
+                "points_last_scan": count, "gpu_launches": launches, "clocks": clocks,
+                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -115,12 +115,86 @@ void o3d_wrapped_phase(const uint8_t *fringe, int N, int W, int H, const int32_t
                     S = S + I * ws[k];
                     C = C + I * wc[k];
                 }
-                wrapped[p] = atan2(-S, C);
+                wrapped[p] = atan2(0.0 - S, C); /* 0.0 - S: S == +0 must not become -0 */
                 t3 = 127.0f + 128.0f * (wrapped[p] / (Pi));
             }
             if (dbg) dbg[p] = (unsigned char)(int)(t3);
         }
     }
+}
+
+/* ---- fdlibm atan2f restated (glibc sysdeps/ieee754/flt-32/e_atan2f.c + s_atanf.c) ----------
+ * NOT used by o3d_wrapped_phase (which calls libm's atan2f like the reference); exported so the
+ * tests can pin this operation sequence -- the one the CUDA path mirrors for the 5-step formula
+ * -- against the libm of the machine the tests run on. */
+static inline int32_t f2i(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
+static inline float i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
+static float atanf_restated(float x)
+{
+    static const float atanhi[] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+    static const float atanlo[] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+    static const float aT[] = {3.3333334327e-01f, -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f,
+                               9.0908870101e-02f, -7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f,
+                               4.9768779427e-02f, -3.6531571299e-02f, 1.6285819933e-02f};
+    float w, s1, s2, z;
+    int32_t ix, hx = f2i(x), id;
+    ix = hx & 0x7fffffff;
+    if (ix >= 0x4c000000) {
+        if (ix > 0x7f800000) return x + x;
+        return hx > 0 ? atanhi[3] + atanlo[3] : -atanhi[3] - atanlo[3];
+    }
+    if (ix < 0x3ee00000) {
+        if (ix < 0x31000000) return x;
+        id = -1;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000) {
+            if (ix < 0x3f300000) { id = 0; x = (2.0f * x - 1.0f) / (2.0f + x); }
+            else { id = 1; x = (x - 1.0f) / (x + 1.0f); }
+        } else {
+            if (ix < 0x401c0000) { id = 2; x = (x - 1.5f) / (1.0f + 1.5f * x); }
+            else { id = 3; x = -1.0f / x; }
+        }
+    }
+    z = x * x;
+    w = z * z;
+    s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+    s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+    if (id < 0) return x - x * (s1 + s2);
+    z = atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
+    return hx < 0 ? -z : z;
+}
+float o3d_atan2f_restated(float y, float x)
+{
+    const float tiny = 1.0e-30f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+    float z;
+    int32_t k, m, hx = f2i(x), hy = f2i(y), ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    if (ix > 0x7f800000 || iy > 0x7f800000) return x + y;
+    if (hx == 0x3f800000) return atanf_restated(y);
+    m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+    if (iy == 0) return m < 2 ? y : (m == 2 ? pi + tiny : -pi - tiny);
+    if (ix == 0) return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    k = (iy - ix) >> 23;
+    if (k > 60) z = pi_o_2 + 0.5f * pi_lo;
+    else if (hx < 0 && k < -60) z = 0.0f;
+    else z = atanf_restated(fabsf(y / x));
+    switch (m) {
+        case 0: return z;
+        case 1: return i2f(f2i(z) ^ (int32_t)0x80000000);
+        case 2: return pi - (z - pi_lo);
+        default: return (z - pi_lo) - pi;
+    }
+}
+/* count of (t1,t2) on the 5-step input grid where the restatement differs from libm atan2f */
+long o3d_atan2f_restated_mismatches(void)
+{
+    long bad = 0;
+    for (int a = -510; a <= 510; a += 2)
+        for (int b = -510; b <= 510; b++) {
+            const float r = atan2f((float)a, (float)b), q = o3d_atan2f_restated((float)a, (float)b);
+            bad += f2i(r) != f2i(q);
+        }
+    return bad;
 }
 
 /* 3/wrapped_phase.cpp:266-279 (vertical) == :306-318 (horizontal): one raster pass,

@@ -59,6 +59,10 @@ void o3d_check_roi(const uint8_t *roi, int W, int H, int32_t *valid);
 void o3d_wrapped_phase(const uint8_t *fringe, int N, int W, int H, const int32_t *valid,
                        float *wrapped, uint8_t *dbg, int threads);
 
+/* fdlibm atan2f restated; pinned against libm by the tests (see .c). */
+float o3d_atan2f_restated(float y, float x);
+long o3d_atan2f_restated_mismatches(void);
+
 /* save_wrapped_image :266-279 (== :306-318): the literal sequential raster recurrence. */
 void o3d_mask_recurrence(int32_t *valid, int W, int H, uint8_t *dbg);
 

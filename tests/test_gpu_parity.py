@@ -49,8 +49,7 @@ def test_wrapped_phase_random(N):
     bad = int((got.view(np.uint32) != want.view(np.uint32)).sum())
     print(f"N={N}: non-identical wrapped-phase floats: {bad} of {got.size}")
     assert np.abs(got.astype(np.float64) - want).max() <= 4e-7
-    if N != 5:       # N=5: the reference calls float atan2f (glibc flt-32), see DESIGN.md
-        assert bad <= 2
+    assert bad <= 2
     ctx.close()
 
 
@@ -62,7 +61,6 @@ def test_debug_atan2_modes_agree_with_libm():
     x[:8] = [0, 5, -5, 0, 0, 5, -5, 1]
     cfg = s3.make_config(16, 16, N=3, M_v=1, dirs=1)
     ctx = s3.Scan3D(cfg, 0)
-    want = np.array([np.float32(np.math.atan2(a, b)) if False else 0 for a, b in ()], np.float32)
     import math
     want = np.fromiter((math.atan2(a, b) for a, b in zip(y, x)), np.float64, y.size).astype(np.float32)
     for mode in (0, 1):

@@ -136,3 +136,13 @@ def test_quirks():
     cp, valid = o.compute_c_p_map(unw * 0 + 1000.0, unw * 0, np.ones((1, 1), np.int32),
                                   np.ones((1, 1), np.int32), 4, 4, 10, 10)
     assert valid[0, 0] == 0 and cp[0, 0] == int(np.rint(4 * (1000.0 / (44.0 / 7.0))))
+
+
+def test_fdlibm_atan2f_restatement_equals_libm():
+    """the 5-step formula calls float atan2f (3/wrapped_phase.cpp:220); the CUDA path mirrors
+    glibc's fdlibm operation sequence, pinned here against this machine's libm on every
+    (t1, t2) the 5-step formula can produce."""
+    import ctypes
+    L = o.lib()
+    L.o3d_atan2f_restated_mismatches.restype = ctypes.c_long
+    assert L.o3d_atan2f_restated_mismatches() == 0
