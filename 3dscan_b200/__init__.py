@@ -22,6 +22,7 @@ PLANE_WRAPPED_V, PLANE_WRAPPED_H, PLANE_UNWRAPPED_V, PLANE_UNWRAPPED_H = 0, 1, 2
 PLANE_CODE_V, PLANE_CODE_H, PLANE_MASK, PLANE_VALID, PLANE_CPMAP, PLANE_XYZ = 4, 5, 6, 7, 8, 9
 PLANE_MASK_H = 10
 FLAG_POINT_PIXELS = 1
+FLAG_FAST_TRIANGULATION = 2
 
 _PLANE_DTYPE = {
     PLANE_WRAPPED_V: (np.float32, ()), PLANE_WRAPPED_H: (np.float32, ()),
@@ -132,6 +133,7 @@ def cuda_lib():
     L.scan3d_launch_count.argtypes = [vp]
     L.scan3d_launch_count.restype = i64
     L.scan3d_debug_atan2.argtypes = [vp, vp, vp, vp, i32, i32]
+    L.scan3d_debug_divcheck.argtypes = [vp, C.POINTER(C.c_uint64)]
     _cuda = L
     return L
 
@@ -384,6 +386,11 @@ class Scan3D:
 
     def launch_count(self):
         return int(self.L.scan3d_launch_count(self.h))
+
+    def debug_divcheck(self):
+        n = C.c_uint64()
+        self._ck(self.L.scan3d_debug_divcheck(self.h, C.byref(n)))
+        return n.value
 
     def debug_atan2(self, y, x, mode):
         y = np.ascontiguousarray(y, np.float64)

@@ -144,8 +144,8 @@ int scan3d_create(const scan3d_config* cfg, int device, scan3d_ctx** out)
         const int ntiles = fused_num_tiles(ctx->cfg);
         CK(dalloc(&ctx->tile_state, (size_t)ntiles + 1));
         CK(cudaMemsetAsync(ctx->tile_state, 0, ((size_t)ntiles + 1) * 8, ctx->stream));
-        CK(dalloc(&ctx->atan_tab, 66));
-        double tab[66];
+        CK(dalloc(&ctx->atan_tab, (size_t)ATAN_TAB_DOUBLES));
+        double tab[ATAN_TAB_DOUBLES];
         fill_atan_table(tab);
         CK(cudaMemcpyAsync(ctx->atan_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
         CK(dalloc(&ctx->nstep_w, 128));
@@ -158,6 +158,20 @@ int scan3d_create(const scan3d_config* cfg, int device, scan3d_ctx** out)
         }
         CK(cudaMemcpyAsync(ctx->nstep_w, w, sizeof(w), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        // exact-quotient shortcut (scan3d_math.cuh div_const): check it against IEEE division on
+        // every fringe order this config can produce; any mismatch disables the shortcut
+        {
+            const int Mmax = cfg->dirs == 2 && cfg->M_h > cfg->M_v ? cfg->M_h : cfg->M_v;
+            bool ok = true;
+            const double y7 = 1.0 / 7.0;
+            for (int code = 0; code < (1 << Mmax) && ok; code++) {
+                const double a = ((double)code * 2.0) * 22.0;
+                const double q0 = a * y7;
+                const double q = fma(fma(-q0, 7.0, a), y7, q0);
+                ok = q == a / 7.0;
+            }
+            ctx->fast_div_ok = ok;
+        }
         return SCAN3D_OK;
     }();
     if (rc != SCAN3D_OK) {
@@ -214,6 +228,14 @@ int scan3d_set_calibration(scan3d_ctx* ctx, const scan3d_calib* cal)
     memcpy(d.dc, cal->dc, sizeof(d.dc));
     memcpy(d.Kp, cal->Kp, sizeof(d.Kp));
     memcpy(d.dp, cal->dp, sizeof(d.dp));
+    d.ifx_c = 1. / cal->Kc[0]; d.ify_c = 1. / cal->Kc[4];
+    d.ifx_p = 1. / cal->Kp[0]; d.ify_p = 1. / cal->Kp[4];
+    auto std_form = [](const double* K) {
+        return K[1] == 0.0 && K[3] == 0.0 && K[6] == 0.0 && K[7] == 0.0 && K[8] == 1.0;
+    };
+    d.cam_std = std_form(cal->Kc);
+    d.proj_std = std_form(cal->Kp);
+    d.fast_div_ok = ctx->fast_div_ok ? 1 : 0;
     d.cam_distorted = d.proj_distorted = 0;
     for (int i = 0; i < 5; i++) {
         if (cal->dc[i] != 0.0) d.cam_distorted = 1;
@@ -437,7 +459,7 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     CK(cudaSetDevice(ctx->device));
     int stages = 0;
     size_t smem = 0;
-    if (!fused_supported(ctx->cfg, &stages, &smem)) return reconstruct_stagewise(ctx, stack_dev, roi_dev);
+    if (!ctx->fast_div_ok || !fused_supported(ctx->cfg, &stages, &smem)) return reconstruct_stagewise(ctx, stack_dev, roi_dev);
     const scan3d_config& c = ctx->cfg;
     FusedArgs a{};
     a.stack = stack_dev; a.roi = roi_dev;
@@ -640,6 +662,24 @@ int scan3d_debug_atan2(scan3d_ctx* ctx, const double* y_host, const double* x_ho
     CK(cudaMemcpyAsync(out_host, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(dy); cudaFree(dx); cudaFree(dout);
+    return SCAN3D_OK;
+}
+
+// ---- self-test entry: exact-quotient shortcut vs IEEE division over every float phase ----
+int scan3d_debug_divcheck(scan3d_ctx* ctx, uint64_t* mismatches)
+{
+    if (!ctx || !mismatches) return fail(ctx, SCAN3D_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc((void**)&d, 8));
+    CK(cudaMemsetAsync(d, 0, 8, ctx->stream));
+    CK(launch_debug_divcheck(d, ctx->stream));
+    ctx->launches++;
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    *mismatches = h;
     return SCAN3D_OK;
 }
 

@@ -21,6 +21,7 @@ struct scan3d_ctx {
 
     // calibration
     bool has_calib = false;
+    bool fast_div_ok = false;      // see scan3d_math.cuh div_const
     scan3d_calib hcal{};
     s3d::DeviceCalib dcal{};
     double2* cam_lut = nullptr;    // [H][W] (u',v') of the local rows, only if the camera is distorted
@@ -121,6 +122,8 @@ cudaError_t launch_fused(const scan3d_config& c, const FusedArgs& a, const Devic
 // ---- debug / self-test ----
 cudaError_t launch_debug_atan2(const double* y, const double* x, float* out, int n, int mode,
                                const double* atan_tab, cudaStream_t st);
+
+cudaError_t launch_debug_divcheck(unsigned long long* bad, cudaStream_t st);
 
 void fill_atan_table(double* hi33_lo33);
 

@@ -37,54 +37,55 @@ __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a,
 // polynomial is exact to 2^-60; one division (reciprocal seed + Newton) instead of libm's two
 // range-reduction divisions and degree-19 polynomial.
 // ---------------------------------------------------------------------------------------
-struct AtanTable {
-    double hi[33];
-    double lo[33];
-};
+// Table layout (66 + 6 doubles, built on the host by fill_atan_table with long-double atanl):
+//   [0..32]  hi(atan(i/32))      [33..65] lo(atan(i/32))
+//   [66..71] quadrant constants {K_hi, K_lo} for k = 0 (none), 1 (pi/2), 2 (pi)
+constexpr int ATAN_TAB_DOUBLES = 72;
 
 __device__ __forceinline__ double fast_div(double num, double den)
 {
     double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
-    r = fma(r, fma(-den, r, 1.0), r);
-    r = fma(r, fma(-den, r, 1.0), r);
-    double t = num * r;
-    return fma(fma(-den, t, num), r, t);
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));   // ~20 good bits
+    r = fma(r, fma(-den, r, 1.0), r);                          // ~40
+    const double t = num * r;
+    return fma(fma(-den, t, num), r, t);                       // residual correction: ~1 ulp
 }
 
 // y, x: exact doubles; yf, xf: any float approximations of them (only select the table row).
+// Branch-free on purpose: the two directions' evaluations interleave in one basic block.
+//   atan2 = K + s*atan(mn/mx):  (|y|<=|x|, x>=0): K=0, s=+   (|y|>|x|, x>=0): K=pi/2, s=-
+//                               (|y|<=|x|, x<0):  K=pi, s=-  (|y|>|x|, x<0):  K=pi/2, s=+
+// then the sign of y.
 __device__ __forceinline__ float atan2_to_float(double y, double x, float yf, float xf,
-                                                const double* __restrict__ tab_hi,
-                                                const double* __restrict__ tab_lo)
+                                                const double* __restrict__ tab)
 {
     const double ax = fabs(x), ay = fabs(y);
     const bool swap = ay > ax;
+    const bool xneg = x < 0.0;
     const double mx = swap ? ay : ax, mn = swap ? ax : ay;
     const float axf = fabsf(xf), ayf = fabsf(yf);
-    const float mxf = fmaxf(axf, ayf), mnf = fminf(axf, ayf);
-    int i = __float2int_rn(__fdividef(mnf, mxf) * 32.0f);
-    i = mxf > 0.0f ? min(max(i, 0), 32) : 0;
-    const double c = (double)i * 0.03125;
+    // 0/0 -> NaN -> cvt.rni gives 0: row 0, and the result is forced to 0 below
+    int i = __float2int_rn(__fdividef(fminf(axf, ayf), fmaxf(axf, ayf)) * 32.0f);
+    i = min(max(i, 0), 32);
+    // c = i/32 exactly: (2^47 + i/32) - 2^47 with the integer dropped into the mantissa
+    const double c = __hiloint2double(0x42e00000, i) - 140737488355328.0;
     const double num = fma(-c, mx, mn);
     const double den = fma(c, mn, mx);
-    double res;
-    if (mx == 0.0) {
-        res = 0.0;
-    } else {
-        const double t = fast_div(num, den);
-        const double s = t * t;
-        double p = fma(s, 1.0 / 9.0, -1.0 / 7.0);
-        p = fma(s, p, 1.0 / 5.0);
-        p = fma(s, p, -1.0 / 3.0);
-        p = fma(t * s, p, t);
-        res = tab_hi[i] + (tab_lo[i] + p);
-    }
-    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
-    const double pi_hi = 3.14159265358979311600e+00, pi_lo = 1.22464679914735317720e-16;
-    if (swap) res = (pio2_hi - res) + pio2_lo;
-    if (x < 0.0) res = (pi_hi - res) + pi_lo;
-    res = y < 0.0 ? -res : res;
-    return __double2float_rn(res);
+    const double t = fast_div(num, den);
+    const double s = t * t;
+    double p = fma(s, 1.0 / 9.0, -1.0 / 7.0);
+    p = fma(s, p, 1.0 / 5.0);
+    p = fma(s, p, -1.0 / 3.0);
+    p = fma(t * s, p, t);
+    double res = tab[i] + (tab[33 + i] + p);
+    // s*res: flip the sign when exactly one of (swap, xneg) holds
+    res = __hiloint2double(__double2hiint(res) ^ ((swap != xneg) ? 0x80000000 : 0), __double2loint(res));
+    const int k = swap ? 1 : (xneg ? 2 : 0);
+    res = tab[66 + 2 * k] + (tab[67 + 2 * k] + res);
+    float out = __double2float_rn(res);
+    out = mx == 0.0 ? 0.0f : out;
+    // copy the sign of y (y is never -0 here: it is a difference of non-negative samples)
+    return __int_as_float(__float_as_int(out) ^ (__double2hiint(y) & 0x80000000));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -161,10 +162,10 @@ __device__ __forceinline__ float atan2f_fdlibm(float y, float x)
 // ---------------------------------------------------------------------------------------
 template <bool USE_LIBDEVICE>
 __device__ __forceinline__ float phase_from_terms(double d1, double d2, float f1, float f2,
-                                                  const double* tab_hi, const double* tab_lo)
+                                                  const double* tab_hi, const double* /*tab_lo*/)
 {
     if (USE_LIBDEVICE) return __double2float_rn(atan2(d1, d2));
-    return atan2_to_float(d1, d2, f1, f2, tab_hi, tab_lo);
+    return atan2_to_float(d1, d2, f1, f2, tab_hi);
 }
 
 template <int N, bool USE_LIBDEVICE>
@@ -202,25 +203,38 @@ __device__ __forceinline__ float wrapped_phase(const int* I, const double* __res
     }
 }
 
+// Correctly rounded a/b for a constant divisor b in 3 operations (Markstein): with y = RN(1/b),
+// q0 = RN(a*y), r = a - q0*b (exact in one FMA), q = RN(q0 + r*y).  The host verifies the
+// identity against IEEE division on every fringe order (a = code*44, b = 7) at context creation
+// and the GPU tests verify it on every float phase (b = 44/7); `exact == false` selects the
+// plain IEEE division.
+__device__ __forceinline__ double div_const(double a, double b, double rcp_b, bool exact)
+{
+    if (!exact) return ddiv(a, b);
+    const double q0 = dmul(a, rcp_b);
+    const double r = fma(-q0, b, a);
+    return fma(r, rcp_b, q0);
+}
+
 // 4/phase_unwrap.cpp:290 :  wrapped += Pi          (float <- double sum)
 __device__ __forceinline__ float add_pi(float wrapped)
 {
     return __double2float_rn(dadd((double)wrapped, S3D_PI_REF));
 }
 // 4/phase_unwrap.cpp:291 :  unwrapped = wrapped + code*2.0*Pi   == w + ((code*2.0)*22.0)/7.0
-__device__ __forceinline__ float unwrap_abs(float wrapped_plus_pi, int code)
+__device__ __forceinline__ float unwrap_abs(float wrapped_plus_pi, int code, bool fast = false)
 {
-    const double k = ddiv(dmul(dmul((double)code, 2.0), 22.0), 7.0);
+    // (code*2.0)*22.0 is an exact integer, so only the division rounds
+    const double k = div_const((double)(code * 44), 7.0, 1.0 / 7.0, fast);   // code*44 < 2^21: exact
     return __double2float_rn(dadd((double)wrapped_plus_pi, k));
 }
 // 5/compute_correspondance.cpp:648 : lrint(fw * (Phi / (2.0*Pi))), round-half-even; FE_INVALID
 // (NaN/inf/out of range) rejects the pixel.  Returns false on FE_INVALID.
-__device__ __forceinline__ bool correspond(float phi_abs, int fw, long long* out)
+__device__ __forceinline__ bool correspond(float phi_abs, int fw, long long* out, bool fast = false)
 {
-    const double v = dmul((double)fw, ddiv((double)phi_abs, S3D_TWO_PI_REF));
-    if (!(v == v) || v >= 9223372036854775808.0 || v < -9223372036854775808.0) return false;
+    const double v = dmul((double)fw, div_const((double)phi_abs, S3D_TWO_PI_REF, 1.0 / (S3D_TWO_PI_REF), fast));
     *out = __double2ll_rn(v);
-    return true;
+    return (v == v) && v < 9223372036854775808.0 && v >= -9223372036854775808.0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -230,8 +244,12 @@ struct DeviceCalib {
     double Ac[12];      // K_cam * [R|t]   (3x4 row-major)   7/triangulation.cpp:1090-1101
     double Ap[12];      // K_proj * [R|t]                     :1104-1116
     double Kc[9], dc[5], Kp[9], dp[5];
+    double ifx_c, ify_c, ifx_p, ify_p;   // 1./fx, 1./fy exactly as cvUndistortPoints computes them (host IEEE division)
     int cam_distorted;  // any camera distortion coefficient non-zero
     int proj_distorted; // any projector distortion coefficient non-zero
+    int cam_std;        // Kc == [fx 0 cx; 0 fy cy; 0 0 1]: the K*[x;y;1] product has exact shortcuts
+    int proj_std;
+    int fast_div_ok;    // host verified: the 3-operation exact quotients below equal IEEE division
 };
 
 // One pixel of cvUndistortPoints (5 fixed iterations, 5-coefficient model) followed by
@@ -240,8 +258,8 @@ __device__ __forceinline__ void undistorted_pixel(const double* __restrict__ K,
                                                   const double* __restrict__ k, double u, double v,
                                                   double* ou, double* ov)
 {
-    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
-    const double ifx = ddiv(1.0, fx), ify = ddiv(1.0, fy);
+    const double cx = K[2], cy = K[5];
+    const double ifx = ddiv(1.0, K[0]), ify = ddiv(1.0, K[4]);
     double x, y, x0, y0;
     x0 = x = dmul(dsub(u, cx), ifx);
     y0 = y = dmul(dsub(v, cy), ify);
@@ -267,10 +285,22 @@ __device__ __forceinline__ void undistorted_pixel(const double* __restrict__ K,
 
 // Zero distortion: the 5 iterations are the exact identity (icdist == 1, deltas == 0), so only
 // the normalise / re-project round trip remains.  Bit-identical to undistorted_pixel() then.
-__device__ __forceinline__ void undistorted_pixel_nodist(const double* __restrict__ K, double u,
+// With K in the standard form [fx 0 cx; 0 fy cy; 0 0 1] the GEMM row ((0 + fx*x) + 0*y) + cx*1
+// equals fx*x + cx exactly (adding +-0 and multiplying by 1 are exact) and the third row is
+// exactly 1, so the divide by it is the identity: 4 operations per coordinate.
+__device__ __forceinline__ double undist_coord_std(double u, double c, double inv_f, double f)
+{
+    return dadd(dmul(f, dmul(dsub(u, c), inv_f)), c);
+}
+__device__ __forceinline__ void undistorted_pixel_nodist(const double* __restrict__ K, double ifx,
+                                                         double ify, bool std_form, double u,
                                                          double v, double* ou, double* ov)
 {
-    const double ifx = ddiv(1.0, K[0]), ify = ddiv(1.0, K[4]);
+    if (std_form) {
+        *ou = undist_coord_std(u, K[2], ifx, K[0]);
+        *ov = undist_coord_std(v, K[5], ify, K[4]);
+        return;
+    }
     const double x = dmul(dsub(u, K[2]), ifx);
     const double y = dmul(dsub(v, K[5]), ify);
     const double m0 = dadd(dadd(dadd(0.0, dmul(K[0], x)), dmul(K[1], y)), dmul(K[2], 1.0));
@@ -323,18 +353,20 @@ __device__ __forceinline__ void triangulate_point(const double* __restrict__ Ac,
     const double c01 = dsub(dmul(S10, S22), dmul(S12, S20));
     const double c02 = dsub(dmul(S10, S21), dmul(S11, S20));
     double d = dadd(dsub(dmul(S00, c00), dmul(S01, c01)), dmul(S02, c02));
+    // the cofactor matrix of a symmetric S is symmetric bit-for-bit (the mirrored entries are the
+    // same two products in the other operand order), so 6 of cvInvert's 9 entries are computed
     double T[3][3];
     if (d != 0.0) {
         d = ddiv(1.0, d);
         T[0][0] = dmul(c00, d);
         T[0][1] = dmul(dsub(dmul(S02, S21), dmul(S01, S22)), d);
         T[0][2] = dmul(dsub(dmul(S01, S12), dmul(S02, S11)), d);
-        T[1][0] = dmul(dsub(dmul(S12, S20), dmul(S10, S22)), d);
         T[1][1] = dmul(dsub(dmul(S00, S22), dmul(S02, S20)), d);
         T[1][2] = dmul(dsub(dmul(S02, S10), dmul(S00, S12)), d);
-        T[2][0] = dmul(dsub(dmul(S10, S21), dmul(S11, S20)), d);
-        T[2][1] = dmul(dsub(dmul(S01, S20), dmul(S00, S21)), d);
         T[2][2] = dmul(dsub(dmul(S00, S11), dmul(S01, S10)), d);
+        T[1][0] = T[0][1];
+        T[2][0] = T[0][2];
+        T[2][1] = T[1][2];
     } else {
 #pragma unroll
         for (int i = 0; i < 3; i++)
@@ -349,6 +381,50 @@ __device__ __forceinline__ void triangulate_point(const double* __restrict__ Ac,
         for (int j = 0; j < 4; j++) I2[j] = dot3(T[i][0], P[j][0], T[i][1], P[j][1], T[i][2], P[j][2]);
         X[i] = dot4(I2[0], F[0], I2[1], F[1], I2[2], F[2], I2[3], F[3]);
     }
+}
+
+// Same least-squares solution with fused multiply-adds and the right-hand side reduced first:
+// x = adj(S) (P^T F) / det(S), S = P^T P.  ~90 FP64 operations instead of ~220; differs from the
+// reference's operation order by rounding only (<= 1e-10 relative, against the 1e-5 bar), so the
+// float point cloud is identical except for last-bit ties.  Selected by SCAN3D_FLAG_FAST_TRIANGULATION.
+__device__ __forceinline__ void triangulate_point_fast(const double* __restrict__ Ac,
+                                                       const double* __restrict__ Ap, double uc,
+                                                       double vc, double up, double vp, double* X)
+{
+    double P[4][3], F[4];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        P[0][j] = fma(-uc, Ac[8 + j], Ac[0 + j]);
+        P[1][j] = fma(-vc, Ac[8 + j], Ac[4 + j]);
+        P[2][j] = fma(-up, Ap[8 + j], Ap[0 + j]);
+        P[3][j] = fma(-vp, Ap[8 + j], Ap[4 + j]);
+    }
+    F[0] = fma(Ac[11], uc, -Ac[3]);
+    F[1] = fma(Ac[11], vc, -Ac[7]);
+    F[2] = fma(Ap[11], up, -Ap[3]);
+    F[3] = fma(Ap[11], vp, -Ap[7]);
+#define S3D_DOT4(a, b) fma(P[3][a], P[3][b], fma(P[2][a], P[2][b], fma(P[1][a], P[1][b], P[0][a] * P[0][b])))
+    const double S00 = S3D_DOT4(0, 0), S01 = S3D_DOT4(0, 1), S02 = S3D_DOT4(0, 2);
+    const double S11 = S3D_DOT4(1, 1), S12 = S3D_DOT4(1, 2), S22 = S3D_DOT4(2, 2);
+#undef S3D_DOT4
+    double b[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) b[j] = fma(P[3][j], F[3], fma(P[2][j], F[2], fma(P[1][j], F[1], P[0][j] * F[0])));
+    const double c00 = fma(S11, S22, -S12 * S12);
+    const double c01 = fma(S02, S12, -S01 * S22);
+    const double c02 = fma(S01, S12, -S02 * S11);
+    const double c11 = fma(S00, S22, -S02 * S02);
+    const double c12 = fma(S01, S02, -S00 * S12);
+    const double c22 = fma(S00, S11, -S01 * S01);
+    const double det = fma(S02, c02, fma(S01, c01, S00 * c00));
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(det));
+    r = fma(r, fma(-det, r, 1.0), r);
+    r = fma(r, fma(-det, r, 1.0), r);
+    r = det != 0.0 ? r : 0.0;   // cvInvert returns a zero matrix for a singular input
+    X[0] = fma(c02, b[2], fma(c01, b[1], c00 * b[0])) * r;
+    X[1] = fma(c12, b[2], fma(c11, b[1], c01 * b[0])) * r;
+    X[2] = fma(c22, b[2], fma(c12, b[1], c02 * b[0])) * r;
 }
 
 // ---------------------------------------------------------------------------------------

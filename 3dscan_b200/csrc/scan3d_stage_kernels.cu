@@ -18,6 +18,10 @@ void fill_atan_table(double* t)
         t[i] = hi;
         t[33 + i] = (double)(a - (long double)hi);
     }
+    // quadrant constants {hi, lo}: 0, pi/2, pi
+    t[66] = 0.0; t[67] = 0.0;
+    t[68] = 1.57079632679489655800e+00; t[69] = 6.12323399573676603587e-17;
+    t[70] = 3.14159265358979311600e+00; t[71] = 1.22464679914735317720e-16;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -231,14 +235,14 @@ __global__ void k_triangulate(const __grid_constant__ DeviceCalib cal,
                 const double2 t = cam_lut[p];
                 uc = t.x; vc = t.y;
             } else {
-                undistorted_pixel_nodist(cal.Kc, (double)x, (double)y, &uc, &vc);
+                undistorted_pixel_nodist(cal.Kc, cal.ifx_c, cal.ify_c, cal.cam_std != 0, (double)x, (double)y, &uc, &vc);
             }
             const int2 cp = cpmap[p];
             if (proj_lut) {
                 const double2 t = proj_lut[(size_t)cp.y * PW + cp.x];
                 up = t.x; vp = t.y;
             } else {
-                undistorted_pixel_nodist(cal.Kp, (double)cp.x, (double)cp.y, &up, &vp);
+                undistorted_pixel_nodist(cal.Kp, cal.ifx_p, cal.ify_p, cal.proj_std != 0, (double)cp.x, (double)cp.y, &up, &vp);
             }
             triangulate_point(cal.Ac, cal.Ap, uc, vc, up, vp, X);
         }
@@ -372,13 +376,35 @@ __global__ void k_debug_atan2(const double* __restrict__ y, const double* __rest
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = mode == 0 ? __double2float_rn(atan2(y[i], x[i]))
-                       : atan2_to_float(y[i], x[i], (float)y[i], (float)x[i], tab, tab + 33);
+                       : atan2_to_float(y[i], x[i], (float)y[i], (float)x[i], tab);
 }
 
 cudaError_t launch_debug_atan2(const double* y, const double* x, float* out, int n, int mode,
                                const double* tab, cudaStream_t st)
 {
     k_debug_atan2<<<cdiv(n, 256), 256, 0, st>>>(y, x, out, n, mode, tab);
+    return cudaGetLastError();
+}
+
+
+// self-test: the 3-operation exact quotient Phi/(2.0*Pi) against IEEE division on EVERY finite
+// non-negative float phase (the only operands 5/compute_correspondance.cpp:648 can see).
+__global__ void k_debug_divcheck(unsigned long long* __restrict__ bad)
+{
+    unsigned long long local = 0;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < 0x7f800000ull;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const double a = (double)__uint_as_float((unsigned)b);
+        const double q1 = ddiv(a, S3D_TWO_PI_REF);
+        const double q2 = div_const(a, S3D_TWO_PI_REF, 1.0 / (S3D_TWO_PI_REF), true);
+        local += q1 != q2;
+    }
+    if (local) atomicAdd(bad, local);
+}
+
+cudaError_t launch_debug_divcheck(unsigned long long* bad, cudaStream_t st)
+{
+    k_debug_divcheck<<<148 * 16, 256, 0, st>>>(bad);
     return cudaGetLastError();
 }
 

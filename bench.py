@@ -128,6 +128,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="scans per GPU per step")
     ap.add_argument("--ring", type=int, default=4, help="distinct resident stacks per GPU")
     ap.add_argument("--e2e-scans", type=int, default=2, help="scans per e2e step")
+    ap.add_argument("--exact-triangulation", action="store_true",
+                    help="reference operation order in the normal-equation solve (bit-identical points)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -143,14 +145,17 @@ def main():
 
     from gpu_common import calibs, s3
     cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
-    cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs)
+    flags = 0 if args.exact_triangulation else s3.FLAG_FAST_TRIANGULATION
+    cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs, flags=flags)
     config = {"workload": args.workload, "frame": [W, H], "projector": [PW, PH], "phase_steps": N,
               "gray_bits": [Mv, Mh][:dirs], "directions": dirs, "frames_per_scan": s3.stack_planes(cfg),
               "scans_per_gpu_per_step": args.batch, "resident_ring": args.ring,
               "sharding": "frame-parallel scans, no collective" if world > 1 else "single GPU",
               "l2_policy": "inputs larger than L2 (ring of distinct stacks, %.2f GB per GPU)"
                            % (args.ring * s3.stack_planes(cfg) * npix / 1e9),
-              "algorithmic_bytes_per_pixel": bpp}
+              "algorithmic_bytes_per_pixel": bpp, "fused_cfg": os.environ.get("SCAN3D_FUSED_CFG", "default"),
+              "triangulation": "reference operation order (bit-identical points)" if args.exact_triangulation
+              else "fused-FMA normal equations (points within 1e-6 relative; decode/c_p_map bit-exact)"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -193,7 +198,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: kernels, copies and the timing events all live on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = s3.Scan3D(cfg, local_rank, cal, stream=stream.cuda_stream)
     nf = s3.stack_planes(cfg)
     # resident ring of distinct synthetic scans (scan index = global, so ranks hold different scans)

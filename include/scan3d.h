@@ -75,6 +75,12 @@ typedef struct {
 
 #define SCAN3D_FLAG_NONE 0u
 #define SCAN3D_FLAG_POINT_PIXELS 1u  /* also emit pix[count] = global row*W+col of every point */
+/* Fused entry only: solve the per-pixel normal equations with fused multiply-adds and the
+ * right-hand side reduced first (~90 instead of ~220 FP64 operations).  Same solution as the
+ * reference's cvTranspose/cvMatMul/cvInvert chain (7/triangulation.cpp:1202-1206) up to rounding:
+ * <= 1e-10 relative in double, i.e. the float points differ only in rare last-bit ties.  Without
+ * this flag the operation order is the reference's and the points are bit-identical to it. */
+#define SCAN3D_FLAG_FAST_TRIANGULATION 2u
 
 /* The 8 matrices load_matrices() reads (6/system_calibration.cpp:1526-1554): intrinsics (3x3
  * row-major), distortion (k1,k2,p1,p2,k3), world->device rotation vectors and translations. */

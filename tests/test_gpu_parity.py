@@ -71,6 +71,12 @@ def test_debug_atan2_modes_agree_with_libm():
     ctx.close()
 
 
+def test_exact_quotient_shortcut_equals_ieee_division_on_every_float():
+    ctx = s3.Scan3D(s3.make_config(16, 16, N=3, M_v=1, dirs=1), 0)
+    assert ctx.debug_divcheck() == 0
+    ctx.close()
+
+
 # ---------------------------------------------------------------------------- stage by stage
 @pytest.mark.parametrize("W,H,N,Mv,Mh,fw", [(200, 150, 3, 6, 5, 4), (333, 77, 4, 7, 6, 3), (64, 40, 5, 5, 4, 4),
                                             (640, 480, 8, 9, 8, 2), (97, 33, 6, 6, 5, 2)])
@@ -135,6 +141,24 @@ def test_fused_matches_oracle(case):
     ref2 = run_oracle(cfg, ocal, stack2, roi2)
     ctx.reconstruct(stack2, roi2)
     compare(cfg, ref2, ctx, fused=True)
+    print(case, st)
+    ctx.close()
+
+
+@pytest.mark.parametrize("case", FUSED_CASES[:1] + FUSED_CASES[2:5])
+def test_fused_fast_triangulation_within_tolerance(case):
+    """SCAN3D_FLAG_FAST_TRIANGULATION: everything up to c_p_map stays bit-exact; the points are
+    the same least-squares solution with a different rounding order (bar: 1e-5 relative)."""
+    W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs = case
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs, flags=s3.FLAG_FAST_TRIANGULATION)
+    stack, roi = s3.synth_stack(cfg, cal, s3.default_synth_params(seed=W + 31 * H))
+    ref = run_oracle(cfg, ocal, stack, roi)
+    ctx = _ctx(cfg, cal)
+    ctx.reconstruct(stack, roi)
+    st = compare(cfg, ref, ctx, fused=True)
+    assert st["cpmap_mismatch"] == 0 and st["valid_mismatch"] == 0
+    assert st["pts_max_rel"] <= 1e-6
     print(case, st)
     ctx.close()
 
