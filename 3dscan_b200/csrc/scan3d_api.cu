@@ -3,6 +3,7 @@
 // compute entry launches CUDA kernels and fails with SCAN3D_ERR_CUDA when that is impossible.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -144,6 +145,12 @@ int scan3d_create(const scan3d_config* cfg, int device, scan3d_ctx** out)
         const int ntiles = fused_num_tiles(ctx->cfg);
         CK(dalloc(&ctx->tile_state, (size_t)ntiles + 1));
         CK(cudaMemsetAsync(ctx->tile_state, 0, ((size_t)ntiles + 1) * 8, ctx->stream));
+        if (getenv("SCAN3D_TRACE")) {
+            CK(dalloc(&ctx->trace, (size_t)1024 * 64 * 8));
+            CK(cudaMemsetAsync(ctx->trace, 0, (size_t)1024 * 64 * 8 * 8, ctx->stream));
+        }
+        CK(dalloc(&ctx->tile_flags, (size_t)ntiles + 16));
+        CK(dalloc(&ctx->tile_list, (size_t)ntiles + 16));
         CK(dalloc(&ctx->atan_tab, (size_t)ATAN_TAB_DOUBLES));
         double tab[ATAN_TAB_DOUBLES];
         fill_atan_table(tab);
@@ -191,7 +198,7 @@ void scan3d_destroy(scan3d_ctx* ctx)
     void* ptrs[] = {ctx->cam_lut, ctx->proj_lut, ctx->atan_tab, ctx->nstep_w, ctx->wrapped[0], ctx->wrapped[1],
                     ctx->unwrapped[0], ctx->unwrapped[1], ctx->code[0], ctx->code[1], ctx->mask[0],
                     ctx->mask[1], ctx->valid, ctx->cpmap, ctx->xyz, ctx->pts, ctx->pix, ctx->rgb,
-                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->d_stack, ctx->d_roi};
+                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -468,7 +475,7 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     a.valid = ctx->valid; a.cpmap = ctx->cpmap;
     a.pts = ctx->pts; a.pix = ctx->pix;
     a.rgb = ctx->texture ? ctx->rgb : nullptr; a.texture = ctx->texture;
-    a.d_count = ctx->d_count; a.tile_state = ctx->tile_state;
+    a.d_count = ctx->d_count; a.tile_state = ctx->tile_state; a.trace = ctx->trace; a.tile_flags = ctx->tile_flags; a.tile_list = ctx->tile_list + 1; a.n_list = ctx->tile_list;
     a.cam_lut = ctx->cam_lut; a.proj_lut = ctx->proj_lut; a.atan_tab = ctx->atan_tab;
     a.epoch = ++ctx->epoch;
     if ((ctx->epoch & 0x3fffffffu) == 0) {   // epoch wrapped: clear the look-back words once
@@ -478,7 +485,7 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     a.W = c.W; a.H = c.H; a.row0 = c.row0; a.H_total = c.H_total; a.PW = c.PW; a.PH = c.PH;
     a.N = c.N; a.M_v = c.M_v; a.M_h = c.M_h; a.fw_v = c.fw_v; a.fw_h = c.fw_h;
     CK(launch_fused(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
-    ctx->launches++;
+    ctx->launches += 3;   // work-list flags, work-list scan, persistent fused kernel
     ctx->have_wrapped[0] = ctx->have_wrapped[1] = false;
     ctx->have_unwrapped[0] = true;
     ctx->have_unwrapped[1] = c.dirs == 2;
@@ -662,6 +669,17 @@ int scan3d_debug_atan2(scan3d_ctx* ctx, const double* y_host, const double* x_ho
     CK(cudaMemcpyAsync(out_host, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(dy); cudaFree(dx); cudaFree(dout);
+    return SCAN3D_OK;
+}
+
+// ---- diagnostics: pipeline timeline of the last fused launch (needs SCAN3D_TRACE=1 at create) ----
+int scan3d_debug_get_trace(scan3d_ctx* ctx, uint64_t* out_host, int64_t n_words)
+{
+    if (!ctx || !out_host || !ctx->trace) return fail(ctx, SCAN3D_ERR_STATE, "tracing is not enabled");
+    CK(cudaSetDevice(ctx->device));
+    if (n_words > 1024 * 64 * 8) n_words = 1024 * 64 * 8;
+    CK(cudaMemcpyAsync(out_host, ctx->trace, (size_t)n_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return SCAN3D_OK;
 }
 

@@ -32,13 +32,13 @@ namespace s3d {
 constexpr int ROI_HALO = 16;               // bytes of halo each side (16 B aligned bulk copies)
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int MAX_STAGES = 4;
-constexpr int SMEM_FIXED = 3 * MAX_STAGES * 8 + ATAN_TAB_DOUBLES * 8 + 32;   // barriers + atan table + pad
+constexpr int SMEM_FIXED = 3 * MAX_STAGES * 8 + ATAN_TAB_DOUBLES * 8 + MAX_STAGES * 4 + MAX_STAGES * 8 * 4 + 32;   // barriers + atan table + slot tile ids + per-slot warp counts + pad
 
 struct TileGeom {
     int T;            // pixels per tile
     int roi_row;      // T + 2*halo
     int roi_bytes;    // 4 rows
-    int out_unwv, out_codev, out_valid, out1_bytes, out_unwh, out_codeh, out_cp, out_x, out2_bytes;
+    int out_unwv, out_codev, out_valid, out1_bytes, out_unwh, out_codeh, out_cp, out_x, out_cx, out2_bytes;
 };
 __host__ __device__ constexpr TileGeom geom_of(int T)
 {
@@ -54,7 +54,8 @@ __host__ __device__ constexpr TileGeom geom_of(int T)
     g.out_codeh = g.out_unwh + 4 * T;
     g.out_cp = g.out_codeh + 2 * T;
     g.out_x = g.out_cp + 8 * T;
-    g.out2_bytes = g.out_x + 12 * T;
+    g.out_cx = g.out_x + 12 * T;            // the tile's points, compacted in raster order
+    g.out2_bytes = g.out_cx + 12 * T;
     return g;
 }
 
@@ -148,10 +149,21 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
     return done != 0;
 }
 // poll with back-off so that a waiting warp does not steal issue slots from the computing ones
+// (one copy per warp role so that profiles attribute the waiting to the right role)
+#define S3D_WAIT_BODY                                        \
+    if (mbar_try(bar, parity)) return;                      \
+    while (!mbar_try(bar, parity)) __nanosleep(128);
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    if (mbar_try(bar, parity)) return;
-    while (!mbar_try(bar, parity)) __nanosleep(128);
+    S3D_WAIT_BODY
+}
+__device__ __forceinline__ void mbar_wait_consumer(uint32_t bar, uint32_t parity)
+{
+    S3D_WAIT_BODY
+}
+__device__ __forceinline__ void mbar_wait_epilogue(uint32_t bar, uint32_t parity)
+{
+    S3D_WAIT_BODY
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
 {
@@ -279,7 +291,85 @@ __device__ __forceinline__ int sat32(long long v)
     return (int)max(min(v, 2147483647LL), -2147483648LL);
 }
 
-// ---- the kernel --------------------------------------------------------------------------------
+// ---- work list: tiles that contain at least one ROI pixel ---------------------------------------
+// One warp per tile looks at the tile's ROI bytes.  Tiles without any selected pixel never enter
+// the main kernel: their outputs (phase 0, fringe order -1, valid 0, c_p_map 0) are written right
+// here and their 56 input frame segments are never read.  The flags are then compacted, in raster
+// order, into the work list the persistent kernel walks in phase-aligned rounds.
+__global__ void k_tile_flags(const uint8_t* __restrict__ roi, int T, int plane, int n_tiles, size_t roi_off,
+                             uint8_t* __restrict__ flags, float* __restrict__ unw_v, float* __restrict__ unw_h,
+                             int16_t* __restrict__ code_v, int16_t* __restrict__ code_h, uint8_t* __restrict__ valid,
+                             int2* __restrict__ cpmap, int dirs)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= n_tiles) return;
+    const int p0 = t * T, wt = min(T, plane - p0);
+    const uint4* r = reinterpret_cast<const uint4*>(roi + roi_off + p0);
+    bool any = false;
+    for (int i = lane; i < wt / 16; i += 32) {
+        const uint4 v = r[i];
+        any |= (v.x | v.y | v.z | v.w) != 0;
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) flags[t] = any ? 1 : 0;
+    if (any) return;
+    const uint4 z = make_uint4(0, 0, 0, 0), m1 = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (int i = lane; i < wt / 4; i += 32) {       // 4 floats
+        reinterpret_cast<uint4*>(unw_v + p0)[i] = z;
+        if (dirs == 2) reinterpret_cast<uint4*>(unw_h + p0)[i] = z;
+    }
+    for (int i = lane; i < wt / 8; i += 32) {       // 8 int16 = -1
+        reinterpret_cast<uint4*>(code_v + p0)[i] = m1;
+        if (dirs == 2) reinterpret_cast<uint4*>(code_h + p0)[i] = m1;
+    }
+    for (int i = lane; i < wt / 16; i += 32) reinterpret_cast<uint4*>(valid + p0)[i] = z;
+    if (dirs == 2)
+        for (int i = lane; i < wt / 2; i += 32) reinterpret_cast<uint4*>(cpmap + p0)[i] = z;
+}
+
+// exclusive scan of the flags by one CTA -> list of non-empty tile ids (raster order) + its length
+__global__ void k_tile_list(const uint8_t* __restrict__ flags, int n_tiles, int* __restrict__ list,
+                            int* __restrict__ n_list, uint32_t* __restrict__ d_count)
+{
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) { carry = 0; *d_count = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int f = i < n_tiles ? flags[i] : 0;
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wsum[w] = __popc(b);
+        __syncthreads();
+        if (w == 0) {
+            int v = wsum[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            wsum[lane] = v;   // inclusive
+        }
+        __syncthreads();
+        const int c = carry;
+        if (f) list[c + (w ? wsum[w - 1] : 0) + __popc(b & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + wsum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_list = carry;
+}
+
+// optional per-CTA timeline (SCAN3D_TRACE=1): clock64 stamps of the pipeline events of the first
+// TRACE_TILES tiles of every CTA; slot = (cta * TRACE_TILES + it) * 8 + event
+constexpr int TRACE_TILES = 64;
+__device__ __forceinline__ void trace(unsigned long long* t, int it, int ev)
+{
+    if (t && it < TRACE_TILES) t[((size_t)blockIdx.x * TRACE_TILES + it) * 8 + ev] = clock64();
+}
+
+// ---- the kernel ----// ---- the kernel --------------------------------------------------------------------------------
 template <int N, int DIRS, int CW, int MINB, bool EXACT>
 __global__ void __launch_bounds__((CW + 2) * 32, MINB)
 k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal, const int stages,
@@ -293,6 +383,8 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
     double* tab = reinterpret_cast<double*>(bars + 3 * MAX_STAGES);
+    volatile int* slot_tile = reinterpret_cast<volatile int*>(tab + ATAN_TAB_DOUBLES);   // tile held by each slot (-1: no more work)
+    volatile uint32_t* slot_cnt = reinterpret_cast<volatile uint32_t*>(const_cast<int*>(slot_tile) + MAX_STAGES);   // [slot][warp] valid points
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES),
                    bar_staged = smem_u32(bars + 2 * MAX_STAGES);
 
@@ -314,15 +406,29 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
     for (int i = tid; i < ATAN_TAB_DOUBLES; i += (CW + 2) * 32) tab[i] = a.atan_tab[i];
     __syncthreads();
 
-    const int first = blockIdx.x;
-    const int my_tiles = first < a.n_tiles ? (a.n_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-
+    // Static, phase-aligned schedule over the work list (tiles holding ROI pixels, raster order):
+    // in round r the grid works on list entries [r*G, (r+1)*G), so the tiles a look-back has to wait
+    // for are always being computed at the same time (a dynamic scheduler de-phases the CTAs and,
+    // with a 2-slot pipeline, turns the in-order look-back into a convoy: measured 4x slower).
+    // The producer publishes each slot's list position; -1 ends every role's loop.  The look-back
+    // chain runs over list positions; `tile` below is the pixel tile the entry points to.
+    const int n_work = *a.n_list;
     if (warp == CW) {
         // ================================ PRODUCER ================================
         const long long roi_total = (long long)W * a.H_total;
-        for (int it = 0; it < my_tiles; it++) {
-            const int tile = first + it * (int)gridDim.x;
+        for (int it = 0;; it++) {
             const int s = it % stages, ph = (it / stages) & 1;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            if (lane == 0) trace(a.trace, it, 0);
+            const int pos = it * (int)gridDim.x + (int)blockIdx.x;
+            if (pos >= n_work) {
+                if (lane == 0) {
+                    slot_tile[s] = -1;
+                    mbar_arrive(bar_full + 8 * s);
+                }
+                break;
+            }
+            const int tile = a.tile_list[pos];
             const int p0 = tile * T, wt = min(T, plane - p0);
             // ROI window: 4 linear segments, one per row offset dr = -2..+1, each covering the
             // tile's pixels shifted by dr rows plus a 16-byte halo on both sides
@@ -338,9 +444,11 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
             roi_sum += __shfl_xor_sync(0xffffffffu, roi_sum, 1);
             roi_sum += __shfl_xor_sync(0xffffffffu, roi_sum, 2);
             roi_sum = __shfl_sync(0xffffffffu, roi_sum, 0);
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);
             const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
-            if (lane == 0) mbar_expect_tx(bar_full + 8 * s, (uint32_t)NF * wt + roi_sum);
+            if (lane == 0) {
+                slot_tile[s] = pos;
+                mbar_expect_tx(bar_full + 8 * s, (uint32_t)NF * wt + roi_sum);
+            }
             __syncwarp();
             const uint8_t* src = a.stack + p0;
             for (int f = lane; f < NF; f += 32)
@@ -349,6 +457,7 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
                 bulk_g2s(dst + (stage_bytes - G.roi_bytes) + lane * G.roi_row +
                              (uint32_t)(seg0 - (gbase + (long long)(lane - 2) * W)),
                          a.roi + seg0, roi_tx, bar_full + 8 * s);
+            if (lane == 0) trace(a.trace, it, 1);
         }
         return;
     }
@@ -356,12 +465,14 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
     if (warp == CW + 1) {
         // ================================ EPILOGUE ================================
         const unsigned long long tag = (unsigned long long)(a.epoch & 0x3fffffffu) << 34;
-        for (int it = 0; it < my_tiles; it++) {
-            const int tile = first + it * (int)gridDim.x;
+        for (int it = 0;; it++) {
             const int s = it % stages, ph = (it / stages) & 1;
-            const int p0 = tile * T, wt = min(T, plane - p0);
+            mbar_wait_epilogue(bar_staged + 8 * s, ph);
+            if (lane == 0) trace(a.trace, it, 5);
+            const int tile = slot_tile[s];           // position in the work list == look-back index
+            if (tile < 0) break;
+            const int p0 = a.tile_list[tile] * T, wt = min(T, plane - p0);
             uint8_t* stage = smem + (size_t)s * stage_bytes;
-            mbar_wait(bar_staged + 8 * s, ph);
             if (lane == 0) {
                 bulk_s2g(a.unw_v + p0, smem_u32(stage + G.out_unwv), 4u * wt);
                 bulk_s2g(a.code_v + p0, smem_u32(stage + G.out_codev), 2u * wt);
@@ -374,18 +485,13 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
                 bulk_commit();
             }
             if (DIRS == 2) {
-                // ---- tile total (valid flags are 0/1 bytes: popc of the packed words) ----
+                // ---- tile total: the consumers left one count per warp ----
                 const uint32_t* vw = reinterpret_cast<const uint32_t*>(stage + G.out_valid);
-                uint32_t total = 0;
-#pragma unroll
-                for (int k = 0; k < CW; k++) {
-                    const int w = k * 32 + lane;
-                    total += (4 * w < wt) ? __popc(vw[w]) : 0;
-                }
+                uint32_t total = lane < CW ? slot_cnt[s * 8 + lane] : 0u;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
                 // ---- decoupled look-back: exclusive prefix of the valid counts of tiles < tile ----
-                const bool last = tile == a.n_tiles - 1;
+                const bool last = tile == n_work - 1;
                 uint32_t excl = 0;
                 if (total == 0 && !last && tile > 0) {
                     // an empty tile has nothing to scatter: it never waits.  If its predecessor's
@@ -425,38 +531,48 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
                         if (last) *a.d_count = excl + total;
                     }
                 }
-                // ---- raster-ordered scatter (8/save_point_cloud.cpp:85-136), 4 pixels per lane ----
+                if (lane == 0) trace(a.trace, it, 6);
+                // ---- the tile's points are already compacted in the slot: stream them out as one
+                //      contiguous block at the tile's offset (8/save_point_cloud.cpp:85-136) ----
                 if (total) {
-                    const float* xs = reinterpret_cast<const float*>(stage + G.out_x);
-                    uint32_t run = excl;
-#pragma unroll 1
-                    for (int k = 0; k < CW; k++) {
-                        const int w = k * 32 + lane, lp = 4 * w;
-                        const uint32_t f = lp < wt ? vw[w] : 0u;
-                        const uint32_t cnt = __popc(f);
-                        uint32_t incl = cnt;
+                    const float* cx = reinterpret_cast<const float*>(stage + G.out_cx);
+                    float* dst = a.pts + 3 * (size_t)excl;
+                    const int n = 3 * (int)total;
+                    // head so that the body is 16-byte aligned in global memory
+                    const int head = min(n, (int)((4 - (((uintptr_t)dst >> 2) & 3)) & 3));
+                    if (lane < head) dst[lane] = cx[lane];
+                    const int nvec = (n - head) >> 2;
+                    for (int v = lane; v < nvec; v += 32) {
+                        const int i = head + 4 * v;
+                        *reinterpret_cast<float4*>(dst + i) = make_float4(cx[i], cx[i + 1], cx[i + 2], cx[i + 3]);
+                    }
+                    const int tail0 = head + 4 * nvec;
+                    if (lane < n - tail0) dst[tail0 + lane] = cx[tail0 + lane];
+                    if (a.pix || a.rgb) {      // optional per-point extras: slow path over the flags
+                        uint32_t run = excl;
+                        for (int k = 0; k < CW; k++) {
+                            const int w = k * 32 + lane, lp = 4 * w;
+                            const uint32_t f = lp < wt ? vw[w] : 0u;
+                            const uint32_t cnt = __popc(f);
+                            uint32_t incl = cnt;
 #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                            if (lane >= o) incl += t;
-                        }
-                        uint32_t dstp = run + incl - cnt;
-                        run += __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if ((f >> (8 * j)) & 1u) {
-                                float* o = a.pts + 3 * (size_t)dstp;
-                                o[0] = xs[3 * (lp + j) + 0];
-                                o[1] = xs[3 * (lp + j) + 1];
-                                o[2] = xs[3 * (lp + j) + 2];
-                                const size_t gp = (size_t)p0 + lp + j;
-                                if (a.pix) a.pix[dstp] = (uint32_t)((size_t)a.row0 * W + gp);
-                                if (a.rgb) {
-                                    a.rgb[3 * (size_t)dstp + 0] = a.texture[3 * gp + 2];
-                                    a.rgb[3 * (size_t)dstp + 1] = a.texture[3 * gp + 1];
-                                    a.rgb[3 * (size_t)dstp + 2] = a.texture[3 * gp + 0];
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                                if (lane >= o) incl += t;
+                            }
+                            uint32_t dstp = run + incl - cnt;
+                            run += __shfl_sync(0xffffffffu, incl, 31);
+                            for (int j = 0; j < 4; j++) {
+                                if ((f >> (8 * j)) & 1u) {
+                                    const size_t gp = (size_t)p0 + lp + j;
+                                    if (a.pix) a.pix[dstp] = (uint32_t)((size_t)a.row0 * W + gp);
+                                    if (a.rgb) {
+                                        a.rgb[3 * (size_t)dstp + 0] = a.texture[3 * gp + 2];
+                                        a.rgb[3 * (size_t)dstp + 1] = a.texture[3 * gp + 1];
+                                        a.rgb[3 * (size_t)dstp + 2] = a.texture[3 * gp + 0];
+                                    }
+                                    dstp++;
                                 }
-                                dstp++;
                             }
                         }
                     }
@@ -465,6 +581,7 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
             __syncwarp();
             if (lane == 0) {
                 bulk_wait_read();                    // the TMA stores have read the slot
+                trace(a.trace, it, 7);
                 mbar_arrive(bar_empty + 8 * s);      // hand it back to the producer
             }
         }
@@ -473,10 +590,17 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
     }
 
     // ================================ CONSUMERS ================================
-    for (int it = 0; it < my_tiles; it++) {
-        const int tile = first + it * (int)gridDim.x;
+    for (int it = 0;; it++) {
         const int s = it % stages, ph = (it / stages) & 1;
-        const int p0 = tile * T, wt = min(T, plane - p0);
+        mbar_wait_consumer(bar_full + 8 * s, ph);
+        if (tid == 0) trace(a.trace, it, 2);
+        const int tile = slot_tile[s];
+        if (tile < 0) {                          // no more work: pass the end marker to the epilogue
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_staged + 8 * s);
+            break;
+        }
+        const int p0 = a.tile_list[tile] * T, wt = min(T, plane - p0);
         const int lp0 = 4 * tid;                 // first of this thread's 4 pixels inside the tile
         const bool active = lp0 < wt;
         const int row = (p0 + lp0) / W;          // the 4 pixels share a row (W % 4 == 0)
@@ -485,8 +609,6 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
         uint8_t* stage = smem + (size_t)s * stage_bytes;
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage);
         const uint8_t* sroi = stage + (stage_bytes - G.roi_bytes);
-
-        mbar_wait(bar_full + 8 * s, ph);
 
         // ---------------- integer phase: mask, fringe terms, Gray bits ----------------
         uint32_t mbits = 0;
@@ -537,6 +659,7 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
         // every consumer is done reading this slot's inputs: they are overwritten by the staged
         // outputs below
         cons_sync<NCONS>();
+        if (tid == 0) trace(a.trace, it, 3);
 
         // ---------------- FP64 phase, one pixel at a time, results staged in the slot ----------------
         float* o_unwv = reinterpret_cast<float*>(stage + G.out_unwv);
@@ -546,6 +669,7 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
         int16_t* o_codeh = reinterpret_cast<int16_t*>(stage + G.out_codeh);
         int2* o_cp = reinterpret_cast<int2*>(stage + G.out_cp);
         float* o_x = reinterpret_cast<float*>(stage + G.out_x);
+        uint32_t vbits = 0;
         if (active) {
 #pragma unroll 1
             for (int j = 0; j < 4; j++) {
@@ -599,10 +723,39 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
                     }
                 }
                 o_valid[lp] = v ? 1 : 0;
+                vbits |= (v ? 1u : 0u) << j;
+            }
+        }
+        if (DIRS == 2) {
+            // ---- tile-local compaction: block scan of the valid counts, then every thread moves
+            //      its points to their raster rank inside the slot ----
+            const uint32_t cnt = __popc(vbits);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) slot_cnt[s * 8 + warp] = incl;
+            cons_sync<NCONS>();
+            uint32_t rank = incl - cnt;
+#pragma unroll
+            for (int w2 = 0; w2 < CW; w2++) rank += w2 < warp ? slot_cnt[s * 8 + w2] : 0u;
+            float* cx = reinterpret_cast<float*>(stage + G.out_cx);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if ((vbits >> j) & 1u) {
+                    const int lp = lp0 + j;
+                    cx[3 * rank + 0] = o_x[3 * lp + 0];
+                    cx[3 * rank + 1] = o_x[3 * lp + 1];
+                    cx[3 * rank + 2] = o_x[3 * lp + 2];
+                    rank++;
+                }
             }
         }
         fence_async_smem();   // staged outputs -> visible to the async (TMA) proxy
         __syncwarp();
+        if (tid == 0) trace(a.trace, it, 4);
         if (lane == 0) mbar_arrive(bar_staged + 8 * s);
     }
 }
@@ -621,6 +774,10 @@ static cudaError_t launch_fused_t(const FusedArgs& a, const DeviceCalib& cal, in
     if (per_sm > MINB) per_sm = MINB;
     // every CTA must be resident (the look-back chain waits on earlier tiles)
     const int grid = a.n_tiles < sm_count * per_sm ? a.n_tiles : sm_count * per_sm;
+    constexpr int T = 128 * CW;
+    k_tile_flags<<<(a.n_tiles + 7) / 8, 256, 0, st>>>(a.roi, T, a.W * a.H, a.n_tiles, (size_t)a.row0 * a.W, a.tile_flags,
+                                                      a.unw_v, a.unw_h, a.code_v, a.code_h, a.valid, a.cpmap, DIRS);
+    k_tile_list<<<1, 1024, 0, st>>>(a.tile_flags, a.n_tiles, a.tile_list, a.n_list, a.d_count);
     kern<<<grid, (CW + 2) * 32, p.smem, st>>>(a, cal, p.stages, p.stage_bytes);
     return cudaGetLastError();
 }

@@ -46,6 +46,9 @@ struct scan3d_ctx {
     uint32_t* d_count = nullptr;   // [1]
     uint32_t* block_counts = nullptr;  // stage-API compaction scratch
     unsigned long long* tile_state = nullptr;  // fused kernel decoupled look-back
+    uint8_t* tile_flags = nullptr;             // fused kernel work list (see k_tile_flags)
+    int* tile_list = nullptr;
+    unsigned long long* trace = nullptr;       // SCAN3D_TRACE=1: per-CTA pipeline timeline
     uint32_t epoch = 0;
 
     // staging for the host-buffer entries
@@ -107,6 +110,10 @@ struct FusedArgs {
     float* pts; uint32_t* pix; uint8_t* rgb; const uint8_t* texture;
     uint32_t* d_count;
     unsigned long long* tile_state;
+    uint8_t* tile_flags;          // [n_tiles] tile holds at least one ROI pixel
+    int* tile_list;               // [n_tiles] ids of those tiles, raster order
+    int* n_list;                  // [1]
+    unsigned long long* trace;    // optional timeline buffer (SCAN3D_TRACE), else null
     const double2* cam_lut; const double2* proj_lut;
     const double* atan_tab;
     uint32_t epoch;

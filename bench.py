@@ -248,13 +248,15 @@ def main():
     value = total_pix / (ms_max * 1e-3) / 1e6
 
     # ---- roofline of the dominant (only) kernel: algorithmic bytes per launch / avg launch time
-    per_launch_s = ms * 1e-3 / max(launches, 1)
+    # per scan: 2 tiny work-list kernels + the persistent fused kernel; the whole scan time is
+    # charged to the fused kernel (conservative: its own duration is slightly shorter)
+    per_launch_s = ms * 1e-3 / (args.steps * args.batch)
     peak, peak_kind = measured_peak_gbs()
     achieved = bpp * npix / per_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload), "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
                 "kernel": "s3d::k_fused<%d,%d>" % (N, dirs), "algorithmic_bytes_per_launch": bpp * npix,
-                "avg_launch_us": per_launch_s * 1e6, "frac_of_8TBs_nominal": achieved / 8000.0}
+                "avg_launch_us": per_launch_s * 1e6, "launches_per_scan": launches / (args.steps * args.batch), "frac_of_8TBs_nominal": achieved / 8000.0}
 
     # ---- e2e: host-buffer entry, pinned input, H2D + kernel + D2H of the point cloud per scan
     e2e = None
