@@ -32,7 +32,7 @@ namespace s3d {
 constexpr int ROI_HALO = 16;               // bytes of halo each side (16 B aligned bulk copies)
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int MAX_STAGES = 4;
-constexpr int SMEM_FIXED = 3 * MAX_STAGES * 8 + ATAN_TAB_DOUBLES * 8 + MAX_STAGES * 4 + MAX_STAGES * 8 * 4 + 32;   // barriers + atan table + slot tile ids + per-slot warp counts + pad
+constexpr int SMEM_FIXED = 3 * MAX_STAGES * 8 + ATAN_TAB_DOUBLES * 8 + MAX_STAGES * 4 + MAX_STAGES * 8 * 4 + 16;   // barriers + atan table + slot tile ids + per-slot warp counts + pad
 
 struct TileGeom {
     int T;            // pixels per tile
@@ -76,13 +76,14 @@ struct FusedPlan {
     size_t smem;
 };
 
-// Launch shape: consumer warps per CTA, CTAs per SM, pipeline slots.  Default picked from the
-// sweep in profiles/; SCAN3D_FUSED_CFG="cw,ctas_per_sm,stages" overrides it for tuning runs.
+// Launch shape: consumer warps per CTA, CTAs per SM, pipeline slots.  Default (6 consumer warps,
+// 2 CTAs/SM, 2 slots = 12 consumer warps per SM at 128 registers) picked from the sweep recorded in
+// profiles/; SCAN3D_FUSED_CFG="cw,ctas_per_sm,stages" overrides it for tuning runs.
 static bool plan_for(const scan3d_config& c, FusedPlan* out)
 {
     if (c.W % 16 != 0) return false;
     if (!(c.N == 3 || c.N == 4 || c.N == 5 || c.N == 8)) return false;
-    int cw = 4, minb = 3, stages = 2;
+    int cw = 6, minb = 2, stages = 2;
     if (const char* e = getenv("SCAN3D_FUSED_CFG")) {
         int a = 0, b = 0, s = 0;
         if (sscanf(e, "%d,%d,%d", &a, &b, &s) == 3) { cw = a; minb = b; stages = s; }
@@ -91,13 +92,14 @@ static bool plan_for(const scan3d_config& c, FusedPlan* out)
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     // instantiated launch shapes (consumer warps, CTAs/SM): the requested one first, then the
     // rest from most to least parallel; first one whose slots fit in shared memory wins
-    const int shapes[5][2] = {{cw, minb}, {4, 3}, {6, 2}, {4, 2}, {8, 1}};
-    for (int i = 0; i < 5; i++) {
+    const int shapes[4][2] = {{cw, minb}, {6, 2}, {4, 2}, {8, 1}};
+    for (int i = 0; i < 4; i++) {
         const int w = shapes[i][0], b = shapes[i][1];
-        if (!((w == 4 && b == 3) || (w == 6 && b == 2) || (w == 4 && b == 2) || (w == 8 && b == 1))) continue;
+        if (!((w == 6 && b == 2) || (w == 4 && b == 2) || (w == 8 && b == 1))) continue;
         for (int st = stages; st >= 2; st--) {
             const int sb = stage_bytes_of(c, 128 * w);
-            const size_t smem = (size_t)st * sb + SMEM_FIXED;
+            // slots + fixed area + (both directions) the epilogue's private copy of one tile's points
+            const size_t smem = (size_t)st * sb + SMEM_FIXED + (c.dirs == 2 ? 12 * 128 * w : 0);
             if ((smem + 1024) * b <= (size_t)SMEM_MAX + 1024) {   // 1 KB per CTA is reserved by the runtime
                 out->cw = w; out->minb = b; out->stages = st; out->stage_bytes = sb; out->smem = smem;
                 return true;
@@ -370,8 +372,15 @@ __device__ __forceinline__ void trace(unsigned long long* t, int it, int ev)
 }
 
 // ---- the kernel ----// ---- the kernel --------------------------------------------------------------------------------
+// registers per thread for a launch shape: the whole register file split over MINB resident CTAs
+constexpr int regs_for(int cw, int minb)
+{
+    const int r = 65536 / (minb * (cw + 2) * 32);
+    return r > 255 ? 255 : (r / 8) * 8;
+}
+
 template <int N, int DIRS, int CW, int MINB, bool EXACT>
-__global__ void __launch_bounds__((CW + 2) * 32, MINB)
+__global__ void __launch_bounds__((CW + 2) * 32) __maxnreg__(regs_for(CW, MINB))
 k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal, const int stages,
         const int stage_bytes)
 {
@@ -385,6 +394,9 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
     double* tab = reinterpret_cast<double*>(bars + 3 * MAX_STAGES);
     volatile int* slot_tile = reinterpret_cast<volatile int*>(tab + ATAN_TAB_DOUBLES);   // tile held by each slot (-1: no more work)
     volatile uint32_t* slot_cnt = reinterpret_cast<volatile uint32_t*>(const_cast<int*>(slot_tile) + MAX_STAGES);   // [slot][warp] valid points
+    // epilogue-private buffer for one tile's compacted points (lets the slot go back to the
+    // producer before the look-back has resolved); 16-byte aligned right after the fixed area
+    float* xbuf = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes + SMEM_FIXED);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES),
                    bar_staged = smem_u32(bars + 2 * MAX_STAGES);
 
@@ -490,11 +502,28 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
                 uint32_t total = lane < CW ? slot_cnt[s * 8 + lane] : 0u;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-                // ---- decoupled look-back: exclusive prefix of the valid counts of tiles < tile ----
+                // ---- publish the aggregate at once, take a private copy of the points and hand the
+                //      slot back: the look-back below then overlaps the next tile's compute ----
                 const bool last = tile == n_work - 1;
+                const bool resolve = total != 0 || last || tile == 0;
+                if (tile > 0 && resolve && lane == 0) st_state(a.tile_state + tile, tag | (1ull << 32) | total);
+                if (total) {
+                    const float4* cx4 = reinterpret_cast<const float4*>(stage + G.out_cx);
+                    float4* xb4 = reinterpret_cast<float4*>(xbuf);
+                    const int nv = (3 * (int)total + 3) >> 2;
+                    for (int v = lane; v < nv; v += 32) xb4[v] = cx4[v];
+                }
+                __syncwarp();
+                const bool extras = a.pix != nullptr || a.rgb != nullptr;   // they need the slot's flags later
+                if (!extras && lane == 0) {
+                    bulk_wait_read();                    // the TMA stores have read the slot
+                    trace(a.trace, it, 7);
+                    mbar_arrive(bar_empty + 8 * s);      // hand it back to the producer
+                }
+                // ---- decoupled look-back: exclusive prefix of the valid counts of tiles < tile ----
                 uint32_t excl = 0;
-                if (total == 0 && !last && tile > 0) {
-                    // an empty tile has nothing to scatter: it never waits.  If its predecessor's
+                if (!resolve) {
+                    // an empty tile has nothing to write: it never waits.  If its predecessor's
                     // inclusive prefix happens to be there it forwards it, else it posts aggregate 0.
                     if (lane == 0) {
                         const unsigned long long w = ld_state(a.tile_state + tile - 1);
@@ -503,7 +532,6 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
                     }
                 } else {
                     if (tile > 0) {
-                        if (lane == 0) st_state(a.tile_state + tile, tag | (1ull << 32) | total);
                         int look = tile - 1;
                         while (true) {
                             const int idx = look - lane;
@@ -511,7 +539,7 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
                             if (idx >= 0) {
                                 w = ld_state(a.tile_state + idx);
                                 while ((w >> 34) != (tag >> 34) || ((w >> 32) & 3ull) == 0) {
-                                    __nanosleep(64);
+                                    __nanosleep(200);
                                     w = ld_state(a.tile_state + idx);
                                 }
                             }
@@ -532,10 +560,10 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
                     }
                 }
                 if (lane == 0) trace(a.trace, it, 6);
-                // ---- the tile's points are already compacted in the slot: stream them out as one
-                //      contiguous block at the tile's offset (8/save_point_cloud.cpp:85-136) ----
+                // ---- stream the tile's points out as one contiguous block at its offset
+                //      (8/save_point_cloud.cpp:85-136) ----
                 if (total) {
-                    const float* cx = reinterpret_cast<const float*>(stage + G.out_cx);
+                    const float* cx = xbuf;
                     float* dst = a.pts + 3 * (size_t)excl;
                     const int n = 3 * (int)total;
                     // head so that the body is 16-byte aligned in global memory
@@ -548,7 +576,11 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
                     }
                     const int tail0 = head + 4 * nvec;
                     if (lane < n - tail0) dst[tail0 + lane] = cx[tail0 + lane];
-                    if (a.pix || a.rgb) {      // optional per-point extras: slow path over the flags
+                }
+                if (extras) {
+                    // optional per-point extras (pixel index, texture colour): walk the valid flags
+                    // that are still in the slot, then release it
+                    if (total) {
                         uint32_t run = excl;
                         for (int k = 0; k < CW; k++) {
                             const int w = k * 32 + lane, lp = 4 * w;
@@ -576,7 +608,15 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
                             }
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) {
+                        bulk_wait_read();
+                        trace(a.trace, it, 7);
+                        mbar_arrive(bar_empty + 8 * s);
+                    }
                 }
+                __syncwarp();   // xbuf is reused by the next tile
+                continue;
             }
             __syncwarp();
             if (lane == 0) {
@@ -671,59 +711,79 @@ k_fused(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib
         float* o_x = reinterpret_cast<float*>(stage + G.out_x);
         uint32_t vbits = 0;
         if (active) {
-#pragma unroll 1
+            // (a) decode, straight-line and branch-free so that the 4 pixels (and, inside each,
+            //     the two directions) interleave in the FP64 pipe.  Pixels outside the mask are
+            //     computed too and discarded by selects (tiles without ROI pixels never get here).
+            float r_unwv[4], r_unwh[4];
+            int r_cv[4], r_ch[4];
+            int2 r_cp[4];
+#pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int x = xt + j, lp = lp0 + j;
-                float unwv = 0.0f, unwh = 0.0f;
-                int cv = -1, ch = -1;
-                int2 cp = make_int2(0, 0);
-                bool v = (mbits >> j) & 1u;
-                if (v) {
-                    cv = code_of(gvA, gvB, j, a.M_v);
-                    const float wv = add_pi(phase_of<N>(Tv, j, tab));                    // 4/phase_unwrap.cpp:290
-                    unwv = (x == 0 || x == W - 1) ? 0.0f : unwrap_abs(wv, cv, fastdiv);  // :285, :291
-                    if (DIRS == 2) {
-                        ch = code_of(ghA, ghB, j, a.M_h);
-                        const float wh = add_pi(phase_of<N>(Th, j, tab));
-                        unwh = (y == 0 || y == a.H_total - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);  // :304, :309
-                        long long px = 0, py = 0;                                         // 5/compute_correspondance.cpp:648-675
-                        const bool okx = correspond(unwv, a.fw_v, &px, fastdiv);
-                        const bool oky = correspond(unwh, a.fw_h, &py, fastdiv);
-                        // FE_INVALID on x rejects before y is computed (:650-655); on y after x is stored
-                        cp.x = okx ? sat32(px) : 0;
-                        cp.y = (okx && oky) ? sat32(py) : 0;
-                        v = okx && oky && !(px > a.PW - 1 || py > a.PH - 1 || px < 0 || py < 0);
-                    }
-                }
-                o_unwv[lp] = unwv;
-                o_codev[lp] = (int16_t)cv;
+                const int x = xt + j;
+                const bool m = (mbits >> j) & 1u;
+                const int cv = code_of(gvA, gvB, j, a.M_v);
+                const float wv = add_pi(phase_of<N>(Tv, j, tab));                    // 4/phase_unwrap.cpp:290
+                float unwv = (x == 0 || x == W - 1) ? 0.0f : unwrap_abs(wv, cv, fastdiv);  // :285, :291
+                unwv = m ? unwv : 0.0f;
+                bool v = m;
+                r_cv[j] = m ? cv : -1;
                 if (DIRS == 2) {
-                    o_unwh[lp] = unwh;
-                    o_codeh[lp] = (int16_t)ch;
-                    o_cp[lp] = cp;
-                    if (v) {                                                              // 7/triangulation.cpp:1230-1247
-                        double uc, vc, up, vp, X[3];
-                        if (a.cam_lut) {
-                            const double2 t = a.cam_lut[(size_t)p0 + lp];
-                            uc = t.x; vc = t.y;
-                        } else {
-                            undistorted_pixel_nodist(cal.Kc, cal.ifx_c, cal.ify_c, cal.cam_std != 0, (double)x, (double)y, &uc, &vc);
-                        }
-                        if (a.proj_lut) {
-                            const double2 t = a.proj_lut[(size_t)cp.y * a.PW + cp.x];
-                            up = t.x; vp = t.y;
-                        } else {
-                            undistorted_pixel_nodist(cal.Kp, cal.ifx_p, cal.ify_p, cal.proj_std != 0, (double)cp.x, (double)cp.y, &up, &vp);
-                        }
-                        if (EXACT) triangulate_point(cal.Ac, cal.Ap, uc, vc, up, vp, X);
-                        else triangulate_point_fast(cal.Ac, cal.Ap, uc, vc, up, vp, X);
-                        o_x[3 * lp + 0] = __double2float_rn(X[0]);                       // 8/save_point_cloud.cpp:94-96
-                        o_x[3 * lp + 1] = __double2float_rn(X[1]);
-                        o_x[3 * lp + 2] = __double2float_rn(X[2]);
-                    }
+                    const int ch = code_of(ghA, ghB, j, a.M_h);
+                    const float wh = add_pi(phase_of<N>(Th, j, tab));
+                    float unwh = (y == 0 || y == a.H_total - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);  // :304, :309
+                    unwh = m ? unwh : 0.0f;
+                    long long px = 0, py = 0;                                         // 5/compute_correspondance.cpp:648-675
+                    const bool okx = correspond(unwv, a.fw_v, &px, fastdiv);
+                    const bool oky = correspond(unwh, a.fw_h, &py, fastdiv);
+                    // FE_INVALID on x rejects before y is computed (:650-655); on y after x is stored
+                    r_cp[j].x = (m && okx) ? sat32(px) : 0;
+                    r_cp[j].y = (m && okx && oky) ? sat32(py) : 0;
+                    v = m && okx && oky && !(px > a.PW - 1 || py > a.PH - 1 || px < 0 || py < 0);
+                    r_unwh[j] = unwh;
+                    r_ch[j] = m ? ch : -1;
                 }
-                o_valid[lp] = v ? 1 : 0;
+                r_unwv[j] = unwv;
                 vbits |= (v ? 1u : 0u) << j;
+            }
+            // the thread's 4 pixels are consecutive: one vector store per plane
+            *reinterpret_cast<float4*>(o_unwv + lp0) = make_float4(r_unwv[0], r_unwv[1], r_unwv[2], r_unwv[3]);
+            *reinterpret_cast<uint2*>(o_codev + lp0) =
+                make_uint2((uint32_t)(r_cv[0] & 0xffff) | ((uint32_t)r_cv[1] << 16), (uint32_t)(r_cv[2] & 0xffff) | ((uint32_t)r_cv[3] << 16));
+            *reinterpret_cast<uint32_t*>(o_valid + lp0) =
+                (vbits & 1u) | ((vbits & 2u) << 7) | ((vbits & 4u) << 14) | ((vbits & 8u) << 21);
+            if (DIRS == 2) {
+                *reinterpret_cast<float4*>(o_unwh + lp0) = make_float4(r_unwh[0], r_unwh[1], r_unwh[2], r_unwh[3]);
+                *reinterpret_cast<uint2*>(o_codeh + lp0) =
+                    make_uint2((uint32_t)(r_ch[0] & 0xffff) | ((uint32_t)r_ch[1] << 16), (uint32_t)(r_ch[2] & 0xffff) | ((uint32_t)r_ch[3] << 16));
+                *reinterpret_cast<int4*>(o_cp + lp0) = make_int4(r_cp[0].x, r_cp[0].y, r_cp[1].x, r_cp[1].y);
+                *reinterpret_cast<int4*>(o_cp + lp0 + 2) = make_int4(r_cp[2].x, r_cp[2].y, r_cp[3].x, r_cp[3].y);
+            }
+            // (b) triangulation of the surviving pixels (7/triangulation.cpp:1230-1247)
+            if (DIRS == 2) {
+#pragma unroll 1
+                for (int j = 0; j < 4; j++) {
+                    if (!((vbits >> j) & 1u)) continue;
+                    const int x = xt + j, lp = lp0 + j;
+                    const int2 cp = o_cp[lp];
+                    double uc, vc, up, vp, X[3];
+                    if (a.cam_lut) {
+                        const double2 t = a.cam_lut[(size_t)p0 + lp];
+                        uc = t.x; vc = t.y;
+                    } else {
+                        undistorted_pixel_nodist(cal.Kc, cal.ifx_c, cal.ify_c, cal.cam_std != 0, (double)x, (double)y, &uc, &vc);
+                    }
+                    if (a.proj_lut) {
+                        const double2 t = a.proj_lut[(size_t)cp.y * a.PW + cp.x];
+                        up = t.x; vp = t.y;
+                    } else {
+                        undistorted_pixel_nodist(cal.Kp, cal.ifx_p, cal.ify_p, cal.proj_std != 0, (double)cp.x, (double)cp.y, &up, &vp);
+                    }
+                    if (EXACT) triangulate_point(cal.Ac, cal.Ap, uc, vc, up, vp, X);
+                    else triangulate_point_fast(cal.Ac, cal.Ap, uc, vc, up, vp, X);
+                    o_x[3 * lp + 0] = __double2float_rn(X[0]);                       // 8/save_point_cloud.cpp:94-96
+                    o_x[3 * lp + 1] = __double2float_rn(X[1]);
+                    o_x[3 * lp + 2] = __double2float_rn(X[2]);
+                }
             }
         }
         if (DIRS == 2) {
@@ -792,7 +852,7 @@ static cudaError_t launch_fused_nd(const FusedArgs& a, const DeviceCalib& cal, i
         if (exact || DIRS == 1) return launch_fused_t<N, DIRS, CWV, MB, true>(a, cal, sm_count, p, st); \
         return launch_fused_t<N, DIRS, CWV, MB, (DIRS == 1)>(a, cal, sm_count, p, st);                  \
     }
-    S3D_CASE(4, 3) S3D_CASE(6, 2) S3D_CASE(4, 2) S3D_CASE(8, 1)
+    S3D_CASE(6, 2) S3D_CASE(4, 2) S3D_CASE(8, 1)
 #undef S3D_CASE
     return cudaErrorInvalidValue;
 }
