@@ -23,7 +23,8 @@ NVCC_FLAGS = [
     "-cudart", "static", "-ccbin", "/usr/bin/g++",
 ]
 CU_SOURCES = ["scan3d_api.cu", "scan3d_stage_kernels.cu", "scan3d_fused_kernel.cu"]
-HOST_SOURCES = ["scan3d_io.cpp", "scan3d_synth.cpp", "scan3d_stages.cpp"]
+HOST_SOURCES = ["scan3d_io.cpp", "scan3d_synth.cpp"]
+COMPAT_SOURCES = ["scan3d_stages.cpp"]
 
 
 def _stale(target, deps):
@@ -80,8 +81,22 @@ def build_host(force=False):
     return so
 
 
+def build_compat(force=False):
+    """libscan3d_compat.so: the reference-named stage functions; links libscan3d.so + libscan3d_host.so."""
+    so = os.path.join(LIB, "libscan3d_compat.so")
+    srcs = [os.path.join(HOST, s) for s in COMPAT_SOURCES]
+    deps = _deps(HOST, [os.path.join(HERE, "..", "include", h) for h in ("scan3d.h", "scan3d_host.h", "scan3d_compat.h")])
+    if not (force or _stale(so, deps + [os.path.join(LIB, "libscan3d.so"), os.path.join(LIB, "libscan3d_host.so")])):
+        return so
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-ffp-contract=off",
+           "-I", os.path.join(HERE, "..", "include"), "-o", so] + srcs + [
+           "-L", LIB, "-lscan3d", "-lscan3d_host", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return so
+
+
 def build_all(force=False, verbose=False):
-    return build_cuda(force, verbose), build_host(force)
+    return build_cuda(force, verbose), build_host(force), build_compat(force)
 
 
 if __name__ == "__main__":

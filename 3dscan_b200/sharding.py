@@ -1,0 +1,92 @@
+"""Multi-GPU partitioning of the reconstruction path (one process per GPU, torch.distributed).
+
+Two schemes, both named by BASELINE.json's north star:
+
+  * frame-parallel batches (configs[3]): scans are independent, scan i goes to rank i % world.
+    No collective touches the data path (`scans_for_rank`).
+
+  * one very large frame, row-sharded (configs[4]): rank r owns a contiguous block of rows of
+    every frame of the stack (`row_block`).  Everything on the path is per pixel except the ROI
+    mask recurrence (3/wrapped_phase.cpp:266-279), whose closed form needs ROI rows y-2..y+1; the
+    ROI plane (1 B/pixel) is simply replicated and each ctx is created with (row0, H_total), so no
+    halo exchange is needed.  Each rank's compacted point list is in raster order of its rows, so
+    concatenating the lists in rank order gives the raster order of the full frame.  The one real
+    exchange step is `gather_points`: an all-gather of the per-rank counts followed by
+    point-to-point sends of the compacted points into rank `dst`'s buffer at the right offset
+    (NCCL over NVLink on GPUs; the same code runs over gloo on CPU tensors in the tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def scans_for_rank(n_scans, rank, world):
+    """Indices of the scans rank `rank` reconstructs in a frame-parallel batch."""
+    return list(range(rank, n_scans, world))
+
+
+def row_block(H_total, rank, world):
+    """(row0, rows) of the contiguous row block owned by `rank`; blocks differ by at most 1 row."""
+    base, extra = divmod(H_total, world)
+    rows = base + (1 if rank < extra else 0)
+    row0 = rank * base + min(rank, extra)
+    return row0, rows
+
+
+def gather_points(points, count, dst=0, group=None, out=None):
+    """Concatenate the ranks' compacted point lists, in rank order, on rank `dst`.
+
+    points: [capacity, C] tensor on this rank (only the first `count` rows are valid)
+    count : int, number of valid rows on this rank
+    Returns (all_points, counts) on rank `dst` ([sum(counts), C] tensor, list of ints) and
+    (None, counts) elsewhere.  `out` may preallocate the destination on rank `dst`.
+    """
+    if not dist.is_initialized():
+        return points[:int(count)], [int(count)]
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = points.device
+    if torch.is_tensor(count):              # device-resident count (no host sync before the exchange)
+        c = count.reshape(1).to(torch.int64)
+    else:
+        c = torch.tensor([int(count)], dtype=torch.int64, device=dev)
+    counts_all = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts_all, c, group=group)
+    counts = [int(v) for v in counts_all.tolist()]     # the one host sync: sizes of the sends
+    count = counts[rank]
+    offsets = [0]
+    for n in counts:
+        offsets.append(offsets[-1] + n)
+    if world == 1:
+        return points[:count], counts
+    ops = []
+    result = None
+    if rank == dst:
+        total = offsets[-1]
+        result = out[:total] if out is not None else torch.empty((total,) + tuple(points.shape[1:]), dtype=points.dtype, device=dev)
+        if counts[dst]:
+            result[offsets[dst]:offsets[dst + 1]].copy_(points[:counts[dst]])
+        for r in range(world):
+            if r != dst and counts[r]:
+                ops.append(dist.P2POp(dist.irecv, result[offsets[r]:offsets[r + 1]], r, group))
+    elif count:
+        ops.append(dist.P2POp(dist.isend, points[:count].contiguous(), dst, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return result, counts
+
+
+def allgather_points(points, count, group=None):
+    """Every rank receives the full, rank-ordered point list (padded all-gather)."""
+    world = dist.get_world_size(group)
+    dev = points.device
+    c = torch.tensor([int(count)], dtype=torch.int64, device=dev)
+    counts_t = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts_t, c, group=group)
+    counts = [int(t.item()) for t in counts_t]
+    cap = max(max(counts), 1)
+    padded = torch.zeros((cap,) + tuple(points.shape[1:]), dtype=points.dtype, device=dev)
+    padded[:count].copy_(points[:count])
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, counts)]), counts

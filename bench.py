@@ -36,6 +36,8 @@ WORKLOADS = {
     "c3_12mp_8step_10bit_vh": (4096, 3000, 4096, 3000, 8, 10, 10, 4, 4, 2),
     "c2_1080p_3step_8bit_v": (1920, 1080, 1920, 1080, 3, 8, 8, 8, 8, 1),
     "c1_1600x1200_3step_6bit_vh": (1600, 1200, 1280, 720, 3, 6, 5, 32, 32, 2),
+    # configs[4]: ONE 50 MP frame, row-sharded over the ranks, NCCL gather of the compacted points
+    "c5_50mp_rowshard_8step_10bit_vh": (8192, 6144, 8192, 6144, 8, 10, 10, 8, 8, 2),
 }
 
 
@@ -116,6 +118,90 @@ def oracle_scan_seconds(cfg, ocal, stack, roi, threads, min_seconds, max_runs):
         run_oracle(cfg, ocal, stack, roi, threads=threads)
         times.append(time.time() - t)
     return float(np.median(times)), len(times)
+
+
+def bench_rowshard(args, s3, cal, cfg_full, config, rank, world, local_rank, stream, barrier, bpp):
+    """configs[4]: one very large frame; rank r decodes + triangulates its block of rows, then the
+    compacted point lists are gathered (rank order == raster order) on rank 0 over NCCL."""
+    import importlib
+    import torch
+    import torch.distributed as dist
+    sh = importlib.import_module("3dscan_b200.sharding")
+    W, Ht = cfg_full.W, cfg_full.H
+    row0, rows = sh.row_block(Ht, rank, world)
+    cfg = s3.make_config(W, rows, cfg_full.PW, cfg_full.PH, cfg_full.N, cfg_full.M_v, cfg_full.M_h,
+                         cfg_full.fw_v, cfg_full.fw_h, 2, row0=row0, H_total=Ht, flags=cfg_full.flags)
+    nf = s3.stack_planes(cfg)
+    ctx = s3.Scan3D(cfg, local_rank, cal, stream=stream.cuda_stream)
+    stack_h = torch.empty((nf, rows, W), dtype=torch.uint8, pin_memory=True)
+    roi_h = torch.empty((Ht, W), dtype=torch.uint8, pin_memory=True)
+    s3.synth_stack(cfg, cal, s3.default_synth_params(seed=0x3D5CA9), out=stack_h.numpy(), roi_out=roi_h.numpy(),
+                   threads=max(1, (os.cpu_count() or 8) // max(1, world)))
+    stack_d, roi_d = stack_h.to("cuda"), roi_h.to("cuda")
+    del stack_h
+    out = torch.empty((Ht * W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None
+    total = [0]
+
+    src = _wrap_device(torch, ctx.device_points(), (rows * W, 3), "<f4")
+    cnt_dev = _wrap_device(torch, ctx.device_point_count(), (1,), "<u4" if False else "<i4")
+
+    def step():
+        ctx.reconstruct_dev(stack_d.data_ptr(), roi_d.data_ptr())
+        res, counts = sh.gather_points(src, cnt_dev, dst=0, out=out)   # counts stay on the device until the exchange
+        total[0] = sum(counts)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    t1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t0, t1)
+    tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    npix = W * Ht
+    value = args.steps * npix / (ms_max * 1e-3) / 1e6
+    peak, peak_kind = measured_peak_gbs()
+    achieved = bpp * npix / (ms_max * 1e-3 / args.steps) / 1e9
+    if rank == 0:
+        config.update({"sharding": "one frame row-sharded over %d rank(s); all-gather of counts + NCCL send/recv of compacted points to rank 0" % world,
+                       "rows_per_rank": rows, "scans_per_gpu_per_step": 1, "resident_ring": 1,
+                       "l2_policy": "inputs larger than L2 (%.2f GB per GPU)" % (nf * rows * W / 1e9)})
+        line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "scans_per_s": args.steps / (ms_max * 1e-3), "points_last_scan": total[0],
+                "gpu_launches": ctx.launch_count() - l0, "clocks": clocks,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
+                             "frac": achieved / (peak * world), "traffic": None,
+                             "peak_kind": "%d x MEASURED_PEAKS.json hbm_gbs; time includes the point gather" % world},
+                "e2e": None, "cpu_baseline": None}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _wrap_device(torch, ptr, shape, typestr):
+    """torch view of a ctx-owned device buffer (no copy)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(h, device="cuda")
 
 
 def main():
@@ -201,6 +287,8 @@ def main():
     # a dedicated non-default stream: kernels, copies and the timing events all live on it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
+    if args.workload.startswith("c5_"):
+        return bench_rowshard(args, s3, cal, cfg, config, rank, world, local_rank, stream, barrier, bpp)
     ctx = s3.Scan3D(cfg, local_rank, cal, stream=stream.cuda_stream)
     nf = s3.stack_planes(cfg)
     # resident ring of distinct synthetic scans (scan index = global, so ranks hold different scans)

@@ -1,0 +1,106 @@
+"""The reference's own call sequence (PROJECT_GLOBAL/intermodule_dependencies.h:10-25, called at
+m_tech_project_console.cpp:372-401) through libscan3d_compat.so on a reference-layout directory
+tree, checked against the oracle plane by plane -- the test reads like the reference's main()."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_ffi as o
+from gpu_common import calibs, run_oracle, s3
+
+pytestmark = pytest.mark.gpu
+LIBDIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "3dscan_b200", "lib")
+
+
+def _xml(path, name, arr, rows, cols):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    data = " ".join(repr(float(v)) for v in np.asarray(arr).ravel())
+    open(path, "w").write(
+        f'<?xml version="1.0"?>\n<opencv_storage>\n<{name} type_id="opencv-matrix">\n  <rows>{rows}</rows>\n'
+        f"  <cols>{cols}</cols>\n  <dt>d</dt>\n  <data>\n    {data}</data></{name}>\n</opencv_storage>\n")
+
+
+def _bmp(path, img):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    img = np.ascontiguousarray(img, np.uint8)
+    assert s3.host_lib().scan3d_write_bmp8(path.encode(), img.shape[1], img.shape[0], img.ctypes.data_as(C.c_void_p)) == 0
+
+
+def test_reference_call_sequence(tmp_path):
+    W, H, PW, PH, N, Mv, Mh, fw = 320, 240, 256, 192, 3, 5, 5, 8
+    cal, ocal, c = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fw, fw, 2)
+    stack, roi = s3.synth_stack(cfg, cal)
+    d = s3.split_stack(cfg, stack)
+    root = str(tmp_path / "M_tech_project_console")
+    for key, name in (("v", "Vertical"), ("h", "Horizontal")):
+        for i, img in enumerate(d["fringe_" + key]):
+            _bmp(f"{root}/Captured_patterns/Fringe_patterns/{name}/Undistorted/Gray_captured_image_{i}.bmp", img)
+        for i, img in enumerate(d["gray_" + key]):
+            _bmp(f"{root}/Captured_patterns/Coded_patterns/Gray_coded/{name}/Undistorted/Gray_captured_image_{i}.bmp", img)
+        for i, img in enumerate(d["inv_" + key]):
+            _bmp(f"{root}/Captured_patterns/Coded_patterns/Gray_coded/{name}/Undistorted/inverse_Gray_captured_image_{i}.bmp", img)
+    _xml(f"{root}/Camera_calibration/Matrices/cam_intrinsic_mat.xml", "cam_intrinsic_mat", c["Kc"], 3, 3)
+    _xml(f"{root}/Camera_calibration/Matrices/cam_distortion_vect.xml", "cam_distortion_vect", c["dc"], 5, 1)
+    _xml(f"{root}/Projector_calibration/Matrices/proj_intrinsic_mat.xml", "proj_intrinsic_mat", c["Kp"], 3, 3)
+    _xml(f"{root}/Projector_calibration/Matrices/proj_distortion_vect.xml", "proj_distortion_vect", c["dp"], 5, 1)
+    t = f"{root}/Triangulation"
+    _xml(f"{t}/Camera_extrinsic_parametrs/world_to_cam_rot_vect.xml", "world_to_cam_rot_vect", c["rc"], 3, 1)
+    _xml(f"{t}/Camera_extrinsic_parametrs/world_to_cam_trans_vect.xml", "world_to_cam_trans_vect", c["tc"], 3, 1)
+    _xml(f"{t}/Projector_extrinsic_parametrs/world_to_proj_rot_vect.xml", "world_to_proj_rot_vect", c["rp"], 3, 1)
+    _xml(f"{t}/Projector_extrinsic_parametrs/world_to_proj_trans_vect.xml", "world_to_proj_trans_vect", c["tp"], 3, 1)
+    os.makedirs(f"{root}/Point_cloud", exist_ok=True)
+
+    s3.cuda_lib(); s3.host_lib()
+    L = C.CDLL(os.path.join(LIBDIR, "libscan3d_compat.so"))
+    g = lambda n, t=C.c_int: t.in_dll(L, n)
+    init = getattr(L, "_Z18scan3d_compat_initPKciiiii")
+    init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    assert init(root.encode(), W, H, PW, PH, 0) == 0
+    g("number_of_patterns_fringe").value = N
+    g("number_of_patterns_binary_vertical").value = Mv
+    g("number_of_patterns_binary_horizontal").value = Mh
+    g("fringe_width_pixels_vertical").value = fw
+    g("fringe_width_pixels_horizontal").value = fw
+    sel = np.ascontiguousarray(roi.T.astype(np.int32))          # selected_region[col][row]
+    g("selected_region", C.c_void_p).value = sel.ctypes.data
+
+    # ---- the reference's main() sequence ----
+    getattr(L, "_Z13load_matricesv")()
+    cwp = getattr(L, "_Z21compute_wrapped_phasei"); cwp.argtypes = [C.c_int]
+    uwp = getattr(L, "_Z12unwrap_phasei"); uwp.argtypes = [C.c_int]
+    cwp(0); cwp(1)
+    uwp(0); uwp(1)
+    getattr(L, "_Z15compute_c_p_mapv")()
+    getattr(L, "_Z11triangulatev")()
+    spc = getattr(L, "_Z16save_point_cloudj"); spc.argtypes = [C.c_uint]
+    spc(0)
+
+    ref = run_oracle(cfg, ocal, stack, roi)
+
+    def plane(name, ctype, tail=()):
+        ptr = C.c_void_p.in_dll(L, name).value
+        assert ptr
+        n = W * H * int(np.prod(tail)) if tail else W * H
+        a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
+        return a.reshape((W, H) + tuple(tail))            # the reference's [col][row]
+
+    assert np.array_equal(plane("valid_map_vertical", C.c_int).T, ref.valid_v)
+    assert np.array_equal(plane("code_vertical", C.c_int).T, ref.code_v)
+    assert np.array_equal(plane("code_horizontal", C.c_int).T, ref.code_h)
+    assert np.array_equal(plane("unwrapped_phi_vertical", C.c_float).T, ref.unwrapped_v)
+    assert np.array_equal(plane("unwrapped_phi_horizontal", C.c_float).T, ref.unwrapped_h)
+    assert np.array_equal(plane("wrapped_phi_vertical", C.c_float).T, ref.wrapped_v)
+    assert np.array_equal(plane("valid_map", C.c_int).T, ref.valid)
+    cp = np.ctypeslib.as_array(C.cast(C.c_void_p.in_dll(L, "c_p_map").value, C.POINTER(C.c_long)), shape=(W * H, 2))
+    assert np.array_equal(cp, ref.cpmap)
+    xyz = plane("intersection_points", C.c_double, (3,)).transpose(1, 0, 2)
+    m = ref.valid == 1
+    assert np.array_equal(xyz[m], ref.xyz[m])
+    body = open(f"{root}/Point_cloud/point_cloud_0.ply").read().split("end_header\n")[1]
+    rows = np.loadtxt(body.splitlines())
+    assert rows.shape == (ref.count, 6)
+    assert np.array_equal(rows[:, :3].astype(np.float32), ref.pts)
+    getattr(L, "_Z22scan3d_compat_shutdownv")()
