@@ -330,37 +330,40 @@ __global__ void k_tile_flags(const uint8_t* __restrict__ roi, int T, int plane, 
         for (int i = lane; i < wt / 2; i += 32) reinterpret_cast<uint4*>(cpmap + p0)[i] = z;
 }
 
-// exclusive scan of the flags by one CTA -> list of non-empty tile ids (raster order) + its length
+// exclusive scan of the flags by one CTA -> list of non-empty tile ids (raster order) + its length.
+// Each thread owns a contiguous chunk of flags, so one block-wide scan suffices.
 __global__ void k_tile_list(const uint8_t* __restrict__ flags, int n_tiles, int* __restrict__ list,
                             int* __restrict__ n_list, uint32_t* __restrict__ d_count)
 {
     __shared__ int wsum[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) { carry = 0; *d_count = 0; }
-    __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int base = 0; base < n_tiles; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int f = i < n_tiles ? flags[i] : 0;
-        const unsigned b = __ballot_sync(0xffffffffu, f);
-        if (lane == 0) wsum[w] = __popc(b);
-        __syncthreads();
-        if (w == 0) {
-            int v = wsum[lane];
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, v, o);
-                if (lane >= o) v += t;
-            }
-            wsum[lane] = v;   // inclusive
-        }
-        __syncthreads();
-        const int c = carry;
-        if (f) list[c + (w ? wsum[w - 1] : 0) + __popc(b & ((1u << lane) - 1u))] = i;
-        __syncthreads();
-        if (threadIdx.x == 0) carry = c + wsum[31];
-        __syncthreads();
+    const int per = (n_tiles + 1023) / 1024;
+    const int i0 = threadIdx.x * per, i1 = min(n_tiles, i0 + per);
+    int cnt = 0;
+    for (int i = i0; i < i1; i++) cnt += flags[i] != 0;
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
-    if (threadIdx.x == 0) *n_list = carry;
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int v = wsum[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        wsum[lane] = v;   // inclusive over warps
+    }
+    __syncthreads();
+    int pos = (w ? wsum[w - 1] : 0) + incl - cnt;
+    for (int i = i0; i < i1; i++)
+        if (flags[i]) list[pos++] = i;
+    if (threadIdx.x == 0) {
+        *n_list = wsum[31];
+        *d_count = 0;   // overwritten by the fused kernel's last tile when there is any work
+    }
 }
 
 // optional per-CTA timeline (SCAN3D_TRACE=1): clock64 stamps of the pipeline events of the first
