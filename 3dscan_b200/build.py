@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-Wall", "-Xptxas", "-v",
     "-cudart", "static", "-ccbin", "/usr/bin/g++",
 ]
-CU_SOURCES = ["scan3d_api.cu", "scan3d_stage_kernels.cu", "scan3d_fused_kernel.cu"]
+CU_SOURCES = ["scan3d_api.cu", "scan3d_stage_kernels.cu", "scan3d_fused_kernel.cu", "scan3d_fused_kernel7.cu"]
 HOST_SOURCES = ["scan3d_io.cpp", "scan3d_synth.cpp"]
 COMPAT_SOURCES = ["scan3d_stages.cpp"]
 

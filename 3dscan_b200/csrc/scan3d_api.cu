@@ -484,7 +484,10 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     }
     a.W = c.W; a.H = c.H; a.row0 = c.row0; a.H_total = c.H_total; a.PW = c.PW; a.PH = c.PH;
     a.N = c.N; a.M_v = c.M_v; a.M_h = c.M_h; a.fw_v = c.fw_v; a.fw_h = c.fw_h;
-    CK(launch_fused(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
+    const char* impl = getenv("SCAN3D_FUSED_IMPL");
+    const bool use7 = (!impl || atoi(impl) != 6) && fused7_supported(c);
+    if (use7) CK(launch_fused7(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
+    else CK(launch_fused(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
     ctx->launches += 3;   // work-list flags, work-list scan, persistent fused kernel
     ctx->have_wrapped[0] = ctx->have_wrapped[1] = false;
     ctx->have_unwrapped[0] = true;

@@ -25,12 +25,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "scan3d_internal.h"
+#include "scan3d_fused_common.cuh"
 
 namespace s3d {
 
-constexpr int ROI_HALO = 16;               // bytes of halo each side (16 B aligned bulk copies)
-constexpr int SMEM_MAX = 227 * 1024;
 constexpr int MAX_STAGES = 4;
 constexpr int SMEM_FIXED = 3 * MAX_STAGES * 8 + ATAN_TAB_DOUBLES * 8 + MAX_STAGES * 4 + MAX_STAGES * 8 * 4 + 16;   // barriers + atan table + slot tile ids + per-slot warp counts + pad
 
@@ -124,175 +122,6 @@ int fused_num_tiles(const scan3d_config& c)
     return (int)(((size_t)c.W * c.H + 255) / 256) + 1;
 }
 
-// ---- PTX helpers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-// poll with back-off so that a waiting warp does not steal issue slots from the computing ones
-// (one copy per warp role so that profiles attribute the waiting to the right role)
-#define S3D_WAIT_BODY                                        \
-    if (mbar_try(bar, parity)) return;                      \
-    while (!mbar_try(bar, parity)) __nanosleep(128);
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    S3D_WAIT_BODY
-}
-__device__ __forceinline__ void mbar_wait_consumer(uint32_t bar, uint32_t parity)
-{
-    S3D_WAIT_BODY
-}
-__device__ __forceinline__ void mbar_wait_epilogue(uint32_t bar, uint32_t parity)
-{
-    S3D_WAIT_BODY
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-template <int NT>
-__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
-
-__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// ---- SWAR pieces -----------------------------------------------------------------------------
-// per-byte unsigned a >= b  ->  bit 7 of each byte
-__device__ __forceinline__ uint32_t ge_bytes(uint32_t a, uint32_t b)
-{
-    const uint32_t d = (a | 0x80808080u) - (b & 0x7f7f7f7fu);
-    return ((a & ~b) | (~(a ^ b) & d)) & 0x80808080u;
-}
-// bytes (b0,b1,b2,b3) -> 16-bit lanes (b0,b1) and (b2,b3)
-__device__ __forceinline__ uint32_t lanes_lo(uint32_t w) { return __byte_perm(w, 0, 0x4140); }
-__device__ __forceinline__ uint32_t lanes_hi(uint32_t w) { return __byte_perm(w, 0, 0x4342); }
-
-struct Terms {            // up to 4 biased 16-bit terms for 4 pixels: [term][0]=(px0,px1) [1]=(px2,px3)
-    uint32_t t[4][2];
-};
-// phase-shift numerators/denominators for 4 pixels (3/wrapped_phase.cpp:171-173,195-196,217-218)
-template <int N>
-__device__ __forceinline__ void fringe_terms(const uint32_t* __restrict__ sw, int f0, int wpf, int tid, Terms& T)
-{
-    uint32_t L[N][2];
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-        const uint32_t w = sw[(f0 + k) * wpf + tid];
-        L[k][0] = lanes_lo(w);
-        L[k][1] = lanes_hi(w);
-    }
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        if (N == 3) {          // t1 = I0 - I2 (+512) ; t2 = 2*I1 - I0 - I2 (+1024)
-            T.t[0][h] = L[0][h] + 0x02000200u - L[2][h];
-            T.t[1][h] = 2 * L[1][h] + 0x04000400u - L[0][h] - L[2][h];
-        } else if (N == 4) {   // t1 = I3 - I1 ; t2 = I0 - I2
-            T.t[0][h] = L[3 % N][h] + 0x02000200u - L[1][h];
-            T.t[1][h] = L[0][h] + 0x02000200u - L[2][h];
-        } else if (N == 5) {   // t1 = 2(I1 - I3) (+1024) ; t2 = 2*I2 - I0 - I4 (+1024)
-            T.t[0][h] = 2 * L[1][h] + 0x04000400u - 2 * L[3 % N][h];
-            T.t[1][h] = 2 * L[2][h] + 0x04000400u - L[0][h] - L[4 % N][h];
-        } else {               // N == 8: a1 = I6-I2, b1 = I5+I7-I1-I3, a2 = I0-I4, b2 = I1+I7-I3-I5
-            T.t[0][h] = L[6 % N][h] + 0x02000200u - L[2][h];
-            T.t[1][h] = L[5 % N][h] + L[7 % N][h] + 0x04000400u - L[1][h] - L[3 % N][h];
-            T.t[2][h] = L[0][h] + 0x02000200u - L[4 % N][h];
-            T.t[3][h] = L[1][h] + L[7 % N][h] + 0x04000400u - L[3 % N][h] - L[5 % N][h];
-        }
-    }
-}
-__device__ __forceinline__ int term_of(const Terms& T, int k, int j, int bias)
-{
-    const uint32_t r = (j & 2) ? T.t[k][1] : T.t[k][0];
-    return (int)((r >> ((j & 1) * 16)) & 0xffffu) - bias;
-}
-
-// Gray threshold for 4 pixels, all M planes: byte accumulators with plane i at bit (7 - i%8)
-// (4/phase_unwrap.cpp:183: (uchar)img - (uchar)inv >= 0, tie -> 1)
-__device__ __forceinline__ void gray_bits(const uint32_t* __restrict__ sw, int g0, int i0, int M, int wpf, int tid,
-                                          uint32_t& accA, uint32_t& accB)
-{
-    accA = 0; accB = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-        if (i < M) accA |= ge_bytes(sw[(g0 + i) * wpf + tid], sw[(i0 + i) * wpf + tid]) >> i;
-#pragma unroll
-    for (int i = 8; i < 15; i++)
-        if (i < M) accB |= ge_bytes(sw[(g0 + i) * wpf + tid], sw[(i0 + i) * wpf + tid]) >> (i - 8);
-}
-// Gray -> binary (B0 = G0, Bi = B(i-1) xor Gi) as a prefix xor; code = sum Bi << (M-1-i)  (:187-193)
-__device__ __forceinline__ int code_of(uint32_t accA, uint32_t accB, int j, int M)
-{
-    const uint32_t a = (accA >> (8 * j)) & 0xffu, b = (accB >> (8 * j)) & 0xffu;
-    uint32_t g = ((a << 8) | b) >> (16 - M);
-    g ^= g >> 1; g ^= g >> 2; g ^= g >> 4; g ^= g >> 8;
-    return (int)g;
-}
-
-template <int N>
-__device__ __forceinline__ float phase_of(const Terms& T, int j, const double* tab)
-{
-    if (N == 8) {
-        const int a1 = term_of(T, 0, j, 512), b1 = term_of(T, 1, j, 1024);
-        const int a2 = term_of(T, 2, j, 512), b2 = term_of(T, 3, j, 1024);
-        const double r = 0.70710678118654752440;
-        const double d1 = dadd((double)a1, dmul((double)b1, r));
-        const double d2 = dadd((double)a2, dmul((double)b2, r));
-        const float f1 = fmaf((float)b1, 0.70710678f, (float)a1);
-        const float f2 = fmaf((float)b2, 0.70710678f, (float)a2);
-        return atan2_to_float(d1, d2, f1, f2, tab);
-    } else {
-        const int t1 = term_of(T, 0, j, N == 5 ? 1024 : 512);
-        const int t2 = term_of(T, 1, j, N == 4 ? 512 : 1024);
-        if (N == 5) return atan2f_fdlibm((float)t1, (float)t2);   // 3/wrapped_phase.cpp:220 (float atan2f)
-        return atan2_to_float((double)t1, (double)t2, (float)t1, (float)t2, tab);
-    }
-}
-
-__device__ __forceinline__ int sat32(long long v)
-{
-    return (int)max(min(v, 2147483647LL), -2147483648LL);
-}
-
 // ---- work list: tiles that contain at least one ROI pixel ---------------------------------------
 // One warp per tile looks at the tile's ROI bytes.  Tiles without any selected pixel never enter
 // the main kernel: their outputs (phase 0, fringe order -1, valid 0, c_p_map 0) are written right
@@ -366,15 +195,15 @@ __global__ void k_tile_list(const uint8_t* __restrict__ flags, int n_tiles, int*
     }
 }
 
-// optional per-CTA timeline (SCAN3D_TRACE=1): clock64 stamps of the pipeline events of the first
-// TRACE_TILES tiles of every CTA; slot = (cta * TRACE_TILES + it) * 8 + event
-constexpr int TRACE_TILES = 64;
-__device__ __forceinline__ void trace(unsigned long long* t, int it, int ev)
+cudaError_t launch_worklist(const FusedArgs& a, int T, int dirs, cudaStream_t st)
 {
-    if (t && it < TRACE_TILES) t[((size_t)blockIdx.x * TRACE_TILES + it) * 8 + ev] = clock64();
+    k_tile_flags<<<(a.n_tiles + 7) / 8, 256, 0, st>>>(a.roi, T, a.W * a.H, a.n_tiles, (size_t)a.row0 * a.W, a.tile_flags,
+                                                      a.unw_v, a.unw_h, a.code_v, a.code_h, a.valid, a.cpmap, dirs);
+    k_tile_list<<<1, 1024, 0, st>>>(a.tile_flags, a.n_tiles, a.tile_list, a.n_list, a.d_count);
+    return cudaGetLastError();
 }
 
-// ---- the kernel ----// ---- the kernel --------------------------------------------------------------------------------
+// ---- the kernel --------------------------------------------------------------------------------
 // registers per thread for a launch shape: the whole register file split over MINB resident CTAs
 constexpr int regs_for(int cw, int minb)
 {
@@ -837,10 +666,8 @@ static cudaError_t launch_fused_t(const FusedArgs& a, const DeviceCalib& cal, in
     if (per_sm > MINB) per_sm = MINB;
     // every CTA must be resident (the look-back chain waits on earlier tiles)
     const int grid = a.n_tiles < sm_count * per_sm ? a.n_tiles : sm_count * per_sm;
-    constexpr int T = 128 * CW;
-    k_tile_flags<<<(a.n_tiles + 7) / 8, 256, 0, st>>>(a.roi, T, a.W * a.H, a.n_tiles, (size_t)a.row0 * a.W, a.tile_flags,
-                                                      a.unw_v, a.unw_h, a.code_v, a.code_h, a.valid, a.cpmap, DIRS);
-    k_tile_list<<<1, 1024, 0, st>>>(a.tile_flags, a.n_tiles, a.tile_list, a.n_list, a.d_count);
+    e = launch_worklist(a, 128 * CW, DIRS, st);
+    if (e != cudaSuccess) return e;
     kern<<<grid, (CW + 2) * 32, p.smem, st>>>(a, cal, p.stages, p.stage_bytes);
     return cudaGetLastError();
 }

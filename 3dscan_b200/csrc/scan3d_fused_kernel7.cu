@@ -1,0 +1,545 @@
+// scan3d_fused_kernel7.cu -- second-generation fused kernel ("v7").  Same work, same results and
+// same warp-specialised idea as scan3d_fused_kernel.cu, re-cut so that more consumer warps fit on
+// an SM (throughput of this path follows the number of consumer warps: it is latency/issue bound,
+// see DESIGN.md section 7):
+//
+//   * plane outputs (phases, fringe orders, valid, c_p_map) leave straight from registers as
+//     16-byte vector stores -- each thread owns 4 consecutive pixels, a warp writes 512 contiguous
+//     bytes per plane -- so nothing but the points is staged in shared memory;
+//   * the input slot is therefore dead right after the integer phase: consumers hand it back at
+//     once and ONE slot per CTA keeps the loads a full FP64 phase ahead;
+//   * the triangulated points stay in registers until the block scan, then go to one of two small
+//     compacted-point buffers;
+//   * producer and epilogue are one "IO warp" running an event loop: issue the next tile's TMA bulk
+//     loads when the slot frees, publish a staged tile's count, advance a resumable decoupled
+//     look-back without ever blocking, stream resolved tiles out.
+//
+//   CTA = CW consumer warps + 1 IO warp; shared memory per CTA = NF*T + ROI window + 2*12*T bytes
+//   (66 KB for the 12 MP config at CW = 6) -> 3 CTAs = 18 consumer warps per SM at 96 registers.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "scan3d_fused_common.cuh"
+
+namespace s3d {
+
+struct Geom7 {
+    int T, roi_row, roi_bytes;
+};
+__host__ __device__ constexpr Geom7 geom7(int T) { return Geom7{T, T + 2 * ROI_HALO, 4 * (T + 2 * ROI_HALO)}; }
+
+constexpr int FIXED7 = 64 /*6 mbarriers*/ + ATAN_TAB_DOUBLES * 8 + 16 /*cur_pos, staged_pos[2]*/ + 128 /*cnt[2][16]*/;
+
+static int num_frames7(const scan3d_config& c)
+{
+    return c.dirs == 2 ? 2 * c.N + 2 * (c.M_v + c.M_h) : c.N + 2 * c.M_v;
+}
+static size_t smem7(const scan3d_config& c, int cw)
+{
+    const int T = 128 * cw;
+    return (size_t)num_frames7(c) * T + geom7(T).roi_bytes + (c.dirs == 2 ? 2 * 12 * T + 2 * (T / 4) : 0) + FIXED7;
+}
+
+struct Plan7 {
+    int cw, minb;
+    size_t smem;
+};
+
+static bool plan7(const scan3d_config& c, Plan7* out)
+{
+    if (c.W % 16 != 0) return false;
+    if (!(c.N == 3 || c.N == 4 || c.N == 5 || c.N == 8)) return false;
+    // Shapes are bounded by the register file of an SM sub-partition (16 K registers): warps are
+    // dealt round-robin to the 4 sub-partitions, so ceil(warps per SM / 4) * 32 * regs <= 16384:
+    // 20 warps at 96 registers, 16 at 128, 24 at 80.
+    int cw = 9, minb = 2;
+    if (const char* e = getenv("SCAN3D_FUSED_CFG")) {
+        int a = 0, b = 0, s = 0;
+        if (sscanf(e, "%d,%d,%d", &a, &b, &s) >= 2) { cw = a; minb = b; }
+    }
+    const int shapes[7][2] = {{cw, minb}, {9, 2}, {7, 2}, {7, 3}, {4, 4}, {6, 2}, {5, 4}};
+    for (int i = 0; i < 7; i++) {
+        const int w = shapes[i][0], b = shapes[i][1];
+        if (!((w == 7 && b == 2) || (w == 7 && b == 3) || (w == 9 && b == 2) || (w == 4 && b == 4) || (w == 6 && b == 2) || (w == 5 && b == 4))) continue;
+        const size_t sm = smem7(c, w);
+        if ((sm + 1024) * b <= (size_t)SMEM_MAX + 1024) {
+            out->cw = w; out->minb = b; out->smem = sm;
+            return true;
+        }
+    }
+    return false;
+}
+
+bool fused7_supported(const scan3d_config& c)
+{
+    Plan7 p;
+    return plan7(c, &p);
+}
+
+constexpr int regs7(int cw, int minb)
+{
+    // per sub-partition: ceil(resident warps / 4) warps share 16384 registers
+    const int warps = minb * (cw + 1);
+    const int r = 16384 / (((warps + 3) / 4) * 32);
+    return r > 255 ? 255 : (r / 8) * 8;
+}
+
+template <int N, int DIRS, int CW, int MINB, bool EXACT>
+__global__ void __launch_bounds__((CW + 1) * 32) __maxnreg__(regs7(CW, MINB))
+k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal)
+{
+    constexpr int T = 128 * CW;
+    constexpr int NCONS = 32 * CW;
+    constexpr int WPF = T / 4;
+    constexpr Geom7 G = geom7(T);
+    constexpr bool fastdiv = true;   // host verified (else this kernel is not used)
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int NF = DIRS == 2 ? 2 * N + 2 * (a.M_v + a.M_h) : N + 2 * a.M_v;
+    uint8_t* slot = smem;
+    uint8_t* sroi = smem + (size_t)NF * T;
+    float* cxb = reinterpret_cast<float*>(sroi + G.roi_bytes);                 // [2][3*T]
+    uint8_t* vfl = reinterpret_cast<uint8_t*>(cxb + (DIRS == 2 ? 2 * 3 * T : 0));   // [2][T/4] 4 valid bits per thread
+    uint64_t* bars = reinterpret_cast<uint64_t*>(vfl + (DIRS == 2 ? 2 * (T / 4) : 0));
+    double* tab = reinterpret_cast<double*>(bars + 8);
+    volatile int* ctl = reinterpret_cast<volatile int*>(tab + ATAN_TAB_DOUBLES);   // [0] cur_pos, [1..2] staged_pos
+    volatile uint32_t* cnts = reinterpret_cast<volatile uint32_t*>(const_cast<int*>(ctl) + 4);   // [2][16]
+    const uint32_t bar_full = smem_u32(bars), bar_free = smem_u32(bars + 1), bar_staged = smem_u32(bars + 2),
+                   bar_cxfree = smem_u32(bars + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int W = a.W;
+    const int plane = W * a.H;
+
+    if (tid == 0) {
+        mbar_init(bar_full, 1);
+        mbar_init(bar_free, CW);
+        mbar_init(bar_staged, CW);
+        mbar_init(bar_staged + 8, CW);
+        mbar_init(bar_cxfree, 1);
+        mbar_init(bar_cxfree + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    for (int i = tid; i < ATAN_TAB_DOUBLES; i += (CW + 1) * 32) tab[i] = a.atan_tab[i];
+    __syncthreads();
+
+    // static, phase-aligned schedule over the work list (see scan3d_fused_kernel.cu)
+    const int n_work = *a.n_list;
+    const int Gsz = (int)gridDim.x, bid = (int)blockIdx.x;
+    const int n_mine = bid < n_work ? (n_work - bid + Gsz - 1) / Gsz : 0;
+
+    if (warp == CW) {
+        // ================================ IO WARP (producer + epilogue) ================================
+        const unsigned long long tag = (unsigned long long)(a.epoch & 0x3fffffffu) << 34;
+        const long long roi_total = (long long)W * a.H_total;
+        int load_it = 0;                         // next tile to load
+        int agg_it = DIRS == 2 ? 0 : n_mine;     // next staged tile whose count gets published
+        int epi_it = agg_it;                     // next tile whose points get streamed out
+        bool ended = false;
+        bool resolving = false;
+        int look = 0;
+        uint32_t excl = 0;
+        uint32_t tot[2] = {0, 0};
+        int epos[2] = {0, 0};
+        bool skip[2] = {false, false};
+        while (!ended || epi_it < n_mine) {
+            bool progressed = false;
+            // ---- (1) the slot is free again: issue the next tile's loads (or the end marker) ----
+            if (!ended && __any_sync(0xffffffffu, mbar_try(bar_free, (load_it & 1) ^ 1))) {
+                progressed = true;
+                if (load_it < n_mine) {
+                    const int pos = load_it * Gsz + bid;
+                    const int tile = a.tile_list[pos];
+                    const int p0 = tile * T, wt = min(T, plane - p0);
+                    const long long gbase = (long long)a.row0 * W + p0 - ROI_HALO;
+                    long long seg0 = 0, seg1 = 0;
+                    uint32_t roi_tx = 0;
+                    if (lane < 4) {
+                        seg0 = max(gbase + (long long)(lane - 2) * W, 0LL);
+                        seg1 = min(gbase + (long long)(lane - 2) * W + wt + 2 * ROI_HALO, roi_total);
+                        if (seg1 > seg0) roi_tx = (uint32_t)(seg1 - seg0);
+                    }
+                    uint32_t roi_sum = roi_tx;
+                    roi_sum += __shfl_xor_sync(0xffffffffu, roi_sum, 1);
+                    roi_sum += __shfl_xor_sync(0xffffffffu, roi_sum, 2);
+                    roi_sum = __shfl_sync(0xffffffffu, roi_sum, 0);
+                    if (lane == 0) {
+                        trace(a.trace, load_it, 0);
+                        ctl[0] = pos;
+                        mbar_expect_tx(bar_full, (uint32_t)NF * wt + roi_sum);
+                    }
+                    __syncwarp();
+                    const uint32_t dst = smem_u32(slot);
+                    const uint8_t* src = a.stack + p0;
+                    for (int f = lane; f < NF; f += 32) bulk_g2s(dst + f * T, src + (size_t)f * plane, (uint32_t)wt, bar_full);
+                    if (roi_tx)
+                        bulk_g2s(smem_u32(sroi) + lane * G.roi_row + (uint32_t)(seg0 - (gbase + (long long)(lane - 2) * W)),
+                                 a.roi + seg0, roi_tx, bar_full);
+                    if (lane == 0) trace(a.trace, load_it, 1);
+                    load_it++;
+                } else {
+                    if (lane == 0) {
+                        ctl[0] = -1;
+                        mbar_arrive(bar_full);
+                    }
+                    ended = true;
+                }
+            }
+            if (DIRS == 2) {
+                // ---- (2) a tile got staged: publish its count at once (never behind a look-back) ----
+                if (agg_it < n_mine && agg_it < epi_it + 2 &&
+                    __any_sync(0xffffffffu, mbar_try(bar_staged + 8 * (agg_it & 1), (agg_it >> 1) & 1))) {
+                    progressed = true;
+                    const int b = agg_it & 1;
+                    const int pos = ctl[1 + b];
+                    uint32_t total = lane < CW ? cnts[b * 16 + lane] : 0u;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+                    if (lane == 0) trace(a.trace, agg_it, 5);
+                    tot[b] = total;
+                    epos[b] = pos;
+                    skip[b] = total == 0 && pos != n_work - 1 && pos > 0;
+                    if (skip[b]) {
+                        // empty tile: nothing to write, never waits; forward a ready prefix or post 0
+                        if (lane == 0) {
+                            const unsigned long long w = ld_state(a.tile_state + pos - 1);
+                            const bool fwd = (w >> 34) == (tag >> 34) && ((w >> 32) & 3ull) == 2;
+                            st_state(a.tile_state + pos, fwd ? w : (tag | (1ull << 32)));
+                            mbar_arrive(bar_cxfree + 8 * b);
+                        }
+                    } else if (pos > 0 && lane == 0) {
+                        st_state(a.tile_state + pos, tag | (1ull << 32) | total);
+                    }
+                    agg_it++;
+                }
+                // ---- (3) resumable decoupled look-back + streaming of the oldest pending tile ----
+                if (epi_it < agg_it) {
+                    const int b = epi_it & 1;
+                    if (skip[b]) {
+                        epi_it++;
+                        progressed = true;
+                    } else {
+                        if (!resolving) { resolving = true; excl = 0; look = epos[b] - 1; }
+                        bool resolved = epos[b] == 0;
+                        if (!resolved) {
+                            const int idx = look - lane;
+                            unsigned long long w = tag | (2ull << 32);   // virtual tile < 0: prefix 0
+                            if (idx >= 0) w = ld_state(a.tile_state + idx);
+                            const bool ready = (w >> 34) == (tag >> 34) && ((w >> 32) & 3ull) != 0;
+                            if (__all_sync(0xffffffffu, ready)) {
+                                progressed = true;
+                                const bool is_prefix = ((w >> 32) & 3ull) == 2;
+                                const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+                                const int stop = pm ? __ffs(pm) - 1 : 31;
+                                uint32_t v = lane <= stop ? (uint32_t)w : 0;
+#pragma unroll
+                                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                                excl += v;
+                                if (pm) resolved = true;
+                                else look -= 32;
+                            }
+                        }
+                        if (resolved) {
+                            progressed = true;
+                            const uint32_t total = tot[b];
+                            const int pos = epos[b];
+                            if (lane == 0) {
+                                st_state(a.tile_state + pos, tag | (2ull << 32) | (excl + total));
+                                if (pos == n_work - 1) *a.d_count = excl + total;
+                                trace(a.trace, epi_it, 6);
+                            }
+                            if (total) {
+                                // stream the tile's compacted points as one contiguous block
+                                const float* cx = cxb + b * 3 * T;
+                                float* dstp = a.pts + 3 * (size_t)excl;
+                                const int n = 3 * (int)total;
+                                const int head = min(n, (int)((4 - (((uintptr_t)dstp >> 2) & 3)) & 3));
+                                if (lane < head) dstp[lane] = cx[lane];
+                                const int nvec = (n - head) >> 2;
+                                for (int v = lane; v < nvec; v += 32) {
+                                    const int i = head + 4 * v;
+                                    *reinterpret_cast<float4*>(dstp + i) = make_float4(cx[i], cx[i + 1], cx[i + 2], cx[i + 3]);
+                                }
+                                const int tail0 = head + 4 * nvec;
+                                if (lane < n - tail0) dstp[tail0 + lane] = cx[tail0 + lane];
+                                if (a.pix || a.rgb) {   // optional extras from the per-thread valid bits
+                                    const int p0 = a.tile_list[pos] * T;
+                                    uint32_t run = excl;
+                                    for (int k = 0; k < CW; k++) {
+                                        const int th = k * 32 + lane;
+                                        const uint32_t f = vfl[b * (T / 4) + th];
+                                        const uint32_t c = __popc(f);
+                                        uint32_t incl = c;
+#pragma unroll
+                                        for (int o = 1; o < 32; o <<= 1) {
+                                            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                                            if (lane >= o) incl += t;
+                                        }
+                                        uint32_t dp = run + incl - c;
+                                        run += __shfl_sync(0xffffffffu, incl, 31);
+                                        for (int j = 0; j < 4; j++)
+                                            if ((f >> j) & 1u) {
+                                                const size_t gp = (size_t)p0 + 4 * th + j;
+                                                if (a.pix) a.pix[dp] = (uint32_t)((size_t)a.row0 * W + gp);
+                                                if (a.rgb) {
+                                                    a.rgb[3 * (size_t)dp + 0] = a.texture[3 * gp + 2];
+                                                    a.rgb[3 * (size_t)dp + 1] = a.texture[3 * gp + 1];
+                                                    a.rgb[3 * (size_t)dp + 2] = a.texture[3 * gp + 0];
+                                                }
+                                                dp++;
+                                            }
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                            if (lane == 0) {
+                                trace(a.trace, epi_it, 7);
+                                mbar_arrive(bar_cxfree + 8 * b);
+                            }
+                            epi_it++;
+                            resolving = false;
+                        }
+                    }
+                }
+            }
+            if (!progressed) __nanosleep(100);
+        }
+        return;
+    }
+
+    // ================================ CONSUMERS ================================
+    for (int it = 0;; it++) {
+        if (!mbar_try(bar_full, it & 1))
+            while (!mbar_try(bar_full, it & 1)) __nanosleep(64);
+        if (tid == 0) trace(a.trace, it, 2);
+        const int pos = ctl[0];
+        if (pos < 0) break;
+        const int p0 = a.tile_list[pos] * T, wt = min(T, plane - p0);
+        const int lp0 = 4 * tid;
+        const bool active = lp0 < wt;
+        const int row = (p0 + lp0) / W;
+        const int xt = (p0 + lp0) - row * W;
+        const int y = a.row0 + row;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(slot);
+
+        // ---------------- integer phase: mask, fringe terms, Gray bits ----------------
+        uint32_t mbits = 0;
+        Terms Tv, Th;
+        uint32_t gvA = 0, gvB = 0, ghA = 0, ghB = 0;
+        if (active) {
+            const bool window_ok = y >= 2 && y + 1 < a.H_total && xt >= 4 && xt + 7 < W;
+            bool fast = false;
+            if (window_ok) {
+                uint32_t any_zero = 0;
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(sroi + r * G.roi_row + (lp0 + ROI_HALO - 4) + 4 * c);
+                        any_zero |= (v - 0x01010101u) & ~v & 0x80808080u;
+                    }
+                if (any_zero == 0) { mbits = 0xf; fast = true; }
+            }
+            if (!fast) {
+                const uint32_t centre = *reinterpret_cast<const uint32_t*>(sroi + 2 * G.roi_row + lp0 + ROI_HALO);
+                if (centre != 0) {
+#pragma unroll 1
+                    for (int j = 0; j < 4; j++) {
+                        const int x = xt + j;
+                        auto inv = [&](int gx, int gy) {
+                            return sroi[(gy - y + 2) * G.roi_row + (lp0 + j + (gx - x) + ROI_HALO)] == 0;
+                        };
+                        bool v = !inv(x, y);
+                        const bool border = x == 0 || y == 0 || x == W - 1 || y == a.H_total - 1;
+                        if (v && !border) v = !mask_trigger(x, y, W, a.H_total, inv);
+                        mbits |= (v ? 1u : 0u) << j;
+                    }
+                }
+            }
+            if (mbits) {
+                fringe_terms<N>(sw, 0, WPF, tid, Tv);
+                gray_bits(sw, N, N + a.M_v, a.M_v, WPF, tid, gvA, gvB);
+                if (DIRS == 2) {
+                    const int fh = N + 2 * a.M_v;
+                    fringe_terms<N>(sw, fh, WPF, tid, Th);
+                    gray_bits(sw, fh + N, fh + N + a.M_h, a.M_h, WPF, tid, ghA, ghB);
+                }
+            }
+        }
+        // this warp is done with the slot: the IO warp may refill it once every warp has arrived
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free);
+        if (tid == 0) trace(a.trace, it, 3);
+
+        // ---------------- FP64 phase (registers only) ----------------
+        uint32_t vbits = 0;
+        int4 cp01 = make_int4(0, 0, 0, 0), cp23 = cp01;   // the 4 pixels' correspondences, for the triangulation below
+        if (active) {
+            float r_unwv[4], r_unwh[4];
+            int r_cv[4], r_ch[4];
+            int2 r_cp[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int x = xt + j;
+                const bool m = (mbits >> j) & 1u;
+                const int cv = code_of(gvA, gvB, j, a.M_v);
+                const float wv = add_pi(phase_of<N>(Tv, j, tab));                    // 4/phase_unwrap.cpp:290
+                float unwv = (x == 0 || x == W - 1) ? 0.0f : unwrap_abs(wv, cv, fastdiv);  // :285, :291
+                unwv = m ? unwv : 0.0f;
+                bool v = m;
+                r_cv[j] = m ? cv : -1;
+                if (DIRS == 2) {
+                    const int ch = code_of(ghA, ghB, j, a.M_h);
+                    const float wh = add_pi(phase_of<N>(Th, j, tab));
+                    float unwh = (y == 0 || y == a.H_total - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);  // :304, :309
+                    unwh = m ? unwh : 0.0f;
+                    long long px = 0, py = 0;                                         // 5/compute_correspondance.cpp:648-675
+                    const bool okx = correspond(unwv, a.fw_v, &px, fastdiv);
+                    const bool oky = correspond(unwh, a.fw_h, &py, fastdiv);
+                    r_cp[j].x = (m && okx) ? sat32(px) : 0;
+                    r_cp[j].y = (m && okx && oky) ? sat32(py) : 0;
+                    v = m && okx && oky && !(px > a.PW - 1 || py > a.PH - 1 || px < 0 || py < 0);
+                    r_unwh[j] = unwh;
+                    r_ch[j] = m ? ch : -1;
+                }
+                r_unwv[j] = unwv;
+                vbits |= (v ? 1u : 0u) << j;
+            }
+            // plane outputs: the thread's 4 pixels are consecutive -> one vector store per plane
+            const size_t g = (size_t)p0 + lp0;
+            *reinterpret_cast<float4*>(a.unw_v + g) = make_float4(r_unwv[0], r_unwv[1], r_unwv[2], r_unwv[3]);
+            *reinterpret_cast<uint2*>(a.code_v + g) =
+                make_uint2((uint32_t)(r_cv[0] & 0xffff) | ((uint32_t)r_cv[1] << 16), (uint32_t)(r_cv[2] & 0xffff) | ((uint32_t)r_cv[3] << 16));
+            *reinterpret_cast<uint32_t*>(a.valid + g) =
+                (vbits & 1u) | ((vbits & 2u) << 7) | ((vbits & 4u) << 14) | ((vbits & 8u) << 21);
+            if (DIRS == 2) {
+                *reinterpret_cast<float4*>(a.unw_h + g) = make_float4(r_unwh[0], r_unwh[1], r_unwh[2], r_unwh[3]);
+                *reinterpret_cast<uint2*>(a.code_h + g) =
+                    make_uint2((uint32_t)(r_ch[0] & 0xffff) | ((uint32_t)r_ch[1] << 16), (uint32_t)(r_ch[2] & 0xffff) | ((uint32_t)r_ch[3] << 16));
+                *reinterpret_cast<int4*>(a.cpmap + g) = make_int4(r_cp[0].x, r_cp[0].y, r_cp[1].x, r_cp[1].y);
+                *reinterpret_cast<int4*>(a.cpmap + g + 2) = make_int4(r_cp[2].x, r_cp[2].y, r_cp[3].x, r_cp[3].y);
+                cp01 = make_int4(r_cp[0].x, r_cp[0].y, r_cp[1].x, r_cp[1].y);
+                cp23 = make_int4(r_cp[2].x, r_cp[2].y, r_cp[3].x, r_cp[3].y);
+            }
+        }
+        if (DIRS == 2) {
+            // ---- block scan of the valid counts first: every pixel then knows its raster rank in
+            //      the tile, and the triangulation writes its point straight to that rank ----
+            const int b = it & 1;
+            const uint32_t cnt = __popc(vbits);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            // buffer b (points, counts, valid bits) must have been drained by the IO warp (tile it-2)
+            if (!mbar_try(bar_cxfree + 8 * b, ((it >> 1) & 1) ^ 1))
+                while (!mbar_try(bar_cxfree + 8 * b, ((it >> 1) & 1) ^ 1)) __nanosleep(64);
+            if (lane == 31) cnts[b * 16 + warp] = incl;
+            cons_sync<NCONS>();
+            uint32_t rank = incl - cnt;
+#pragma unroll
+            for (int w2 = 0; w2 < CW; w2++) rank += w2 < warp ? cnts[b * 16 + w2] : 0u;
+            float* cx = cxb + b * 3 * T;
+            vfl[b * (T / 4) + tid] = (uint8_t)vbits;
+            // triangulation of the surviving pixels (7/triangulation.cpp:1230-1247)
+#pragma unroll 1
+            for (int j = 0; j < 4; j++) {
+                if (!((vbits >> j) & 1u)) continue;
+                const int x = xt + j;
+                const int cpx = j == 0 ? cp01.x : j == 1 ? cp01.z : j == 2 ? cp23.x : cp23.z;
+                const int cpy = j == 0 ? cp01.y : j == 1 ? cp01.w : j == 2 ? cp23.y : cp23.w;
+                double uc, vc, up, vp, Xd[3];
+                if (a.cam_lut) {
+                    const double2 t = a.cam_lut[(size_t)p0 + lp0 + j];
+                    uc = t.x; vc = t.y;
+                } else {
+                    undistorted_pixel_nodist(cal.Kc, cal.ifx_c, cal.ify_c, cal.cam_std != 0, (double)x, (double)y, &uc, &vc);
+                }
+                if (a.proj_lut) {
+                    const double2 t = a.proj_lut[(size_t)cpy * a.PW + cpx];
+                    up = t.x; vp = t.y;
+                } else {
+                    undistorted_pixel_nodist(cal.Kp, cal.ifx_p, cal.ify_p, cal.proj_std != 0, (double)cpx, (double)cpy, &up, &vp);
+                }
+                if (EXACT) triangulate_point(cal.Ac, cal.Ap, uc, vc, up, vp, Xd);
+                else triangulate_point_fast(cal.Ac, cal.Ap, uc, vc, up, vp, Xd);
+                cx[3 * rank + 0] = __double2float_rn(Xd[0]);                       // 8/save_point_cloud.cpp:94-96
+                cx[3 * rank + 1] = __double2float_rn(Xd[1]);
+                cx[3 * rank + 2] = __double2float_rn(Xd[2]);
+                rank++;
+            }
+            if (tid == 0) {
+                ctl[1 + b] = pos;
+                trace(a.trace, it, 4);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_staged + 8 * b);
+        }
+    }
+}
+
+template <int N, int DIRS, int CW, int MINB, bool EXACT>
+static cudaError_t launch7_t(const FusedArgs& a, const DeviceCalib& cal, int sm_count, const Plan7& p, cudaStream_t st)
+{
+    auto kern = k_fused7<N, DIRS, CW, MINB, EXACT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (CW + 1) * 32, p.smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    if (getenv("SCAN3D_DEBUG")) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, kern);
+        fprintf(stderr, "k_fused7<%d,%d,%d,%d,%d>: occupancy %d CTAs/SM, %d regs, %zu B dyn smem, %zu B static, local %zu B\n", N, DIRS, CW, MINB,
+                (int)EXACT, per_sm, fa.numRegs, p.smem, fa.sharedSizeBytes, fa.localSizeBytes);
+    }
+    if (per_sm > MINB) per_sm = MINB;
+    const int grid = a.n_tiles < sm_count * per_sm ? a.n_tiles : sm_count * per_sm;   // all CTAs resident
+    e = launch_worklist(a, 128 * CW, DIRS, st);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, (CW + 1) * 32, p.smem, st>>>(a, cal);
+    return cudaGetLastError();
+}
+
+template <int N, int DIRS>
+static cudaError_t launch7_nd(const FusedArgs& a, const DeviceCalib& cal, int sm_count, const Plan7& p, bool exact,
+                              cudaStream_t st)
+{
+#define S3D_CASE7(CWV, MB)                                                                        \
+    if (p.cw == CWV && p.minb == MB) {                                                            \
+        if (exact || DIRS == 1) return launch7_t<N, DIRS, CWV, MB, true>(a, cal, sm_count, p, st); \
+        return launch7_t<N, DIRS, CWV, MB, (DIRS == 1)>(a, cal, sm_count, p, st);                  \
+    }
+    S3D_CASE7(7, 2) S3D_CASE7(7, 3) S3D_CASE7(9, 2) S3D_CASE7(4, 4) S3D_CASE7(6, 2) S3D_CASE7(5, 4)
+#undef S3D_CASE7
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_fused7(const scan3d_config& c, const FusedArgs& a_in, const DeviceCalib& cal, int sm_count,
+                          cudaStream_t st)
+{
+    Plan7 p;
+    if (!plan7(c, &p)) return cudaErrorInvalidValue;
+    if (((uintptr_t)a_in.stack & 15) || ((uintptr_t)a_in.roi & 15)) return cudaErrorMisalignedAddress;
+    FusedArgs a = a_in;
+    const int T = 128 * p.cw;
+    a.tiles_per_row = 0;
+    a.n_tiles = (int)(((size_t)c.W * c.H + T - 1) / T);
+    const bool exact = !(c.flags & SCAN3D_FLAG_FAST_TRIANGULATION);
+#define S3D_F7(NN) (c.dirs == 2 ? launch7_nd<NN, 2>(a, cal, sm_count, p, exact, st) : launch7_nd<NN, 1>(a, cal, sm_count, p, exact, st))
+    switch (c.N) {
+        case 3: return S3D_F7(3);
+        case 4: return S3D_F7(4);
+        case 5: return S3D_F7(5);
+        case 8: return S3D_F7(8);
+    }
+#undef S3D_F7
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace s3d

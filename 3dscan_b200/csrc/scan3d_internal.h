@@ -126,6 +126,11 @@ int fused_num_tiles(const scan3d_config& c);
 cudaError_t launch_fused(const scan3d_config& c, const FusedArgs& a, const DeviceCalib& cal,
                          int sm_count, cudaStream_t st);
 
+// second-generation fused kernel (scan3d_fused_kernel7.cu); SCAN3D_FUSED_IMPL=6|7 selects
+bool fused7_supported(const scan3d_config& c);
+cudaError_t launch_fused7(const scan3d_config& c, const FusedArgs& a, const DeviceCalib& cal,
+                          int sm_count, cudaStream_t st);
+
 // ---- debug / self-test ----
 cudaError_t launch_debug_atan2(const double* y, const double* x, float* out, int n, int mode,
                                const double* atan_tab, cudaStream_t st);

@@ -1,13 +1,9 @@
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 PYFMT='import sys,json
-d=json.loads(sys.stdin.read()); r=d["roofline"]; print(d["config"]["workload"][:3], d["config"]["fused_cfg"], d["config"]["triangulation"][:9], "us/scan %.1f"%r["avg_launch_us"], "frac %.3f"%r["frac"], "scans/s %.0f"%d["scans_per_s"], "Mpix/s %.0f"%d["value"], "clk", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])'
-for mode in "" "--exact-triangulation"; do
-for cfg in 4,3,2 6,2,2; do
-  SCAN3D_FUSED_CFG=$cfg timeout 120 python bench.py --steps 5 --ring 2 --batch 8 --no-e2e --no-cpu-baseline $mode 2>&1 | tail -1 | python -c "$PYFMT"
+d=json.loads(sys.stdin.read()); r=d["roofline"]; print(d["config"]["workload"][:3], d["config"]["fused_cfg"], d["config"]["triangulation"][:9], "us/scan %.1f"%r["avg_launch_us"], "frac %.3f"%r["frac"], "scans/s %.0f"%d["scans_per_s"], "clk", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])'
+for cfg in 7,3 9,2; do
+  SCAN3D_DEBUG=1 SCAN3D_FUSED_CFG=$cfg,1 timeout 90 python bench.py --steps 5 --ring 2 --batch 8 --no-e2e --no-cpu-baseline 2> gpurun_out/err.txt | tail -1 | python -c "$PYFMT"; grep -m1 occupancy gpurun_out/err.txt
 done
-done
-for wl in c2_1080p_3step_8bit_v c1_1600x1200_3step_6bit_vh; do
-for cfg in 4,3,2 6,2,2 8,1,3; do
-  SCAN3D_FUSED_CFG=$cfg timeout 120 python bench.py --workload $wl --steps 5 --ring 8 --batch 32 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | python -c "$PYFMT"
-done
-done
+for wl in c2_1080p_3step_8bit_v c1_1600x1200_3step_6bit_vh; do for cfg in 9,2 7,2 4,4; do
+  SCAN3D_FUSED_CFG=$cfg,1 timeout 90 python bench.py --workload $wl --steps 5 --ring 8 --batch 32 --no-e2e --no-cpu-baseline 2>/dev/null | tail -1 | python -c "$PYFMT"
+done; done
+timeout 200 python tools/trace_fused.py 2>&1 | tail -7
