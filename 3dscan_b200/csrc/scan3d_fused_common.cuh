@@ -82,12 +82,13 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
 }
 
 // ---- SWAR pieces -----------------------------------------------------------------------------
-// per-byte unsigned a >= b  ->  bit 7 of each byte
-__device__ __forceinline__ uint32_t ge_bytes(uint32_t a, uint32_t b)
+// per-byte unsigned a >= b  ->  bit 7 of each byte (the other bits are NOT cleared: callers mask)
+__device__ __forceinline__ uint32_t ge_bytes_raw(uint32_t a, uint32_t b)
 {
     const uint32_t d = (a | 0x80808080u) - (b & 0x7f7f7f7fu);
-    return ((a & ~b) | (~(a ^ b) & d)) & 0x80808080u;
+    return (a & ~b) | (~(a ^ b) & d);
 }
+__device__ __forceinline__ uint32_t ge_bytes(uint32_t a, uint32_t b) { return ge_bytes_raw(a, b) & 0x80808080u; }
 // bytes (b0,b1,b2,b3) -> 16-bit lanes (b0,b1) and (b2,b3)
 __device__ __forceinline__ uint32_t lanes_lo(uint32_t w) { return __byte_perm(w, 0, 0x4140); }
 __device__ __forceinline__ uint32_t lanes_hi(uint32_t w) { return __byte_perm(w, 0, 0x4342); }
@@ -137,12 +138,13 @@ __device__ __forceinline__ void gray_bits(const uint32_t* __restrict__ sw, int g
                                           uint32_t& accA, uint32_t& accB)
 {
     accA = 0; accB = 0;
+    // shift first, then mask and merge in one 3-input logic op: acc | ((ge >> i) & (0x80808080 >> i))
 #pragma unroll
     for (int i = 0; i < 8; i++)
-        if (i < M) accA |= ge_bytes(sw[(g0 + i) * wpf + tid], sw[(i0 + i) * wpf + tid]) >> i;
+        if (i < M) accA |= (ge_bytes_raw(sw[(g0 + i) * wpf + tid], sw[(i0 + i) * wpf + tid]) >> i) & (0x80808080u >> i);
 #pragma unroll
     for (int i = 8; i < 15; i++)
-        if (i < M) accB |= ge_bytes(sw[(g0 + i) * wpf + tid], sw[(i0 + i) * wpf + tid]) >> (i - 8);
+        if (i < M) accB |= (ge_bytes_raw(sw[(g0 + i) * wpf + tid], sw[(i0 + i) * wpf + tid]) >> (i - 8)) & (0x80808080u >> (i - 8));
 }
 // Gray -> binary (B0 = G0, Bi = B(i-1) xor Gi) as a prefix xor; code = sum Bi << (M-1-i)  (:187-193)
 __device__ __forceinline__ int code_of(uint32_t accA, uint32_t accB, int j, int M)

@@ -394,12 +394,14 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     const float wh = add_pi(phase_of<N>(Th, j, tab));
                     float unwh = (y == 0 || y == a.H_total - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);  // :304, :309
                     unwh = m ? unwh : 0.0f;
-                    long long px = 0, py = 0;                                         // 5/compute_correspondance.cpp:648-675
-                    const bool okx = correspond(unwv, a.fw_v, &px, fastdiv);
-                    const bool oky = correspond(unwh, a.fw_h, &py, fastdiv);
-                    r_cp[j].x = (m && okx) ? sat32(px) : 0;
-                    r_cp[j].y = (m && okx && oky) ? sat32(py) : 0;
-                    v = m && okx && oky && !(px > a.PW - 1 || py > a.PH - 1 || px < 0 || py < 0);
+                    int px, py;                                                       // 5/compute_correspondance.cpp:648-675
+                    const bool okx = correspond32(unwv, a.fw_v, &px);
+                    const bool oky = correspond32(unwh, a.fw_h, &py);
+                    // FE_INVALID on x rejects before y is computed (:650-655); on y after x is stored
+                    r_cp[j].x = (m && okx) ? px : 0;
+                    r_cp[j].y = (m && okx && oky) ? py : 0;
+                    // 0 <= p <= P-1 as one unsigned compare (saturated values fall outside as well)
+                    v = m && okx && oky && (unsigned)px <= (unsigned)(a.PW - 1) && (unsigned)py <= (unsigned)(a.PH - 1);
                     r_unwh[j] = unwh;
                     r_ch[j] = m ? ch : -1;
                 }

@@ -236,6 +236,14 @@ __device__ __forceinline__ bool correspond(float phi_abs, int fw, long long* out
     *out = __double2ll_rn(v);
     return (v == v) && v < 9223372036854775808.0 && v >= -9223372036854775808.0;
 }
+// Same decision in 32 bits for the fused kernels: cvt.rni.s32.f64 saturates exactly like the
+// clamp of the 64-bit lrint to int, NaN converts to 0 and fails the |v| < 2^63 test (FE_INVALID).
+__device__ __forceinline__ bool correspond32(float phi_abs, int fw, int* out)
+{
+    const double v = dmul((double)fw, div_const((double)phi_abs, S3D_TWO_PI_REF, 1.0 / (S3D_TWO_PI_REF), true));
+    *out = __double2int_rn(v);
+    return fabs(v) < 9223372036854775808.0;
+}
 
 // ---------------------------------------------------------------------------------------
 // calibration algebra on the device
