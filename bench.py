@@ -291,16 +291,26 @@ def main():
         return bench_rowshard(args, s3, cal, cfg, config, rank, world, local_rank, stream, barrier, bpp)
     ctx = s3.Scan3D(cfg, local_rank, cal, stream=stream.cuda_stream)
     nf = s3.stack_planes(cfg)
-    # resident ring of distinct synthetic scans (scan index = global, so ranks hold different scans)
-    ring, rois = [], []
+    # Resident ring of distinct scans.  One synthetic capture is rendered on the host (rank 0, all
+    # host threads) and broadcast over NCCL; ring member k of rank r is that capture shifted by a
+    # rank- and k-specific number of columns (stack and ROI alike): every member is a valid capture
+    # of the shifted scene in its own memory, so the ring (>> L2) is never served from cache.
     host_stack = torch.empty((nf, H, W), dtype=torch.uint8, pin_memory=True)
     host_roi = torch.empty((H, W), dtype=torch.uint8, pin_memory=True)
+    if rank == 0:
+        s3.synth_stack(cfg, cal, s3.default_synth_params(seed=0x3D5CA9), out=host_stack.numpy(), roi_out=host_roi.numpy())
+    base_stack = host_stack.to("cuda")
+    base_roi = host_roi.to("cuda")
+    if world > 1:
+        dist.broadcast(base_stack, 0)
+        dist.broadcast(base_roi, 0)
+        host_stack.copy_(base_stack)      # every rank's e2e leg reads its own pinned copy
+        host_roi.copy_(base_roi)
+    ring, rois = [], []
     for i in range(args.ring):
-        prm = s3.default_synth_params(seed=0x3D5CA9 + rank * args.ring + i,
-                                      sphere_c=(60.0 + 3.0 * i, 40.0 - 2.0 * i, -30.0 - 1.5 * rank))
-        s3.synth_stack(cfg, cal, prm, out=host_stack.numpy(), roi_out=host_roi.numpy())
-        ring.append(host_stack.to("cuda", non_blocking=False))
-        rois.append(host_roi.to("cuda", non_blocking=False))
+        shift = 16 * ((rank * args.ring + i) * 7 % (W // 16))
+        ring.append(torch.roll(base_stack, shifts=shift, dims=2) if shift else base_stack)
+        rois.append(torch.roll(base_roi, shifts=shift, dims=1) if shift else base_roi)
     torch.cuda.synchronize()
 
     def step():
