@@ -52,12 +52,12 @@ static bool plan7(const scan3d_config& c, Plan7* out)
     // Shapes are bounded by the register file of an SM sub-partition (16 K registers): warps are
     // dealt round-robin to the 4 sub-partitions, so ceil(warps per SM / 4) * 32 * regs <= 16384:
     // 20 warps at 96 registers, 16 at 128, 24 at 80.
-    int cw = 9, minb = 2;
+    int cw = 7, minb = 3;
     if (const char* e = getenv("SCAN3D_FUSED_CFG")) {
         int a = 0, b = 0, s = 0;
         if (sscanf(e, "%d,%d,%d", &a, &b, &s) >= 2) { cw = a; minb = b; }
     }
-    const int shapes[7][2] = {{cw, minb}, {9, 2}, {7, 2}, {7, 3}, {4, 4}, {6, 2}, {5, 4}};
+    const int shapes[7][2] = {{cw, minb}, {7, 3}, {9, 2}, {7, 2}, {4, 4}, {6, 2}, {5, 4}};
     for (int i = 0; i < 7; i++) {
         const int w = shapes[i][0], b = shapes[i][1];
         if (!((w == 7 && b == 2) || (w == 7 && b == 3) || (w == 9 && b == 2) || (w == 4 && b == 4) || (w == 6 && b == 2) || (w == 5 && b == 4))) continue;
@@ -376,53 +376,59 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
         uint32_t vbits = 0;
         int4 cp01 = make_int4(0, 0, 0, 0), cp23 = cp01;   // the 4 pixels' correspondences, for the triangulation below
         if (active) {
-            float r_unwv[4], r_unwh[4];
-            int r_cv[4], r_ch[4];
-            int2 r_cp[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int x = xt + j;
-                const bool m = (mbits >> j) & 1u;
-                const int cv = code_of(gvA, gvB, j, a.M_v);
-                const float wv = add_pi(phase_of<N>(Tv, j, tab));                    // 4/phase_unwrap.cpp:290
-                float unwv = (x == 0 || x == W - 1) ? 0.0f : unwrap_abs(wv, cv, fastdiv);  // :285, :291
-                unwv = m ? unwv : 0.0f;
-                bool v = m;
-                r_cv[j] = m ? cv : -1;
-                if (DIRS == 2) {
-                    const int ch = code_of(ghA, ghB, j, a.M_h);
-                    const float wh = add_pi(phase_of<N>(Th, j, tab));
-                    float unwh = (y == 0 || y == a.H_total - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);  // :304, :309
-                    unwh = m ? unwh : 0.0f;
-                    int px, py;                                                       // 5/compute_correspondance.cpp:648-675
-                    const bool okx = correspond32(unwv, a.fw_v, &px);
-                    const bool oky = correspond32(unwh, a.fw_h, &py);
-                    // FE_INVALID on x rejects before y is computed (:650-655); on y after x is stored
-                    r_cp[j].x = (m && okx) ? px : 0;
-                    r_cp[j].y = (m && okx && oky) ? py : 0;
-                    // 0 <= p <= P-1 as one unsigned compare (saturated values fall outside as well)
-                    v = m && okx && oky && (unsigned)px <= (unsigned)(a.PW - 1) && (unsigned)py <= (unsigned)(a.PH - 1);
-                    r_unwh[j] = unwh;
-                    r_ch[j] = m ? ch : -1;
-                }
-                r_unwv[j] = unwv;
-                vbits |= (v ? 1u : 0u) << j;
-            }
-            // plane outputs: the thread's 4 pixels are consecutive -> one vector store per plane
+            // Two passes of 2 pixels: inside a pass everything is straight-line (2 pixels x 2
+            // directions interleave in the FP64 pipe); the pass loop is rolled to keep the
+            // consumer loop inside the instruction cache.
             const size_t g = (size_t)p0 + lp0;
-            *reinterpret_cast<float4*>(a.unw_v + g) = make_float4(r_unwv[0], r_unwv[1], r_unwv[2], r_unwv[3]);
-            *reinterpret_cast<uint2*>(a.code_v + g) =
-                make_uint2((uint32_t)(r_cv[0] & 0xffff) | ((uint32_t)r_cv[1] << 16), (uint32_t)(r_cv[2] & 0xffff) | ((uint32_t)r_cv[3] << 16));
-            *reinterpret_cast<uint32_t*>(a.valid + g) =
-                (vbits & 1u) | ((vbits & 2u) << 7) | ((vbits & 4u) << 14) | ((vbits & 8u) << 21);
-            if (DIRS == 2) {
-                *reinterpret_cast<float4*>(a.unw_h + g) = make_float4(r_unwh[0], r_unwh[1], r_unwh[2], r_unwh[3]);
-                *reinterpret_cast<uint2*>(a.code_h + g) =
-                    make_uint2((uint32_t)(r_ch[0] & 0xffff) | ((uint32_t)r_ch[1] << 16), (uint32_t)(r_ch[2] & 0xffff) | ((uint32_t)r_ch[3] << 16));
-                *reinterpret_cast<int4*>(a.cpmap + g) = make_int4(r_cp[0].x, r_cp[0].y, r_cp[1].x, r_cp[1].y);
-                *reinterpret_cast<int4*>(a.cpmap + g + 2) = make_int4(r_cp[2].x, r_cp[2].y, r_cp[3].x, r_cp[3].y);
-                cp01 = make_int4(r_cp[0].x, r_cp[0].y, r_cp[1].x, r_cp[1].y);
-                cp23 = make_int4(r_cp[2].x, r_cp[2].y, r_cp[3].x, r_cp[3].y);
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                float r_unwv[2], r_unwh[2];
+                int r_cv[2], r_ch[2];
+                int2 r_cp[2];
+                uint32_t vb = 0;
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int j = 2 * h + u;
+                    const int x = xt + j;
+                    const bool m = (mbits >> j) & 1u;
+                    const int cv = code_of(gvA, gvB, j, a.M_v);
+                    const float wv = add_pi(phase_of<N>(Tv, j, tab));                    // 4/phase_unwrap.cpp:290
+                    float unwv = (x == 0 || x == W - 1) ? 0.0f : unwrap_abs(wv, cv, fastdiv);  // :285, :291
+                    unwv = m ? unwv : 0.0f;
+                    bool v = m;
+                    r_cv[u] = m ? cv : -1;
+                    if (DIRS == 2) {
+                        const int ch = code_of(ghA, ghB, j, a.M_h);
+                        const float wh = add_pi(phase_of<N>(Th, j, tab));
+                        float unwh = (y == 0 || y == a.H_total - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);  // :304, :309
+                        unwh = m ? unwh : 0.0f;
+                        int px, py;                                                       // 5/compute_correspondance.cpp:648-675
+                        const bool okx = correspond32(unwv, a.fw_v, &px);
+                        const bool oky = correspond32(unwh, a.fw_h, &py);
+                        // FE_INVALID on x rejects before y is computed (:650-655); on y after x is stored
+                        r_cp[u].x = (m && okx) ? px : 0;
+                        r_cp[u].y = (m && okx && oky) ? py : 0;
+                        // 0 <= p <= P-1 as one unsigned compare (saturated values fall outside as well)
+                        v = m && okx && oky && (unsigned)px <= (unsigned)(a.PW - 1) && (unsigned)py <= (unsigned)(a.PH - 1);
+                        r_unwh[u] = unwh;
+                        r_ch[u] = m ? ch : -1;
+                    }
+                    r_unwv[u] = unwv;
+                    vb |= (v ? 1u : 0u) << u;
+                }
+                // plane outputs of the 2 pixels: one (vector) store per plane
+                const size_t gh = g + 2 * h;
+                *reinterpret_cast<float2*>(a.unw_v + gh) = make_float2(r_unwv[0], r_unwv[1]);
+                *reinterpret_cast<uint32_t*>(a.code_v + gh) = (uint32_t)(r_cv[0] & 0xffff) | ((uint32_t)r_cv[1] << 16);
+                *reinterpret_cast<uint16_t*>(a.valid + gh) = (uint16_t)((vb & 1u) | ((vb & 2u) << 7));
+                if (DIRS == 2) {
+                    *reinterpret_cast<float2*>(a.unw_h + gh) = make_float2(r_unwh[0], r_unwh[1]);
+                    *reinterpret_cast<uint32_t*>(a.code_h + gh) = (uint32_t)(r_ch[0] & 0xffff) | ((uint32_t)r_ch[1] << 16);
+                    const int4 c4 = make_int4(r_cp[0].x, r_cp[0].y, r_cp[1].x, r_cp[1].y);
+                    *reinterpret_cast<int4*>(a.cpmap + gh) = c4;
+                    if (h == 0) cp01 = c4; else cp23 = c4;
+                }
+                vbits |= vb << (2 * h);
             }
         }
         if (DIRS == 2) {
