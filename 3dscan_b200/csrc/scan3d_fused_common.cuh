@@ -132,6 +132,19 @@ __device__ __forceinline__ int term_of(const Terms& T, int k, int j, int bias)
     return (int)((r >> ((j & 1) * 16)) & 0xffffu) - bias;
 }
 
+// Gray -> binary (B0 = G0, Bi = B(i-1) xor Gi, 4/phase_unwrap.cpp:187-191) for the 4 pixels at
+// once: a prefix xor inside every byte (plane i sits at bit 7 - i%8), then the parity of planes
+// 0..7 (bit 0 of the first accumulator) carried into every bit of the second one.
+__device__ __forceinline__ void gray_to_binary(uint32_t& accA, uint32_t& accB)
+{
+    accA ^= (accA >> 1) & 0x7f7f7f7fu;
+    accA ^= (accA >> 2) & 0x3f3f3f3fu;
+    accA ^= (accA >> 4) & 0x0f0f0f0fu;
+    accB ^= (accB >> 1) & 0x7f7f7f7fu;
+    accB ^= (accB >> 2) & 0x3f3f3f3fu;
+    accB ^= (accB >> 4) & 0x0f0f0f0fu;
+    accB ^= (accA & 0x01010101u) * 0xffu;
+}
 // Gray threshold for 4 pixels, all M planes: byte accumulators with plane i at bit (7 - i%8)
 // (4/phase_unwrap.cpp:183: (uchar)img - (uchar)inv >= 0, tie -> 1)
 __device__ __forceinline__ void gray_bits(const uint32_t* __restrict__ sw, int g0, int i0, int M, int wpf, int tid,
@@ -145,28 +158,35 @@ __device__ __forceinline__ void gray_bits(const uint32_t* __restrict__ sw, int g
 #pragma unroll
     for (int i = 8; i < 15; i++)
         if (i < M) accB |= (ge_bytes_raw(sw[(g0 + i) * wpf + tid], sw[(i0 + i) * wpf + tid]) >> (i - 8)) & (0x80808080u >> (i - 8));
+    gray_to_binary(accA, accB);
 }
-// Gray -> binary (B0 = G0, Bi = B(i-1) xor Gi) as a prefix xor; code = sum Bi << (M-1-i)  (:187-193)
-__device__ __forceinline__ int code_of(uint32_t accA, uint32_t accB, int j, int M)
+// fringe order of pixel j from the binary accumulators: code = sum Bi << (M-1-i)  (:193)
+__device__ __forceinline__ int code_of(uint32_t binA, uint32_t binB, int j, int M)
 {
-    const uint32_t a = (accA >> (8 * j)) & 0xffu, b = (accB >> (8 * j)) & 0xffu;
-    uint32_t g = ((a << 8) | b) >> (16 - M);
-    g ^= g >> 1; g ^= g >> 2; g ^= g >> 4; g ^= g >> 8;
-    return (int)g;
+    const uint32_t a = (binA >> (8 * j)) & 0xffu, b = (binB >> (8 * j)) & 0xffu;
+    return (int)(((a << 8) | b) >> (16 - M));
+}
+
+// biased 16-bit lane -> exact double without the conversion pipe: the lane value u (< 2^16) is
+// dropped into the mantissa of 2^52 and (2^52 + bias) is subtracted
+__device__ __forceinline__ double term_f64(const Terms& T, int k, int j, int bias)
+{
+    const uint32_t r = (j & 2) ? T.t[k][1] : T.t[k][0];
+    const uint32_t u = (j & 1) ? (r >> 16) : (r & 0xffffu);
+    return __hiloint2double(0x43300000, (int)u) - (4503599627370496.0 + (double)bias);
 }
 
 template <int N>
 __device__ __forceinline__ float phase_of(const Terms& T, int j, const double* tab)
 {
     if (N == 8) {
-        const int a1 = term_of(T, 0, j, 512), b1 = term_of(T, 1, j, 1024);
-        const int a2 = term_of(T, 2, j, 512), b2 = term_of(T, 3, j, 1024);
+        const double a1 = term_f64(T, 0, j, 512), b1 = term_f64(T, 1, j, 1024);
+        const double a2 = term_f64(T, 2, j, 512), b2 = term_f64(T, 3, j, 1024);
         const double r = 0.70710678118654752440;
-        const double d1 = dadd((double)a1, dmul((double)b1, r));
-        const double d2 = dadd((double)a2, dmul((double)b2, r));
-        const float f1 = fmaf((float)b1, 0.70710678f, (float)a1);
-        const float f2 = fmaf((float)b2, 0.70710678f, (float)a2);
-        return atan2_to_float(d1, d2, f1, f2, tab);
+        const double d1 = dadd(a1, dmul(b1, r));
+        const double d2 = dadd(a2, dmul(b2, r));
+        // float approximations only pick the atan table row
+        return atan2_to_float(d1, d2, __double2float_rz(d1), __double2float_rz(d2), tab);
     } else {
         const int t1 = term_of(T, 0, j, N == 5 ? 1024 : 512);
         const int t2 = term_of(T, 1, j, N == 4 ? 512 : 1024);

@@ -191,6 +191,7 @@ __global__ void k_tile_list(const uint8_t* __restrict__ flags, int n_tiles, int*
         if (flags[i]) list[pos++] = i;
     if (threadIdx.x == 0) {
         *n_list = wsum[31];
+        n_list[n_tiles + 8] = 0;   // v7 dynamic scheduler: next work-list position
         *d_count = 0;   // overwritten by the fused kernel's last tile when there is any work
     }
 }

@@ -28,7 +28,7 @@ struct Geom7 {
 };
 __host__ __device__ constexpr Geom7 geom7(int T) { return Geom7{T, T + 2 * ROI_HALO, 4 * (T + 2 * ROI_HALO)}; }
 
-constexpr int FIXED7 = 64 /*6 mbarriers*/ + ATAN_TAB_DOUBLES * 8 + 16 /*cur_pos, staged_pos[2]*/ + 128 /*cnt[2][16]*/;
+constexpr int FIXED7 = 64 /*8 mbarriers*/ + ATAN_TAB_DOUBLES * 8 + 16 /*cur_pos*/ + 128 /*cnt[2][16]*/ + 32 /*pos ring[8]*/;
 
 static int num_frames7(const scan3d_config& c)
 {
@@ -104,8 +104,9 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
     double* tab = reinterpret_cast<double*>(bars + 8);
     volatile int* ctl = reinterpret_cast<volatile int*>(tab + ATAN_TAB_DOUBLES);   // [0] cur_pos, [1..2] staged_pos
     volatile uint32_t* cnts = reinterpret_cast<volatile uint32_t*>(const_cast<int*>(ctl) + 4);   // [2][16]
+    volatile int* posr = reinterpret_cast<volatile int*>(const_cast<uint32_t*>(cnts) + 32);       // [8] list positions of the tiles in flight
     const uint32_t bar_full = smem_u32(bars), bar_free = smem_u32(bars + 1), bar_staged = smem_u32(bars + 2),
-                   bar_cxfree = smem_u32(bars + 4);
+                   bar_cxfree = smem_u32(bars + 4), bar_counted = smem_u32(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int W = a.W;
@@ -118,38 +119,48 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
         mbar_init(bar_staged + 8, CW);
         mbar_init(bar_cxfree, 1);
         mbar_init(bar_cxfree + 8, 1);
+        mbar_init(bar_counted, 1);
+        mbar_init(bar_counted + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
     for (int i = tid; i < ATAN_TAB_DOUBLES; i += (CW + 1) * 32) tab[i] = a.atan_tab[i];
     __syncthreads();
 
-    // static, phase-aligned schedule over the work list (see scan3d_fused_kernel.cu)
+    // Work-list positions are handed out in order.  Static mode: CTA b takes b, b + G, b + 2G, ...
+    // Dynamic mode: the IO warp draws the next position from a global counter whenever its slot
+    // frees.  The CTAs of an SM do not run at the same speed (the warp schedulers favour the
+    // lower warp slots: measured 14k / 15k / 19k cycles per tile for the 1st / 2nd / 3rd CTA of an
+    // SM), so equal shares leave the fast CTAs waiting for the slow one's counts.
     const int n_work = *a.n_list;
     const int Gsz = (int)gridDim.x, bid = (int)blockIdx.x;
-    const int n_mine = bid < n_work ? (n_work - bid + Gsz - 1) / Gsz : 0;
+    int* const next_pos = a.n_list + a.n_tiles + 8;      // zeroed by k_tile_list
 
     if (warp == CW) {
         // ================================ IO WARP (producer + epilogue) ================================
         const unsigned long long tag = (unsigned long long)(a.epoch & 0x3fffffffu) << 34;
         const long long roi_total = (long long)W * a.H_total;
         int load_it = 0;                         // next tile to load
-        int agg_it = DIRS == 2 ? 0 : n_mine;     // next staged tile whose count gets published
-        int epi_it = agg_it;                     // next tile whose points get streamed out
+        int agg_it = 0;                          // next counted tile whose count gets published
+        int epi_it = 0;                          // next tile whose points get streamed out
         bool ended = false;
-        bool resolving = false;
+        bool resolving = false, published = false;
         int look = 0;
         uint32_t excl = 0;
         uint32_t tot[2] = {0, 0};
         int epos[2] = {0, 0};
         bool skip[2] = {false, false};
-        while (!ended || epi_it < n_mine) {
+        while (!ended || (DIRS == 2 && epi_it < load_it)) {
             bool progressed = false;
             // ---- (1) the slot is free again: issue the next tile's loads (or the end marker) ----
             if (!ended && __any_sync(0xffffffffu, mbar_try(bar_free, (load_it & 1) ^ 1))) {
                 progressed = true;
-                if (load_it < n_mine) {
-                    const int pos = load_it * Gsz + bid;
+                int pos = load_it * Gsz + bid;
+                if (a.dynamic) {
+                    if (lane == 0) pos = atomicAdd(next_pos, 1);
+                    pos = __shfl_sync(0xffffffffu, pos, 0);
+                }
+                if (pos < n_work) {
                     const int tile = a.tile_list[pos];
                     const int p0 = tile * T, wt = min(T, plane - p0);
                     const long long gbase = (long long)a.row0 * W + p0 - ROI_HALO;
@@ -167,6 +178,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     if (lane == 0) {
                         trace(a.trace, load_it, 0);
                         ctl[0] = pos;
+                        posr[load_it & 7] = pos;
                         mbar_expect_tx(bar_full, (uint32_t)NF * wt + roi_sum);
                     }
                     __syncwarp();
@@ -187,12 +199,14 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 }
             }
             if (DIRS == 2) {
-                // ---- (2) a tile got staged: publish its count at once (never behind a look-back) ----
-                if (agg_it < n_mine && agg_it < epi_it + 2 &&
-                    __any_sync(0xffffffffu, mbar_try(bar_staged + 8 * (agg_it & 1), (agg_it >> 1) & 1))) {
+                // ---- (2) a tile's valid pixels are counted (its triangulation is still running):
+                //      publish the count at once, so that the prefix chain of the whole grid runs
+                //      ahead of the triangulation instead of behind it ----
+                if (agg_it < load_it && agg_it < epi_it + 2 &&
+                    __any_sync(0xffffffffu, mbar_try(bar_counted + 8 * (agg_it & 1), (agg_it >> 1) & 1))) {
                     progressed = true;
                     const int b = agg_it & 1;
-                    const int pos = ctl[1 + b];
+                    const int pos = posr[agg_it & 7];
                     uint32_t total = lane < CW ? cnts[b * 16 + lane] : 0u;
 #pragma unroll
                     for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
@@ -206,22 +220,26 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                             const unsigned long long w = ld_state(a.tile_state + pos - 1);
                             const bool fwd = (w >> 34) == (tag >> 34) && ((w >> 32) & 3ull) == 2;
                             st_state(a.tile_state + pos, fwd ? w : (tag | (1ull << 32)));
-                            mbar_arrive(bar_cxfree + 8 * b);
                         }
-                    } else if (pos > 0 && lane == 0) {
-                        st_state(a.tile_state + pos, tag | (1ull << 32) | total);
+                    } else if (lane == 0) {
+                        if (pos > 0) st_state(a.tile_state + pos, tag | (1ull << 32) | total);
+                        else st_state(a.tile_state, tag | (2ull << 32) | total);
                     }
                     agg_it++;
                 }
-                // ---- (3) resumable decoupled look-back + streaming of the oldest pending tile ----
+                // ---- (3) resumable decoupled look-back, then (once the points are staged) streaming
+                //      of the oldest pending tile ----
                 if (epi_it < agg_it) {
                     const int b = epi_it & 1;
                     if (skip[b]) {
-                        epi_it++;
-                        progressed = true;
+                        if (__any_sync(0xffffffffu, mbar_try(bar_staged + 8 * b, (epi_it >> 1) & 1))) {
+                            if (lane == 0) mbar_arrive(bar_cxfree + 8 * b);
+                            epi_it++;
+                            progressed = true;
+                        }
                     } else {
-                        if (!resolving) { resolving = true; excl = 0; look = epos[b] - 1; }
-                        bool resolved = epos[b] == 0;
+                        if (!resolving) { resolving = true; published = false; excl = 0; look = epos[b] - 1; }
+                        bool resolved = published || epos[b] == 0;
                         if (!resolved) {
                             const int idx = look - lane;
                             unsigned long long w = tag | (2ull << 32);   // virtual tile < 0: prefix 0
@@ -240,15 +258,21 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                                 else look -= 32;
                             }
                         }
+                        if (resolved && !published) {
+                            // the inclusive prefix goes out now, before this tile's points exist
+                            published = true;
+                            progressed = true;
+                            if (lane == 0) {
+                                st_state(a.tile_state + epos[b], tag | (2ull << 32) | (excl + tot[b]));
+                                if (epos[b] == n_work - 1) *a.d_count = excl + tot[b];
+                                trace(a.trace, epi_it, 6);
+                            }
+                        }
+                        resolved = published && __any_sync(0xffffffffu, mbar_try(bar_staged + 8 * b, (epi_it >> 1) & 1));
                         if (resolved) {
                             progressed = true;
                             const uint32_t total = tot[b];
                             const int pos = epos[b];
-                            if (lane == 0) {
-                                st_state(a.tile_state + pos, tag | (2ull << 32) | (excl + total));
-                                if (pos == n_work - 1) *a.d_count = excl + total;
-                                trace(a.trace, epi_it, 6);
-                            }
                             if (total) {
                                 // stream the tile's compacted points as one contiguous block
                                 const float* cx = cxb + b * 3 * T;
@@ -447,6 +471,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 while (!mbar_try(bar_cxfree + 8 * b, ((it >> 1) & 1) ^ 1)) __nanosleep(64);
             if (lane == 31) cnts[b * 16 + warp] = incl;
             cons_sync<NCONS>();
+            if (tid == 0) mbar_arrive(bar_counted + 8 * b);      // the IO warp publishes the tile's count now
             uint32_t rank = incl - cnt;
 #pragma unroll
             for (int w2 = 0; w2 < CW; w2++) rank += w2 < warp ? cnts[b * 16 + w2] : 0u;
@@ -479,10 +504,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 cx[3 * rank + 2] = __double2float_rn(Xd[2]);
                 rank++;
             }
-            if (tid == 0) {
-                ctl[1 + b] = pos;
-                trace(a.trace, it, 4);
-            }
+            if (tid == 0) trace(a.trace, it, 4);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_staged + 8 * b);
         }
@@ -538,6 +560,8 @@ cudaError_t launch_fused7(const scan3d_config& c, const FusedArgs& a_in, const D
     const int T = 128 * p.cw;
     a.tiles_per_row = 0;
     a.n_tiles = (int)(((size_t)c.W * c.H + T - 1) / T);
+    a.dynamic = 1;
+    if (const char* e = getenv("SCAN3D_FUSED_DYN")) a.dynamic = atoi(e) != 0;
     const bool exact = !(c.flags & SCAN3D_FLAG_FAST_TRIANGULATION);
 #define S3D_F7(NN) (c.dirs == 2 ? launch7_nd<NN, 2>(a, cal, sm_count, p, exact, st) : launch7_nd<NN, 1>(a, cal, sm_count, p, exact, st))
     switch (c.N) {

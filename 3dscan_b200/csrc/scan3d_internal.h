@@ -112,7 +112,8 @@ struct FusedArgs {
     unsigned long long* tile_state;
     uint8_t* tile_flags;          // [n_tiles] tile holds at least one ROI pixel
     int* tile_list;               // [n_tiles] ids of those tiles, raster order
-    int* n_list;                  // [1]
+    int* n_list;                  // [1]; n_list[n_tiles + 8] is the dynamic scheduler's counter
+    int dynamic;                  // v7: draw work-list positions from that counter instead of b, b+G, ...
     unsigned long long* trace;    // optional timeline buffer (SCAN3D_TRACE), else null
     const double2* cam_lut; const double2* proj_lut;
     const double* atan_tab;
