@@ -675,9 +675,13 @@ int scan3d_debug_atan2(scan3d_ctx* ctx, const double* y_host, const double* x_ho
     return SCAN3D_OK;
 }
 
-// ---- diagnostics: pipeline timeline of the last fused launch (needs SCAN3D_TRACE=1 at create) ----
+// ---- diagnostics: pipeline timeline of the last fused launch (library built with
+//      SCAN3D_BUILD_TRACE=1, context created with SCAN3D_TRACE=1 in the environment) ----
 int scan3d_debug_get_trace(scan3d_ctx* ctx, uint64_t* out_host, int64_t n_words)
 {
+#if !defined(S3D_TRACE) || !S3D_TRACE
+    return fail(ctx, SCAN3D_ERR_STATE, "this build has no trace hooks: rebuild with SCAN3D_BUILD_TRACE=1");
+#endif
     if (!ctx || !out_host || !ctx->trace) return fail(ctx, SCAN3D_ERR_STATE, "tracing is not enabled");
     CK(cudaSetDevice(ctx->device));
     if (n_words > 1024 * 64 * 8) n_words = 1024 * 64 * 8;

@@ -200,12 +200,16 @@ __device__ __forceinline__ int sat32(long long v)
     return (int)max(min(v, 2147483647LL), -2147483648LL);
 }
 
-// optional per-CTA timeline (SCAN3D_TRACE=1): clock64 stamps of the pipeline events of the first
-// TRACE_TILES tiles of every CTA; slot = (cta * TRACE_TILES + it) * 8 + event
+// optional per-CTA timeline (library built with SCAN3D_BUILD_TRACE=1, run with SCAN3D_TRACE=1):
+// clock64 stamps of the pipeline events of the first TRACE_TILES tiles of every CTA;
+// slot = (cta * TRACE_TILES + it) * 8 + event
+#ifndef S3D_TRACE
+#define S3D_TRACE 0
+#endif
 constexpr int TRACE_TILES = 64;
 __device__ __forceinline__ void trace(unsigned long long* t, int it, int ev)
 {
-    if (t && it < TRACE_TILES) t[((size_t)blockIdx.x * TRACE_TILES + it) * 8 + ev] = clock64();
+    if (S3D_TRACE && t && it < TRACE_TILES) t[((size_t)blockIdx.x * TRACE_TILES + it) * 8 + ev] = clock64();
 }
 
 

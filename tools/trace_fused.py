@@ -1,5 +1,9 @@
 #!/usr/bin/env python
-"""Pipeline timeline of the fused kernel (diagnostics).  SCAN3D_TRACE=1 python tools/trace_fused.py"""
+"""Pipeline timeline of the fused kernel (diagnostics).
+
+Needs a library built with the trace hooks:
+    SCAN3D_BUILD_TRACE=1 python 3dscan_b200/build.py --force && SCAN3D_TRACE=1 python tools/trace_fused.py
+"""
 import ctypes as C, importlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
