@@ -327,7 +327,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     }
                 }
             }
-            if (!progressed) __nanosleep(100);
+            if (!progressed) __nanosleep(250);
         }
         return;
     }
