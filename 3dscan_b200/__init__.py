@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBDIR = os.path.join(_HERE, "lib")
+_LIBDIR = os.environ.get("SCAN3D_LIBDIR") or os.path.join(_HERE, "lib")   # override: a trace-enabled build (tools/trace_fused.py)
 
 # ---- scan3d_plane ----
 PLANE_WRAPPED_V, PLANE_WRAPPED_H, PLANE_UNWRAPPED_V, PLANE_UNWRAPPED_H = 0, 1, 2, 3

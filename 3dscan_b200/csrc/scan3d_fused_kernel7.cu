@@ -199,9 +199,8 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 }
             }
             if (DIRS == 2) {
-                // ---- (2) a tile's valid pixels are counted (its triangulation is still running):
-                //      publish the count at once, so that the prefix chain of the whole grid runs
-                //      ahead of the triangulation instead of behind it ----
+                // ---- (2) a tile's valid pixels are counted (its triangulation is still running; the
+                //      consumers have published the count themselves): note it for the look-back ----
                 if (agg_it < load_it && agg_it < epi_it + 2 &&
                     __any_sync(0xffffffffu, mbar_try(bar_counted + 8 * (agg_it & 1), (agg_it >> 1) & 1))) {
                     progressed = true;
@@ -215,15 +214,12 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     epos[b] = pos;
                     skip[b] = total == 0 && pos != n_work - 1 && pos > 0;
                     if (skip[b]) {
-                        // empty tile: nothing to write, never waits; forward a ready prefix or post 0
+                        // empty tile: nothing to write, never waits; its count (0) is already out --
+                        // upgrade it to a prefix if the predecessor's happens to be known
                         if (lane == 0) {
                             const unsigned long long w = ld_state(a.tile_state + pos - 1);
-                            const bool fwd = (w >> 34) == (tag >> 34) && ((w >> 32) & 3ull) == 2;
-                            st_state(a.tile_state + pos, fwd ? w : (tag | (1ull << 32)));
+                            if ((w >> 34) == (tag >> 34) && ((w >> 32) & 3ull) == 2) st_state(a.tile_state + pos, w);
                         }
-                    } else if (lane == 0) {
-                        if (pos > 0) st_state(a.tile_state + pos, tag | (1ull << 32) | total);
-                        else st_state(a.tile_state, tag | (2ull << 32) | total);
                     }
                     agg_it++;
                 }
@@ -471,10 +467,20 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 while (!mbar_try(bar_cxfree + 8 * b, ((it >> 1) & 1) ^ 1)) __nanosleep(64);
             if (lane == 31) cnts[b * 16 + warp] = incl;
             cons_sync<NCONS>();
-            if (tid == 0) mbar_arrive(bar_counted + 8 * b);      // the IO warp publishes the tile's count now
-            uint32_t rank = incl - cnt;
+            uint32_t rank = incl - cnt, total = 0;
 #pragma unroll
-            for (int w2 = 0; w2 < CW; w2++) rank += w2 < warp ? cnts[b * 16 + w2] : 0u;
+            for (int w2 = 0; w2 < CW; w2++) {
+                const uint32_t c = cnts[b * 16 + w2];
+                rank += w2 < warp ? c : 0u;
+                total += c;
+            }
+            if (tid == 0) {
+                // The tile's count goes out NOW, from here, before the triangulation: every later
+                // tile's look-back needs it, and the IO warp may be busy issuing loads or streaming.
+                const unsigned long long tag = (unsigned long long)(a.epoch & 0x3fffffffu) << 34;
+                st_state(a.tile_state + pos, tag | ((pos ? 1ull : 2ull) << 32) | total);
+                mbar_arrive(bar_counted + 8 * b);
+            }
             float* cx = cxb + b * 3 * T;
             vfl[b * (T / 4) + tid] = (uint8_t)vbits;
             // triangulation of the surviving pixels (7/triangulation.cpp:1230-1247)
