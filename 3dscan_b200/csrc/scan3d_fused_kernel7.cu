@@ -237,21 +237,30 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                         if (!resolving) { resolving = true; published = false; excl = 0; look = epos[b] - 1; }
                         bool resolved = published || epos[b] == 0;
                         if (!resolved) {
-                            const int idx = look - lane;
-                            unsigned long long w = tag | (2ull << 32);   // virtual tile < 0: prefix 0
-                            if (idx >= 0) w = ld_state(a.tile_state + idx);
-                            const bool ready = (w >> 34) == (tag >> 34) && ((w >> 32) & 3ull) != 0;
-                            if (__all_sync(0xffffffffu, ready)) {
-                                progressed = true;
-                                const bool is_prefix = ((w >> 32) & 3ull) == 2;
+                            // Walk back window after window while the words are there.  The distance
+                            // to the nearest known prefix is (count->prefix latency) x (tile rate of
+                            // the grid), so a slow walk feeds itself: one window per event-loop pass
+                            // settled at ~30k cycles and ~600 tiles; a back-to-back walk at ~2k.
+#pragma unroll 1
+                            for (int hop = 0; hop < 24; hop++) {
+                                const int idx = look - lane;
+                                unsigned long long w = tag | (2ull << 32);   // virtual tile < 0: prefix 0
+                                if (idx >= 0) w = ld_state(a.tile_state + idx);
+                                const bool ready = (w >> 34) == (tag >> 34) && ((w >> 32) & 3ull) != 0;
+                                const bool is_prefix = ready && ((w >> 32) & 3ull) == 2;
+                                const unsigned rm = __ballot_sync(0xffffffffu, ready);
                                 const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+                                // needed lanes: from the nearest tile up to the first known prefix
                                 const int stop = pm ? __ffs(pm) - 1 : 31;
+                                const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
+                                if ((rm & need) != need) break;            // a needed count is not out yet
+                                progressed = true;
                                 uint32_t v = lane <= stop ? (uint32_t)w : 0;
 #pragma unroll
                                 for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                                 excl += v;
-                                if (pm) resolved = true;
-                                else look -= 32;
+                                if (pm) { resolved = true; break; }
+                                look -= 32;
                             }
                         }
                         if (resolved && !published) {
