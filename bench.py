@@ -67,6 +67,15 @@ def ncu_traffic(workload):
         return None
 
 
+def host_threads():
+    """All the host cores this process may run on (torchrun exports OMP_NUM_THREADS=1; the oracle
+    takes an explicit thread count, so that setting does not throttle the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -79,12 +88,19 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def wait_first_row(self, timeout=5.0):
+        """nvidia-smi takes a few hundred ms to come up on a fresh box: do not start a short timed
+        region before it delivers samples."""
+        t_end = time.time() + timeout
+        while self.proc and not self.rows and time.time() < t_end:
+            time.sleep(0.02)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -94,7 +110,11 @@ class ClockSampler:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15] or [r for _, r in self.rows[-3:]]
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.05]
+        window = "timed region"
+        if not rows:     # region shorter than the sampling period: nearest samples either side
+            rows = [r for t, r in self.rows if t0 - 0.1 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+            window = "nearest samples (region shorter than the 25 ms sampling period)"
         sm, reasons, mx = [], set(), None
         for r in rows:
             try:
@@ -105,7 +125,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def oracle_scan_seconds(cfg, ocal, stack, roi, threads, min_seconds, max_runs):
@@ -150,12 +170,12 @@ def bench_rowshard(args, s3, cal, cfg_full, config, rank, world, local_rank, str
         res, counts = sh.gather_points(src, cnt_dev, dst=0, out=out)   # counts stay on the device until the exchange
         total[0] = sum(counts)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.25)
+    for _ in range(args.warmup):
+        step()
+    sampler.wait_first_row()
+    barrier()
     l0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -207,7 +227,7 @@ def _wrap_device(torch, ptr, shape, typestr):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_12mp_8step_10bit_vh", choices=sorted(WORKLOADS))
@@ -248,7 +268,7 @@ def main():
         if rank != 0:
             return
         import oracle_ffi as o
-        threads = o.max_threads()
+        threads = host_threads()
         stack, roi = s3.synth_stack(cfg, cal, s3.default_synth_params(seed=0x3D5CA9))
         from gpu_common import run_oracle
         for _ in range(args.warmup):
@@ -318,12 +338,12 @@ def main():
             k = b % args.ring
             ctx.reconstruct_dev(ring[k].data_ptr(), rois[k].data_ptr())
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.25)
+    for _ in range(args.warmup):
+        step()
+    sampler.wait_first_row()
+    barrier()
     l0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -392,7 +412,7 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         import oracle_ffi as o
-        threads = o.max_threads()
+        threads = host_threads()
         sec, runs = oracle_scan_seconds(cfg, ocal, host_stack.numpy(), host_roi.numpy(), threads, 8.0, 4)
         cpu = {"value": npix / sec / 1e6, "unit": "Mpix/s", "cores": threads, "kind": "port",
                "sample": "%d full %dx%d scan(s) of the same workload, median; stages 3-8 incl. full-frame undistort tables; inputs in RAM" % (runs, W, H),

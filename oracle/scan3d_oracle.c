@@ -25,9 +25,11 @@
 static int clamp_threads(int threads)
 {
 #ifdef _OPENMP
-    int mx = omp_get_max_threads();
-    if (threads <= 0 || threads > mx) threads = mx;
-    return threads;
+    /* an explicit request may exceed OMP_NUM_THREADS (launchers such as torchrun export
+     * OMP_NUM_THREADS=1), never the number of processors */
+    if (threads <= 0) return omp_get_max_threads();
+    int np = omp_get_num_procs();
+    return threads > np ? np : threads;
 #else
     (void)threads;
     return 1;
