@@ -456,6 +456,15 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     const int4 c4 = make_int4(r_cp[0].x, r_cp[0].y, r_cp[1].x, r_cp[1].y);
                     *reinterpret_cast<int4*>(a.cpmap + gh) = c4;
                     if (h == 0) cp01 = c4; else cp23 = c4;
+                    // the undistortion tables are gathered once per surviving pixel a few thousand
+                    // cycles from now: pull the lines into L2 meanwhile (DRAM latency -> L2 latency)
+                    if (vb) {
+                        if (a.cam_lut) prefetch_l2(a.cam_lut + gh);
+                        if (a.proj_lut) {
+                            if (vb & 1u) prefetch_l2(a.proj_lut + (size_t)c4.y * a.PW + c4.x);
+                            if (vb & 2u) prefetch_l2(a.proj_lut + (size_t)c4.w * a.PW + c4.z);
+                        }
+                    }
                 }
                 vbits |= vb << (2 * h);
             }
