@@ -72,6 +72,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// one 2-D tiled tensor copy global -> shared through a CUtensorMap (coordinates in elements)
+__device__ __forceinline__ void tensor_g2s_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)

@@ -16,6 +16,7 @@
 //
 //   CTA = CW consumer warps + 1 IO warp; shared memory per CTA = NF*T + ROI window + 2*12*T bytes
 //   (66 KB for the 12 MP config at CW = 6) -> 3 CTAs = 18 consumer warps per SM at 96 registers.
+#include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -86,7 +87,7 @@ constexpr int regs7(int cw, int minb)
 
 template <int N, int DIRS, int CW, int MINB, bool EXACT>
 __global__ void __launch_bounds__((CW + 1) * 32) __maxnreg__(regs7(CW, MINB))
-k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal)
+k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal, const __grid_constant__ CUtensorMap stack_map)
 {
     constexpr int T = 128 * CW;
     constexpr int NCONS = 32 * CW;
@@ -179,12 +180,19 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                         trace(a.trace, load_it, 0);
                         ctl[0] = pos;
                         posr[load_it & 7] = pos;
-                        mbar_expect_tx(bar_full, (uint32_t)NF * wt + roi_sum);
+                        mbar_expect_tx(bar_full, (uint32_t)NF * (a.use_tmap ? T : wt) + roi_sum);
                     }
                     __syncwarp();
                     const uint32_t dst = smem_u32(slot);
-                    const uint8_t* src = a.stack + p0;
-                    for (int f = lane; f < NF; f += 32) bulk_g2s(dst + f * T, src + (size_t)f * plane, (uint32_t)wt, bar_full);
+                    if (a.use_tmap) {
+                        // the whole [NF frames] x [T bytes] tile is ONE 2-D tensor copy (64-bit elements;
+                        // bytes past the end of a frame are zero-filled).  56 per-frame bulk copies took the
+                        // warp ~5k cycles to issue, squarely on the slot-free -> data-ready path.
+                        if (lane == 0) tensor_g2s_2d(dst, &stack_map, p0 >> 3, 0, bar_full);
+                    } else {
+                        const uint8_t* src = a.stack + p0;
+                        for (int f = lane; f < NF; f += 32) bulk_g2s(dst + f * T, src + (size_t)f * plane, (uint32_t)wt, bar_full);
+                    }
                     if (roi_tx)
                         bulk_g2s(smem_u32(sroi) + lane * G.roi_row + (uint32_t)(seg0 - (gbase + (long long)(lane - 2) * W)),
                                  a.roi + seg0, roi_tx, bar_full);
@@ -535,6 +543,33 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
     }
 }
 
+// 2-D view of the capture stack for the tile loads: inner dimension = one frame as 64-bit words,
+// outer = the frames; box = [T/8 words] x [NF frames], landing in shared memory as [NF][T] bytes.
+static bool stack_tensor_map(CUtensorMap* map, const uint8_t* stack, size_t plane, int NF, int T)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool looked_up = false;
+    if (!looked_up) {
+        looked_up = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = (encode_fn)fn;
+    }
+    if (!encode || NF > 256 || T / 8 > 256 || (plane & 15) || ((uintptr_t)stack & 15)) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)(plane / 8), (cuuint64_t)NF};
+    const cuuint64_t gstride[1] = {(cuuint64_t)plane};
+    const cuuint32_t box[2] = {(cuuint32_t)(T / 8), (cuuint32_t)NF};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<uint8_t*>(stack), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int N, int DIRS, int CW, int MINB, bool EXACT>
 static cudaError_t launch7_t(const FusedArgs& a, const DeviceCalib& cal, int sm_count, const Plan7& p, cudaStream_t st)
 {
@@ -556,7 +591,12 @@ static cudaError_t launch7_t(const FusedArgs& a, const DeviceCalib& cal, int sm_
     const int grid = a.n_tiles < sm_count * per_sm ? a.n_tiles : sm_count * per_sm;   // all CTAs resident
     e = launch_worklist(a, 128 * CW, DIRS, st);
     if (e != cudaSuccess) return e;
-    kern<<<grid, (CW + 1) * 32, p.smem, st>>>(a, cal);
+    FusedArgs a2 = a;
+    alignas(64) CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    const int NF = DIRS == 2 ? 2 * N + 2 * (a.M_v + a.M_h) : N + 2 * a.M_v;
+    a2.use_tmap = !getenv("SCAN3D_NO_TMAP") && stack_tensor_map(&map, a.stack, (size_t)a.W * a.H, NF, 128 * CW) ? 1 : 0;
+    kern<<<grid, (CW + 1) * 32, p.smem, st>>>(a2, cal, map);
     return cudaGetLastError();
 }
 

@@ -114,6 +114,7 @@ struct FusedArgs {
     int* tile_list;               // [n_tiles] ids of those tiles, raster order
     int* n_list;                  // [1]; n_list[n_tiles + 8] is the dynamic scheduler's counter
     int dynamic;                  // v7: draw work-list positions from that counter instead of b, b+G, ...
+    int use_tmap;                 // v7: tile loads are one 2-D tensor copy (set by the launcher)
     unsigned long long* trace;    // optional timeline buffer (SCAN3D_TRACE), else null
     const double2* cam_lut; const double2* proj_lut;
     const double* atan_tab;
