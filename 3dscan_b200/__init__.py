@@ -130,6 +130,7 @@ def cuda_lib():
         getattr(L, fn).argtypes = [vp]
         getattr(L, fn).restype = vp
     L.scan3d_write_ply.argtypes = [vp, C.c_char_p, i32]
+    L.scan3d_write_pcd.argtypes = [vp, C.c_char_p]
     L.scan3d_launch_count.argtypes = [vp]
     L.scan3d_launch_count.restype = i64
     L.scan3d_debug_atan2.argtypes = [vp, vp, vp, vp, i32, i32]
@@ -150,6 +151,7 @@ def host_lib():
     L.scan3d_load_calibration.argtypes = [C.c_char_p, C.POINTER(Calib)]
     L.scan3d_load_captured_set.argtypes = [C.c_char_p, C.POINTER(Config), vp]
     L.scan3d_write_ply_points.argtypes = [C.c_char_p, vp, vp, i64, i32]
+    L.scan3d_write_pcd_points.argtypes = [C.c_char_p, vp, vp, i64]
     L.scan3d_host_last_error.restype = C.c_char_p
     L.scan3d_synth_default_params.argtypes = [C.POINTER(SynthParams)]
     L.scan3d_synth_default_params.restype = None
@@ -383,6 +385,9 @@ class Scan3D:
 
     def write_ply(self, path, binary=False):
         self._ck(self.L.scan3d_write_ply(self.h, path.encode(), 1 if binary else 0))
+
+    def write_pcd(self, path):
+        self._ck(self.L.scan3d_write_pcd(self.h, path.encode()))
 
     def launch_count(self):
         return int(self.L.scan3d_launch_count(self.h))

@@ -656,6 +656,31 @@ int scan3d_write_ply(scan3d_ctx* ctx, const char* path, int binary)
     return ok ? SCAN3D_OK : fail(ctx, SCAN3D_ERR_IO, "PLY write failed");
 }
 
+int scan3d_write_pcd(scan3d_ctx* ctx, const char* path)
+{
+    if (!ctx || !path) return fail(ctx, SCAN3D_ERR_ARG, "null argument");
+    int64_t n = 0;
+    int rc = scan3d_point_count(ctx, &n);
+    if (rc) return rc;
+    std::vector<float> xyz((size_t)n * 3);
+    std::vector<uint8_t> rgb((size_t)n * 3);
+    rc = scan3d_get_points(ctx, xyz.data(), nullptr, rgb.data(), n);
+    if (rc) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(ctx, SCAN3D_ERR_IO, "cannot open PCD for writing");
+    fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\n"
+               "TYPE F F F F\nCOUNT 1 1 1 1\nWIDTH %lld\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %lld\nDATA ascii\n",
+            (long long)n, (long long)n);
+    for (int64_t i = 0; i < n; i++) {
+        const uint32_t packed = ((uint32_t)rgb[3 * i] << 16) | ((uint32_t)rgb[3 * i + 1] << 8) | rgb[3 * i + 2];
+        float c;
+        memcpy(&c, &packed, 4);
+        fprintf(f, "%.8g %.8g %.8g %.8g\n", xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], c);
+    }
+    const bool ok = fclose(f) == 0;
+    return ok ? SCAN3D_OK : fail(ctx, SCAN3D_ERR_IO, "PCD write failed");
+}
+
 // ---- self-test entry (not part of the reference boundary): (float)atan2(y,x) on the GPU ----
 int scan3d_debug_atan2(scan3d_ctx* ctx, const double* y_host, const double* x_host, float* out_host, int n, int mode)
 {

@@ -210,4 +210,25 @@ int scan3d_write_ply_points(const char* path, const float* xyz, const uint8_t* r
     return fclose(f) == 0 ? SCAN3D_OK : fail(SCAN3D_ERR_IO, "short write");
 }
 
+// pcl::io::savePCDFileASCII of a PointXYZRGB cloud (8/save_point_cloud.cpp:212; PCL 1.6 writer):
+// one "x y z rgb" line per point, rgb = (r<<16 | g<<8 | b) reinterpreted as a float, all four
+// printed with the stream precision PCL sets (8 significant digits).  No PCL-written file
+// survives in the reference tree, so the header text follows the PCD v0.7 specification.
+int scan3d_write_pcd_points(const char* path, const float* xyz, const uint8_t* rgb, int64_t n)
+{
+    if (!path || (!xyz && n > 0) || n < 0) return fail(SCAN3D_ERR_ARG, "bad argument");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(SCAN3D_ERR_IO, std::string("cannot write ") + path);
+    fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\n"
+               "TYPE F F F F\nCOUNT 1 1 1 1\nWIDTH %lld\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %lld\nDATA ascii\n",
+            (long long)n, (long long)n);
+    for (int64_t i = 0; i < n; i++) {
+        const uint32_t packed = rgb ? ((uint32_t)rgb[3 * i] << 16) | ((uint32_t)rgb[3 * i + 1] << 8) | rgb[3 * i + 2] : 0u;
+        float c;
+        memcpy(&c, &packed, 4);
+        fprintf(f, "%.8g %.8g %.8g %.8g\n", xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], c);
+    }
+    return fclose(f) == 0 ? SCAN3D_OK : fail(SCAN3D_ERR_IO, "short write");
+}
+
 }  // extern "C"

@@ -224,6 +224,8 @@ void save_point_cloud(unsigned cloud_index)
     char name[64];
     snprintf(name, sizeof(name), "/Point_cloud/point_cloud_%u.ply", cloud_index);
     ck(scan3d_write_ply(g_ctx, (g_root + name).c_str(), 0), "scan3d_write_ply");
+    snprintf(name, sizeof(name), "/Point_cloud/point_cloud_%u.pcd", cloud_index);      // 8/save_point_cloud.cpp:211-212
+    ck(scan3d_write_pcd(g_ctx, (g_root + name).c_str()), "scan3d_write_pcd");
     fprintf(stderr, "Saved %lld data points to %s\n", (long long)n, (g_root + name).c_str());
 }
 

@@ -175,6 +175,9 @@ void *scan3d_device_point_count(scan3d_ctx *ctx);   /* u32[1] on device (for col
 /* save_point_cloud()'s pcl::io::savePLYFile equivalent: "x y z red green blue" vertices,
  * ASCII (binary = 0, PCL's default) or binary_little_endian. */
 int scan3d_write_ply(scan3d_ctx *ctx, const char *path, int binary);
+/* save_point_cloud()'s pcl::io::savePCDFileASCII equivalent (8/save_point_cloud.cpp:212): PCD v0.7,
+ * "x y z rgb" per point, 8 significant digits, rgb packed into a float as PCL 1.6 does. */
+int scan3d_write_pcd(scan3d_ctx *ctx, const char *path);
 
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t scan3d_launch_count(const scan3d_ctx *ctx);

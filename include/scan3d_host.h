@@ -10,6 +10,7 @@
  *                                                 6/system_calibration.cpp:1526-1554, 7/triangulation.cpp:152-168
  *   scan3d_synth_pattern_row                      1/pattern_generator.cpp:56-197,291-397,490-507
  *   scan3d_write_ply_points                       pcl::io::savePLYFile at 8/save_point_cloud.cpp:217
+ *   scan3d_write_pcd_points                       pcl::io::savePCDFileASCII at 8/save_point_cloud.cpp:212
  */
 #ifndef SCAN3D_HOST_H
 #define SCAN3D_HOST_H
@@ -34,6 +35,8 @@ int scan3d_load_calibration(const char *root, scan3d_calib *cal);
  * Captured_patterns/{Fringe_patterns,Coded_patterns/Gray_coded}/{Vertical,Horizontal}/Undistorted. */
 int scan3d_load_captured_set(const char *root, const scan3d_config *cfg, uint8_t *stack);
 int scan3d_write_ply_points(const char *path, const float *xyz, const uint8_t *rgb, int64_t n, int binary);
+/* ASCII PCD v0.7, FIELDS x y z rgb (rgb packed into a float as PCL 1.6's PointXYZRGB does) */
+int scan3d_write_pcd_points(const char *path, const float *xyz, const uint8_t *rgb, int64_t n);
 const char *scan3d_host_last_error(void);
 
 /* ---- synthetic captures ---- */

@@ -133,3 +133,14 @@ def test_bmp_and_ply_roundtrip(tmp_path):
     body = open(q).read().split("end_header\n")[1]
     got = np.loadtxt(body.splitlines())[:, :3].astype(np.float32)
     assert np.array_equal(got, xyz)
+    # PCD (pcl::io::savePCDFileASCII layout): 8 significant digits, rgb packed into a float
+    rgb = np.random.default_rng(3).integers(0, 256, (11, 3), dtype=np.uint8)
+    r = str(tmp_path / "a.pcd")
+    assert s3.host_lib().scan3d_write_pcd_points(r.encode(), xyz.ctypes.data_as(C.c_void_p), rgb.ctypes.data_as(C.c_void_p), 11) == 0
+    lines = open(r).read().splitlines()
+    assert lines[1] == "VERSION 0.7" and lines[2] == "FIELDS x y z rgb" and lines[9] == "POINTS 11" and lines[10] == "DATA ascii"
+    rows = np.array([[float(v) for v in ln.split()] for ln in lines[11:]])
+    assert rows.shape == (11, 4)
+    assert np.allclose(rows[:, :3], xyz, rtol=5e-8, atol=0)
+    packed = (rgb[:, 0].astype(np.uint32) << 16) | (rgb[:, 1].astype(np.uint32) << 8) | rgb[:, 2]
+    assert np.allclose(rows[:, 3], packed.view(np.float32).astype(np.float64), rtol=5e-8, atol=0)

@@ -287,4 +287,13 @@ def test_ply_writer(tmp_path):
         else:
             rows = np.loadtxt(body.decode().splitlines()) if n else np.empty((0, 6))
             assert np.array_equal(rows[:, :3].astype(np.float32), xyz)
+    # savePCDFileASCII layout (8/save_point_cloud.cpp:212): x y z rgb, 8 significant digits
+    path = str(tmp_path / "cloud.pcd")
+    ctx.write_pcd(path)
+    lines = open(path).read().splitlines()
+    assert lines[2] == "FIELDS x y z rgb" and lines[9] == f"POINTS {n}" and len(lines) == 11 + n
+    rows = np.array([[float(v) for v in ln.split()] for ln in lines[11:]]).reshape(n, 4)
+    assert np.allclose(rows[:, :3], xyz, rtol=5e-8, atol=0)
+    packed = (rgb[:, 0].astype(np.uint32) << 16) | (rgb[:, 1].astype(np.uint32) << 8) | rgb[:, 2]
+    assert np.allclose(rows[:, 3], packed.view(np.float32).astype(np.float64), rtol=5e-8, atol=0)
     ctx.close()
