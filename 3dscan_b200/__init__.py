@@ -23,6 +23,7 @@ PLANE_CODE_V, PLANE_CODE_H, PLANE_MASK, PLANE_VALID, PLANE_CPMAP, PLANE_XYZ = 4,
 PLANE_MASK_H = 10
 FLAG_POINT_PIXELS = 1
 FLAG_FAST_TRIANGULATION = 2
+FLAG_MODULATION_MASK = 4
 
 _PLANE_DTYPE = {
     PLANE_WRAPPED_V: (np.float32, ()), PLANE_WRAPPED_H: (np.float32, ()),

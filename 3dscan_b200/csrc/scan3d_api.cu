@@ -102,6 +102,10 @@ static int validate(const scan3d_config* c, std::string* why)
     if (c->dirs == 2 && (c->PW < 1 || c->PH < 1)) { *why = "bad projector size"; return 0; }
     const int Ht = c->H_total > 0 ? c->H_total : c->H;
     if (c->row0 < 0 || c->row0 + c->H > Ht) { *why = "row shard outside the frame"; return 0; }
+    if ((c->flags & SCAN3D_FLAG_MODULATION_MASK) && (c->N != 3 || c->row0 != 0 || Ht != c->H)) {
+        *why = "the modulation criterion is defined for 3-step patterns (3/wrapped_phase.cpp:84) and needs the whole frame";
+        return 0;
+    }
     return 1;
 }
 
@@ -198,7 +202,7 @@ void scan3d_destroy(scan3d_ctx* ctx)
     void* ptrs[] = {ctx->cam_lut, ctx->proj_lut, ctx->atan_tab, ctx->nstep_w, ctx->wrapped[0], ctx->wrapped[1],
                     ctx->unwrapped[0], ctx->unwrapped[1], ctx->code[0], ctx->code[1], ctx->mask[0],
                     ctx->mask[1], ctx->valid, ctx->cpmap, ctx->xyz, ctx->pts, ctx->pix, ctx->rgb,
-                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi};
+                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -315,6 +319,12 @@ int scan3d_compute_wrapped_phase_dev(scan3d_ctx* ctx, int dir, const uint8_t* fr
     int rc = ensure_stage_planes(ctx, dir);
     if (rc) return rc;
     const Shape s = shape_of(ctx->cfg);
+    if (ctx->cfg.flags & SCAN3D_FLAG_MODULATION_MASK) {
+        if (!ctx->roi_eff) CK(dalloc(&ctx->roi_eff, npix(ctx)));
+        CK(launch_modulation_roi(s, fringe_dev, roi_dev, ctx->roi_eff, ctx->stream));
+        ctx->launches++;
+        roi_dev = ctx->roi_eff;
+    }
     CK(launch_wrapped(s, ctx->cfg.N, fringe_dev, roi_dev, ctx->wrapped[dir], ctx->atan_tab, ctx->nstep_w, false, ctx->stream));
     CK(launch_mask(s, roi_dev, ctx->mask[dir], ctx->stream));
     ctx->launches += 2;
@@ -466,7 +476,8 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     CK(cudaSetDevice(ctx->device));
     int stages = 0;
     size_t smem = 0;
-    if (!ctx->fast_div_ok || !fused_supported(ctx->cfg, &stages, &smem)) return reconstruct_stagewise(ctx, stack_dev, roi_dev);
+    if (!ctx->fast_div_ok || (ctx->cfg.flags & SCAN3D_FLAG_MODULATION_MASK) || !fused_supported(ctx->cfg, &stages, &smem))
+        return reconstruct_stagewise(ctx, stack_dev, roi_dev);
     const scan3d_config& c = ctx->cfg;
     FusedArgs a{};
     a.stack = stack_dev; a.roi = roi_dev;

@@ -27,6 +27,7 @@ struct scan3d_ctx {
     double2* cam_lut = nullptr;    // [H][W] (u',v') of the local rows, only if the camera is distorted
     double2* proj_lut = nullptr;   // [PH][PW], only if the projector is distorted
     double* atan_tab = nullptr;    // hi[33] then lo[33]
+    uint8_t* roi_eff = nullptr;    // SCAN3D_FLAG_MODULATION_MASK: ROI && modulation criterion of the current direction
     double* nstep_w = nullptr;     // sin[64] then cos[64] (generic-N extension)
 
     // planes (row-major [H][W])
@@ -80,6 +81,7 @@ inline Shape shape_of(const scan3d_config& c)
 
 // ---- stage-wise kernels (any W, H) ----
 cudaError_t launch_mask(const Shape& s, const uint8_t* roi_full, uint8_t* mask, cudaStream_t st);
+cudaError_t launch_modulation_roi(const Shape& s, const uint8_t* fringe, const uint8_t* roi, uint8_t* roi_eff, cudaStream_t st);
 cudaError_t launch_wrapped(const Shape& s, int N, const uint8_t* fringe, const uint8_t* roi_full,
                            float* wrapped, const double* atan_tab, const double* nstep_w,
                            bool libdevice, cudaStream_t st);

@@ -41,6 +41,30 @@ __global__ void k_mask(const uint8_t* __restrict__ roi, uint8_t* __restrict__ ma
     mask[(size_t)yl * W + x] = v ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// optional modulation criterion (3/wrapped_phase.cpp:84-104, disabled in the reference):
+// roi_eff = roi && gamma > 0.01, arithmetic as written there (see oracle/scan3d_oracle.c)
+// ------------------------------------------------------------------------------------------
+__global__ void k_modulation_roi(const uint8_t* __restrict__ fringe, const uint8_t* __restrict__ roi,
+                                 uint8_t* __restrict__ roi_eff, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int i0 = fringe[i], i1 = fringe[n + i], i2 = fringe[2 * n + i];
+    const int d = i0 - i2, e = 2 * i1 - i0 - i2;
+    const float t1 = __fsqrt_rn((float)(3 * d * d + e * e));      // exact integer below 2^24
+    const float t2 = (float)(i0 + i1 + i2);
+    const float t3 = __fdiv_rn(t1, t2);                            // 0/0 -> NaN -> rejected
+    roi_eff[i] = ((double)t3 > 0.01 && roi[i] != 0) ? 1 : 0;
+}
+
+cudaError_t launch_modulation_roi(const Shape& s, const uint8_t* fringe, const uint8_t* roi, uint8_t* roi_eff, cudaStream_t st)
+{
+    const size_t n = (size_t)s.W * s.H;
+    k_modulation_roi<<<(unsigned)cdiv((long long)n, 256), 256, 0, st>>>(fringe, roi, roi_eff, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mask(const Shape& s, const uint8_t* roi_full, uint8_t* mask, cudaStream_t st)
 {
     dim3 grid(cdiv(s.W, 256), s.H);

@@ -81,6 +81,14 @@ typedef struct {
  * <= 1e-10 relative in double, i.e. the float points differ only in rare last-bit ties.  Without
  * this flag the operation order is the reference's and the points are bit-identical to it. */
 #define SCAN3D_FLAG_FAST_TRIANGULATION 2u
+/* check_I_mod_criteria's second, commented-out validity criterion (3/wrapped_phase.cpp:84-104):
+ * a pixel of the selected region is kept only when its fringe modulation
+ * sqrtf(3 (I0-I2)^2 + (2 I1-I0-I2)^2) / (float)(I0+I1+I2) exceeds 0.01 (per direction, from that
+ * direction's three fringe images).  OFF by default: the reference's live path is ROI-only.
+ * 3-step configurations without row sharding only; with the flag scan3d_reconstruct runs the
+ * stage kernels in sequence instead of the single-pass kernel (the mask recurrence then needs
+ * the modulation of pixels two rows up, which a linear tile does not hold). */
+#define SCAN3D_FLAG_MODULATION_MASK 4u
 
 /* The 8 matrices load_matrices() reads (6/system_calibration.cpp:1526-1554): intrinsics (3x3
  * row-major), distortion (k1,k2,p1,p2,k3), world->device rotation vectors and translations. */

@@ -86,6 +86,17 @@ def check_roi(roi):
     return valid
 
 
+def check_I_mod_criteria(fringe, roi):
+    """The reference's commented-out modulation criterion (3/wrapped_phase.cpp:84-104, 3-step)."""
+    H, W = roi.shape
+    fringe = np.ascontiguousarray(fringe, np.uint8)
+    assert fringe.shape == (3, H, W)
+    roi = np.ascontiguousarray(roi, np.uint8)
+    valid = np.empty((H, W), np.int32)
+    lib().o3d_check_I_mod_criteria(_p(fringe), _p(roi), W, H, _p(valid))
+    return valid
+
+
 def wrapped_phase(fringe, valid, threads=1, want_dbg=True):
     N, H, W = fringe.shape
     fringe = np.ascontiguousarray(fringe, np.uint8)
@@ -223,7 +234,7 @@ class Result:
 
 
 def reconstruct(cfg, cal, fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi, threads=1,
-                want_xyz=True):
+                want_xyz=True, modulation=False):
     """cfg: dict with W,H,PW,PH,N,M_v,M_h,fw_v,fw_h,dirs.  Returns a Result of numpy planes."""
     c = Config(**{k: int(cfg[k]) for k in
                   ("W", "H", "PW", "PH", "N", "M_v", "M_h", "fw_v", "fw_h", "dirs")})
@@ -248,8 +259,8 @@ def reconstruct(cfg, cal, fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi,
                 _p(r.cpmap), _p(r.xyz), _p(r.pts), _p(r.pix), 0)
     u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
     keep = [u8(x) for x in (fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi)]
-    lib().o3d_reconstruct(C.byref(c), C.byref(cal), *[_p(k) for k in keep], C.byref(o),
-                          int(threads))
+    lib().o3d_reconstruct_ex(C.byref(c), C.byref(cal), *[_p(k) for k in keep], int(bool(modulation)),
+                             C.byref(o), int(threads))
     r.count = int(o.count)
     if two:
         r.pts = r.pts[:r.count]

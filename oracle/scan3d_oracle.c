@@ -55,6 +55,26 @@ void o3d_check_roi(const uint8_t *roi, int W, int H, int32_t *valid)
 }
 
 /* Extension weights for N not in {3,4,5,8}: shifts delta_k = 2*pi*k/N (true pi), libm. */
+/* check_I_mod_criteria, the branch the reference keeps commented out (3/wrapped_phase.cpp:84-104,
+ * 3-step only): gamma = sqrtf(3 (I0-I2)^2 + (2 I1 - I0 - I2)^2) / (float)(I0+I1+I2), the pixel is
+ * kept when gamma > 0.01 and it lies in the selected region.  Arithmetic as written there: the
+ * differences are ints, the squares and the sum doubles (exact), sqrtf takes the sum as a float
+ * (exact below 2^24), t1/t2 is a float division, the comparison promotes to double.  A black pixel
+ * gives 0/0 = NaN, which fails the comparison. */
+void o3d_check_I_mod_criteria(const uint8_t *fringe, const uint8_t *roi, int W, int H, int32_t *valid)
+{
+    const size_t n = (size_t)W * H;
+    for (size_t i = 0; i < n; i++) {
+        const int i0 = fringe[i], i1 = fringe[n + i], i2 = fringe[2 * n + i];
+        const double d = i0 - i2;
+        const double e = 2.0 * i1 - i0 - i2;
+        const float t1 = sqrtf((float)(3.0 * (d * d) + e * e));
+        const float t2 = (float)(i0 + i1 + i2);
+        const float t3 = t1 / t2;
+        valid[i] = (t3 > 0.01 && roi[i] != 0) ? 1 : 0;
+    }
+}
+
 static void nstep_weights(int N, double *s, double *c)
 {
     for (int k = 0; k < N; k++) {
@@ -561,6 +581,14 @@ void o3d_reconstruct(const o3d_config *cfg, const o3d_calib *cal, const uint8_t 
                      const uint8_t *gray_h, const uint8_t *inv_h, const uint8_t *roi,
                      o3d_outputs *out, int threads)
 {
+    o3d_reconstruct_ex(cfg, cal, fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi, 0, out, threads);
+}
+
+void o3d_reconstruct_ex(const o3d_config *cfg, const o3d_calib *cal, const uint8_t *fringe_v,
+                        const uint8_t *gray_v, const uint8_t *inv_v, const uint8_t *fringe_h,
+                        const uint8_t *gray_h, const uint8_t *inv_h, const uint8_t *roi,
+                        int modulation, o3d_outputs *out, int threads)
+{
     const int W = cfg->W, H = cfg->H;
     const size_t n = (size_t)W * H;
 
@@ -573,7 +601,8 @@ void o3d_reconstruct(const o3d_config *cfg, const o3d_calib *cal, const uint8_t 
         const int M = dir == 0 ? cfg->M_v : cfg->M_h;
         memset(wr, 0, n * sizeof(float));
         memset(un, 0, n * sizeof(float));
-        o3d_check_roi(roi, W, H, valid);
+        if (modulation && cfg->N == 3) o3d_check_I_mod_criteria(dir == 0 ? fringe_v : fringe_h, roi, W, H, valid);
+        else o3d_check_roi(roi, W, H, valid);
         o3d_wrapped_phase(dir == 0 ? fringe_v : fringe_h, cfg->N, W, H, valid, wr, NULL, threads);
         o3d_mask_recurrence(valid, W, H, NULL);
         o3d_decode_gray(dir == 0 ? gray_v : gray_h, dir == 0 ? inv_v : inv_h, M, W, H, valid,

@@ -52,6 +52,8 @@ extern "C" {
 /* ---- stage 3 : 3/wrapped_phase.cpp ---- */
 /* check_I_mod_criteria :64-143 (live part :78-82,106-115): valid0 = (roi != 0). */
 void o3d_check_roi(const uint8_t *roi, int W, int H, int32_t *valid);
+/* the disabled modulation criterion of the same function (:84-104, 3-step): fringe = [3][H][W] */
+void o3d_check_I_mod_criteria(const uint8_t *fringe, const uint8_t *roi, int W, int H, int32_t *valid);
 
 /* create_wrapped_phase :151-238.  fringe = [N][H][W] u8.  wrapped / dbg are written only
  * where valid==1 (caller zero-fills).  N in {3,4,5} follow the reference; N==8 and other
@@ -151,6 +153,12 @@ void o3d_reconstruct(const o3d_config *cfg, const o3d_calib *cal, const uint8_t 
                      const uint8_t *gray_v, const uint8_t *inv_v, const uint8_t *fringe_h,
                      const uint8_t *gray_h, const uint8_t *inv_h, const uint8_t *roi,
                      o3d_outputs *out, int threads);
+
+/* same, with check_I_mod_criteria's commented-out modulation branch switched on (N == 3) */
+void o3d_reconstruct_ex(const o3d_config *cfg, const o3d_calib *cal, const uint8_t *fringe_v,
+                        const uint8_t *gray_v, const uint8_t *inv_v, const uint8_t *fringe_h,
+                        const uint8_t *gray_h, const uint8_t *inv_h, const uint8_t *roi,
+                        int modulation, o3d_outputs *out, int threads);
 
 int o3d_max_threads(void);
 

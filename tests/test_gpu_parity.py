@@ -214,6 +214,45 @@ def test_fused_roi_edge_cases(kind):
     ctx.close()
 
 
+def test_modulation_mask_flag_matches_oracle():
+    """SCAN3D_FLAG_MODULATION_MASK = the reference's commented-out criterion (3/wrapped_phase.cpp:84-104):
+    every (I0,I1,I2) triple through scan3d_compute_wrapped_phase, then a whole scan with flat and
+    nearly flat patches inside the ROI (V and H masks then differ) against the oracle."""
+    v = np.arange(256, dtype=np.int64)
+    i0, i1, i2 = np.meshgrid(v, v, v, indexing="ij")
+    fr = np.stack([i0, i1, i2]).astype(np.uint8).reshape(3, 4096, 4096)
+    roi = np.ones((4096, 4096), np.uint8)
+    roi[7::13, :] = 0
+    cfg = s3.make_config(4096, 4096, 1, 1, 3, 1, 1, 8, 8, 1, flags=s3.FLAG_MODULATION_MASK)
+    ctx = s3.Scan3D(cfg, 0, None)
+    ctx.compute_wrapped_phase(0, fr, roi)
+    valid0 = o.check_I_mod_criteria(fr, roi)
+    want = o.mask_recurrence(valid0)
+    assert np.array_equal(ctx.plane(s3.PLANE_MASK).astype(np.int32), want)
+    ctx.close()
+
+    W, H, PW, PH = 640, 480, 1024, 768
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, 3, 7, 7, 8, 8, 2, flags=s3.FLAG_MODULATION_MASK)
+    stack, roi = s3.synth_stack(cfg, cal)
+    stack = stack.copy()
+    rng = np.random.default_rng(5)
+    stack[0:3, 100:160, 200:300] = 90                                                   # flat in V only
+    stack[17:20, 300:340, 100:220] = rng.integers(118, 122, (3, 40, 120), dtype=np.uint8)   # around the threshold, H only
+    stack[0:3, 200:230, 400:470] = 0                                                    # black: 0/0
+    ctx = _ctx(cfg, cal)
+    n = ctx.reconstruct(stack, roi)
+    ref = run_oracle(cfg, ocal, stack, roi, modulation=True)
+    assert (ref.valid_v != ref.valid_h).any() and 0 < ref.count == n
+    st = compare(cfg, ref, ctx, fused=True)
+    assert st["pts_nonidentical"] == 0
+    plain = run_oracle(cfg, ocal, stack, roi)
+    assert plain.count > ref.count                                                      # the criterion removed pixels
+    ctx.close()
+    with pytest.raises(RuntimeError):
+        s3.Scan3D(s3.make_config(W, H, PW, PH, 4, 7, 7, 8, 8, 2, flags=s3.FLAG_MODULATION_MASK), 0, cal)
+
+
 def test_fused_row_shards_concatenate_to_full_frame():
     W, H, PW, PH = 1024, 90, 1024, 768
     cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)

@@ -146,3 +146,23 @@ def test_fdlibm_atan2f_restatement_equals_libm():
     L = o.lib()
     L.o3d_atan2f_restated_mismatches.restype = ctypes.c_long
     assert L.o3d_atan2f_restated_mismatches() == 0
+
+
+def test_modulation_criterion_restatement_all_triples():
+    """The commented-out criterion of check_I_mod_criteria (3/wrapped_phase.cpp:84-104) over every
+    (I0, I1, I2) triple, against a literal numpy transcription of the expression's C types."""
+    v = np.arange(256, dtype=np.int64)
+    i0, i1, i2 = np.meshgrid(v, v, v, indexing="ij")
+    fr = np.stack([i0, i1, i2]).astype(np.uint8).reshape(3, 4096, 4096)
+    roi = np.ones((4096, 4096), np.uint8)
+    got = o.check_I_mod_criteria(fr, roi)
+    a, b, c = (fr[k].astype(np.float64) for k in range(3))
+    t1 = np.sqrt((3.0 * (a - c) ** 2 + (2.0 * b - a - c) ** 2).astype(np.float32))   # sqrtf(float arg)
+    t2 = (a + b + c).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t3 = (t1 / t2).astype(np.float32)                                            # float division
+        want = (t3.astype(np.float64) > 0.01).astype(np.int32)                      # NaN (0/0) -> 0
+    assert t1.dtype == np.float32 and np.array_equal(got, want)
+    assert got[0, 0] == 0 and 0 < got.sum() < got.size            # black pixel rejected; both outcomes occur
+    roi[:, ::2] = 0
+    assert np.array_equal(o.check_I_mod_criteria(fr, roi), want * (roi != 0))
