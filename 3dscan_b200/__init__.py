@@ -133,6 +133,11 @@ def cuda_lib():
     L.scan3d_write_ply.argtypes = [vp, C.c_char_p, i32]
     L.scan3d_write_pcd.argtypes = [vp, C.c_char_p]
     L.scan3d_launch_count.argtypes = [vp]
+    L.scan3d_set_points_buffer.argtypes = [vp, vp, i64]
+    L.scan3d_peer_alloc.argtypes = [i32, i64, C.POINTER(vp), C.c_char_p]
+    L.scan3d_peer_free.argtypes = [i32, vp]
+    L.scan3d_peer_open.argtypes = [i32, C.c_char_p, C.POINTER(vp)]
+    L.scan3d_peer_close.argtypes = [i32, vp]
     L.scan3d_launch_count.restype = i64
     L.scan3d_debug_atan2.argtypes = [vp, vp, vp, vp, i32, i32]
     L.scan3d_debug_divcheck.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -390,6 +395,10 @@ class Scan3D:
     def write_pcd(self, path):
         self._ck(self.L.scan3d_write_pcd(self.h, path.encode()))
 
+    def set_points_buffer(self, dev_ptr, capacity_points):
+        """Compacted points go to this device pointer (may be another GPU's memory mapped here); 0/None restores."""
+        self._ck(self.L.scan3d_set_points_buffer(self.h, C.c_void_p(dev_ptr) if dev_ptr else None, int(capacity_points)))
+
     def launch_count(self):
         return int(self.L.scan3d_launch_count(self.h))
 
@@ -404,3 +413,43 @@ class Scan3D:
         out = np.empty(y.shape, np.float32)
         self._ck(self.L.scan3d_debug_atan2(self.h, _ptr(y), _ptr(x), _ptr(out), y.size, mode))
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# peer memory helpers (row-sharded mode, 3dscan_b200/sharding.py)
+# ---------------------------------------------------------------------------------------------
+def peer_alloc(device, nbytes):
+    """(device pointer, 64-byte CUDA IPC handle) of a new block on `device`."""
+    p, h = C.c_void_p(), C.create_string_buffer(64)
+    rc = cuda_lib().scan3d_peer_alloc(int(device), int(nbytes), C.byref(p), h)
+    if rc:
+        raise Scan3DError(f"scan3d_peer_alloc failed ({rc})")
+    return int(p.value), bytes(h.raw)
+
+
+def peer_free(device, ptr):
+    cuda_lib().scan3d_peer_free(int(device), C.c_void_p(ptr))
+
+
+def peer_open(device, handle):
+    """Maps another process's block for kernels running on `device`; returns the local pointer."""
+    p = C.c_void_p()
+    rc = cuda_lib().scan3d_peer_open(int(device), C.create_string_buffer(bytes(handle), 64), C.byref(p))
+    if rc:
+        raise Scan3DError(f"scan3d_peer_open failed ({rc})")
+    return int(p.value)
+
+
+def peer_close(device, ptr):
+    cuda_lib().scan3d_peer_close(int(device), C.c_void_p(ptr))
+
+
+def wrap_device(ptr, shape, typestr):
+    """torch view of a raw device buffer (no copy, no ownership)."""
+    import torch
+
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(h, device="cuda")

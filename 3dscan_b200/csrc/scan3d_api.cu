@@ -305,6 +305,8 @@ static int ensure_stage_planes(scan3d_ctx* ctx, int dir)
     return SCAN3D_OK;
 }
 
+static inline float* points_of(const scan3d_ctx* ctx) { return ctx->pts_ext ? ctx->pts_ext : ctx->pts; }
+
 static int roi_bytes(const scan3d_ctx* ctx, size_t* out)
 {
     *out = (size_t)ctx->cfg.W * ctx->cfg.H_total;
@@ -431,7 +433,7 @@ int scan3d_compact_points(scan3d_ctx* ctx, int64_t* count_out)
     if (ctx->texture && !ctx->rgb) CK(dalloc(&ctx->rgb, 3 * n));
     const Shape s = shape_of(ctx->cfg);
     int nl = 0;
-    CK(launch_compact(s, ctx->xyz, ctx->valid, ctx->texture, ctx->block_counts, ctx->pts, ctx->pix,
+    CK(launch_compact(s, ctx->xyz, ctx->valid, ctx->texture, ctx->block_counts, points_of(ctx), ctx->pix,
                       ctx->texture ? ctx->rgb : nullptr, ctx->d_count, ctx->stream, &nl));
     ctx->launches += nl;
     ctx->have_points = true;
@@ -484,7 +486,7 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     a.unw_v = ctx->unwrapped[0]; a.unw_h = ctx->unwrapped[1];
     a.code_v = ctx->code[0]; a.code_h = ctx->code[1];
     a.valid = ctx->valid; a.cpmap = ctx->cpmap;
-    a.pts = ctx->pts; a.pix = ctx->pix;
+    a.pts = points_of(ctx); a.pix = ctx->pix;
     a.rgb = ctx->texture ? ctx->rgb : nullptr; a.texture = ctx->texture;
     a.d_count = ctx->d_count; a.tile_state = ctx->tile_state; a.trace = ctx->trace; a.tile_flags = ctx->tile_flags; a.tile_list = ctx->tile_list + 1; a.n_list = ctx->tile_list;
     a.cam_lut = ctx->cam_lut; a.proj_lut = ctx->proj_lut; a.atan_tab = ctx->atan_tab;
@@ -617,7 +619,7 @@ int scan3d_get_points(scan3d_ctx* ctx, float* xyz_host, uint32_t* pix_host, uint
     if (rc) return rc;
     if (n > max_points) n = max_points;
     if (n <= 0) return SCAN3D_OK;
-    if (xyz_host) CK(cudaMemcpyAsync(xyz_host, ctx->pts, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz_host) CK(cudaMemcpyAsync(xyz_host, points_of(ctx), (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
     if (pix_host) {
         if (!ctx->pix) return fail(ctx, SCAN3D_ERR_STATE, "pixel indices were not produced (stage API or SCAN3D point-pixel flag)");
         CK(cudaMemcpyAsync(pix_host, ctx->pix, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -630,7 +632,73 @@ int scan3d_get_points(scan3d_ctx* ctx, float* xyz_host, uint32_t* pix_host, uint
     return SCAN3D_OK;
 }
 
-void* scan3d_device_points(scan3d_ctx* ctx) { return ctx ? ctx->pts : nullptr; }
+void* scan3d_device_points(scan3d_ctx* ctx) { return ctx ? points_of(ctx) : nullptr; }
+
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+
+int scan3d_peer_alloc(int device, int64_t bytes, void** dev_ptr, uint8_t handle_out[64])
+{
+    if (!dev_ptr || !handle_out || bytes <= 0) return SCAN3D_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return SCAN3D_ERR_CUDA;
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return SCAN3D_ERR_CUDA; }
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return SCAN3D_ERR_CUDA; }
+    memcpy(handle_out, &h, 64);
+    *dev_ptr = p;
+    return SCAN3D_OK;
+}
+
+int scan3d_peer_free(int device, void* dev_ptr)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return SCAN3D_ERR_CUDA;
+    return cudaFree(dev_ptr) == cudaSuccess ? SCAN3D_OK : SCAN3D_ERR_CUDA;
+}
+
+int scan3d_peer_open(int device, const uint8_t handle[64], void** dev_ptr)
+{
+    if (!dev_ptr || !handle) return SCAN3D_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return SCAN3D_ERR_CUDA;     // the ACCESSING device: lazy peer access is set up for it
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return SCAN3D_ERR_CUDA; }
+    *dev_ptr = p;
+    return SCAN3D_OK;
+}
+
+int scan3d_peer_close(int device, void* dev_ptr)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return SCAN3D_ERR_CUDA;
+    return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? SCAN3D_OK : SCAN3D_ERR_CUDA;
+}
+
+int scan3d_set_points_buffer(scan3d_ctx* ctx, void* points_dev, int64_t capacity_points)
+{
+    if (!ctx) return SCAN3D_ERR_ARG;
+    if (ctx->cfg.dirs != 2) return fail(ctx, SCAN3D_ERR_STATE, "no point cloud in a one-direction configuration");
+    if (points_dev && capacity_points < (int64_t)npix(ctx)) return fail(ctx, SCAN3D_ERR_ARG, "points buffer smaller than W*H points");
+    if (points_dev && ((uintptr_t)points_dev & 15)) return fail(ctx, SCAN3D_ERR_ARG, "points buffer must be 16-byte aligned");
+    if (points_dev) {
+        // memory of another GPU (mapped through CUDA IPC, or allocated there by this process):
+        // kernels of this context's device need peer access to it
+        CK(cudaSetDevice(ctx->device));
+        cudaPointerAttributes attr;
+        CK(cudaPointerGetAttributes(&attr, points_dev));
+        if (attr.type != cudaMemoryTypeDevice) return fail(ctx, SCAN3D_ERR_ARG, "points buffer is not device memory");
+        if (attr.device != ctx->device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctx->device, attr.device));
+            if (!can) return fail(ctx, SCAN3D_ERR_ARG, "no peer access from this context's GPU to the points buffer's GPU");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail(ctx, SCAN3D_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    ctx->pts_ext = (float*)points_dev;
+    ctx->have_points = false;
+    return SCAN3D_OK;
+}
 void* scan3d_device_point_pixels(scan3d_ctx* ctx) { return ctx ? ctx->pix : nullptr; }
 void* scan3d_device_point_count(scan3d_ctx* ctx) { return ctx ? ctx->d_count : nullptr; }
 

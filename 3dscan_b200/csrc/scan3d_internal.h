@@ -27,6 +27,7 @@ struct scan3d_ctx {
     double2* cam_lut = nullptr;    // [H][W] (u',v') of the local rows, only if the camera is distorted
     double2* proj_lut = nullptr;   // [PH][PW], only if the projector is distorted
     double* atan_tab = nullptr;    // hi[33] then lo[33]
+    float* pts_ext = nullptr;      // scan3d_set_points_buffer: caller-owned (possibly peer) destination of the points
     uint8_t* roi_eff = nullptr;    // SCAN3D_FLAG_MODULATION_MASK: ROI && modulation criterion of the current direction
     double* nstep_w = nullptr;     // sin[64] then cos[64] (generic-N extension)
 

@@ -113,3 +113,111 @@ def allgather_points(points, count, group=None):
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded, group=group)
     return torch.cat([p[:n] for p, n in zip(parts, counts)]), counts
+
+
+class PeerPointSink:
+    """Row-sharded mode with the exchange folded into the reconstruction kernel.
+
+    Rank `dst` owns `slots` staging blocks per other rank (`scan3d_peer_alloc`) and shares their
+    CUDA IPC handles; every other rank maps its blocks (`scan3d_peer_open`) and hands the mapped
+    pointer to its context
+    (`scan3d_set_points_buffer`), so the fused kernel's IO warps stream the compacted points
+    straight into `dst`'s memory over NVLink while the decode is still running -- no NCCL transfer
+    afterwards, nothing that needs SMs beside the persistent kernel.  What is left per scan is
+    `finish()`: an all-gather of the counts (the one host sync) and, on `dst`, one device copy per
+    other rank that moves its block to its raster offset behind the lower ranks' points.
+
+    Ordering: `finish(slot)` is stream-ordered after the rank's reconstruction; the all-gather
+    completes on `dst` only after every rank's kernel has, and a kernel's peer writes are performed
+    by the time it completes.  A block is written again `slots` scans later; `finish` makes the
+    stream that runs the next all-gather wait for the copy-out of the block that scan will reuse.
+    """
+
+    def __init__(self, ctx, capacity_points, dst=0, group=None, slots=2):
+        import importlib
+        s3 = importlib.import_module("3dscan_b200")
+        self._s3 = s3
+        self.group, self.dst, self.slots = group, dst, slots
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.ctx = list(ctx) if isinstance(ctx, (list, tuple)) else [ctx] * slots
+        self.device = torch.cuda.current_device()
+        caps = [None] * self.world
+        dist.all_gather_object(caps, int(capacity_points), group=group)
+        self.caps = caps
+        self.copied = [None] * slots          # events: block of slot s copied out on dst
+        self.owned, self.opened, self.stage = [], [], {}
+        payload = [None]
+        if self.rank == dst:
+            handles = {}
+            for r in range(self.world):
+                if r == dst:
+                    continue
+                blocks, hs = [], []
+                for _ in range(slots):
+                    ptr, h = s3.peer_alloc(self.device, caps[r] * 12)
+                    self.owned.append(ptr)
+                    blocks.append(s3.wrap_device(ptr, (caps[r], 3), "<f4"))
+                    hs.append(h)
+                self.stage[r], handles[r] = blocks, hs
+            payload[0] = handles
+        dist.broadcast_object_list(payload, src=dst, group=group)
+        if self.rank != dst:
+            for s, h in enumerate(payload[0][self.rank]):
+                ptr = s3.peer_open(self.device, h)        # opened FROM this rank's device: lazy peer access
+                self.opened.append(ptr)
+                self.ctx[s].set_points_buffer(ptr, caps[self.rank])
+        dist.barrier(group=group)
+
+    def begin(self, slot):
+        """Before enqueuing the reconstruction of a scan that uses block `slot` (needed when one
+        context serves several slots; with one context per slot it changes nothing)."""
+        if self.rank != self.dst:
+            self.ctx[slot].set_points_buffer(self.opened[slot], self.caps[self.rank])
+
+    def bind_output(self, slot, out):
+        """dst == lowest rank only: its own points start at offset 0, so its context can write `out` directly."""
+        if self.rank == self.dst and self.dst == 0:
+            self.ctx[slot].set_points_buffer(out.data_ptr(), out.shape[0])
+
+    def finish(self, slot, count, own_points, out):
+        """All ranks, after their reconstruction of this scan was enqueued on the current stream.
+        count: device-resident count tensor of this rank.  Returns (points, counts) on dst."""
+        dev = count.device
+        cur = torch.cuda.current_stream()
+        nxt = (slot + 1) % self.slots
+        if self.rank == self.dst and self.copied[nxt] is not None:
+            cur.wait_event(self.copied[nxt])      # the scan that reuses block `nxt` starts after this all-gather
+        counts_all = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts_all, count.reshape(1).to(torch.int64), group=self.group)
+        counts = [int(v) for v in counts_all.tolist()]
+        if self.rank != self.dst:
+            return None, counts
+        offsets = [0]
+        for n in counts:
+            offsets.append(offsets[-1] + n)
+        result = out[:offsets[-1]]
+        own = result[offsets[self.dst]:offsets[self.dst + 1]]
+        if counts[self.dst] and own.data_ptr() != own_points.data_ptr():
+            own.copy_(own_points[:counts[self.dst]])
+        for r, blocks in self.stage.items():
+            if counts[r]:
+                result[offsets[r]:offsets[r + 1]].copy_(blocks[slot][:counts[r]])
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.copied[slot] = ev
+        return result, counts
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for c in set(self.ctx):
+            try:
+                c.set_points_buffer(None, 0)
+            except Exception:
+                pass
+        for p in self.opened:
+            self._s3.peer_close(self.device, p)
+        dist.barrier(group=self.group)
+        for p in self.owned:
+            self._s3.peer_free(self.device, p)
+        self.opened, self.owned, self.stage = [], [], {}

@@ -177,6 +177,21 @@ int scan3d_point_count(scan3d_ctx *ctx, int64_t *count_out);          /* syncs t
 int scan3d_get_points(scan3d_ctx *ctx, float *xyz_host, uint32_t *pix_host, uint8_t *rgb_host,
                       int64_t max_points);
 void *scan3d_device_points(scan3d_ctx *ctx);        /* f32[capacity][3] */
+/* Let the reconstruction write its compacted points into a caller-provided device buffer of at
+ * least capacity_points*12 bytes (capacity_points >= W*H) instead of the ctx-owned one; NULL
+ * restores the ctx-owned buffer.  The pointer may be PEER memory (another GPU's allocation
+ * mapped into this process, e.g. through CUDA IPC): the kernel's point stream then goes straight
+ * over NVLink while the decode is still running -- how the row-sharded mode delivers every
+ * rank's points to one GPU without a separate exchange (3dscan_b200/sharding.py, PeerPointSink).
+ * No reference counterpart (the reference is single-process, 8/save_point_cloud.cpp:85-136). */
+int scan3d_set_points_buffer(scan3d_ctx *ctx, void *points_dev, int64_t capacity_points);
+/* Helpers for that mode (one process per GPU): allocate a device block on `device` and export
+ * its CUDA IPC handle (64 bytes); map another process's block for kernels running on `device`
+ * (cudaIpcOpenMemHandle with lazy peer access).  close/free undo them. */
+int scan3d_peer_alloc(int device, int64_t bytes, void **dev_ptr, uint8_t handle_out[64]);
+int scan3d_peer_free(int device, void *dev_ptr);
+int scan3d_peer_open(int device, const uint8_t handle[64], void **dev_ptr);
+int scan3d_peer_close(int device, void *dev_ptr);
 void *scan3d_device_point_pixels(scan3d_ctx *ctx);  /* u32[capacity]    */
 void *scan3d_device_point_count(scan3d_ctx *ctx);   /* u32[1] on device (for collectives) */
 

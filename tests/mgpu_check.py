@@ -42,6 +42,34 @@ def main():
         ok = n_ref == sum(counts) and np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
         print("row-shard over %d GPUs: %d points, counts %s, identical to 1 GPU: %s" % (world, n_ref, counts, ok))
         ref.close()
+    # same frame again with the exchange folded into the kernel: the other ranks' IO warps write their
+    # points into rank 0's memory over NVLink (PeerPointSink), rank 0 only moves the blocks into place
+    import bench
+    sink = sh.PeerPointSink(ctx, rows * W, dst=0, slots=2)
+    out = torch.empty((H * W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None
+    cnt = bench._wrap_device(torch, ctx.device_point_count(), (1,), "<i4")
+    st = torch.cuda.Stream()                               # (stream handle 0 would mean "ctx-owned stream")
+    torch.cuda.set_stream(st)
+    ctx.set_stream(st.cuda_stream)
+    stack_d = torch.from_numpy(np.ascontiguousarray(stack[:, row0:row0 + rows])).cuda()
+    roi_d = torch.from_numpy(roi).cuda()
+    ok2 = True
+    for rep in range(3):                                   # slot 0, 1, 0: exercises block reuse
+        if rank == 0:
+            out.zero_()
+        torch.cuda.synchronize(); dist.barrier()
+        sink.begin(rep % 2)
+        ctx.reconstruct_dev(stack_d.data_ptr(), roi_d.data_ptr())
+        own = bench._wrap_device(torch, ctx.device_points(), (rows * W, 3), "<f4") if rank == 0 else None
+        got2, counts2 = sink.finish(rep % 2, cnt, own, out)
+        torch.cuda.synchronize()
+        if rank == 0:
+            same = sum(counts2) == n_ref and np.array_equal(got2.cpu().numpy().view(np.uint32), want.view(np.uint32))
+            ok2 = ok2 and same
+    if rank == 0:
+        print("in-kernel NVLink point stream (PeerPointSink), 3 scans: identical to 1 GPU: %s" % ok2)
+    ok = ok and ok2
+    sink.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     ctx.close()
