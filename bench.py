@@ -171,13 +171,27 @@ def bench_rowshard(args, s3, cal, cfg_full, config, rank, world, local_rank, str
     def decode(k):
         ctxs[k & 1].reconstruct_dev(stack_d.data_ptr(), roi_d.data_ptr())      # runs on streams[k & 1]
 
+    # --exchange peer (default, N > 1): the other ranks' kernels stream their points into rank 0's
+    # memory over NVLink (sharding.PeerPointSink); what is left per scan is the all-gather of the
+    # counts and one device copy per rank on rank 0.  --exchange nccl: send/recv after the kernel.
+    sink = None
+    if world > 1 and args.exchange == "peer":
+        sink = sh.PeerPointSink(ctxs, rows * W, dst=0, slots=2)
+        for i in range(2):
+            sink.bind_output(i, outs[i]) if rank == 0 else None
+        if rank == 0:
+            srcs = [outs[0], outs[1]]          # rank 0's contexts write their points straight into the outputs
+
     def step():
         # one scan per step: enqueue the decode of scan k+1, then exchange scan k (the host wait for
-        # the counts inside gather_points only depends on scan k's stream)
+        # the counts only depends on scan k's stream)
         k = seq[0]
         decode(k + 1)
         with torch.cuda.stream(streams[k & 1]):
-            res, counts = sh.gather_points(srcs[k & 1], cnts[k & 1], dst=0, out=outs[k & 1])
+            if sink is not None:
+                res, counts = sink.finish(k & 1, cnts[k & 1], srcs[k & 1], outs[k & 1])
+            else:
+                res, counts = sh.gather_points(srcs[k & 1], cnts[k & 1], dst=0, out=outs[k & 1])
         total[0] = sum(counts)
         seq[0] = k + 1
 
@@ -213,7 +227,7 @@ def bench_rowshard(args, s3, cal, cfg_full, config, rank, world, local_rank, str
     peak, peak_kind = measured_peak_gbs()
     achieved = bpp * npix / (ms_max * 1e-3 / args.steps) / 1e9
     if rank == 0:
-        config.update({"sharding": "one frame row-sharded over %d rank(s); all-gather of counts + NCCL send/recv of compacted points to rank 0, overlapped with the next scan's decode (2 contexts, 2 streams)" % world,
+        config.update({"sharding": ("one frame row-sharded over %d rank(s); " % world) + ("points streamed by the kernel into rank 0's memory over NVLink (peer memory), all-gather of counts + one device copy per rank" if sink is not None else "all-gather of counts + NCCL send/recv of compacted points to rank 0") + "; 2 contexts on 2 streams",
                        "rows_per_rank": rows, "scans_per_gpu_per_step": 1, "resident_ring": 1,
                        "l2_policy": "inputs larger than L2 (%.2f GB per GPU)" % (nf * rows * W / 1e9)})
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
@@ -227,6 +241,8 @@ def bench_rowshard(args, s3, cal, cfg_full, config, rank, world, local_rank, str
                 "e2e": None, "cpu_baseline": None}
         print(json.dumps(line))
     torch.cuda.synchronize()
+    if sink is not None:
+        sink.close()
     for c in ctxs:
         c.close()
     if world > 1:
@@ -256,6 +272,7 @@ def main():
                     help="reference operation order in the normal-equation solve (bit-identical points)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="row-shard workload, N>1: how the points reach rank 0")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
