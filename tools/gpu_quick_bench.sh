@@ -1,3 +1,4 @@
+# quick parity + bench loop used while optimising the fused kernel
 timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 PYFMT='import sys,json
 d=json.loads(sys.stdin.read()); r=d["roofline"]; print(d["config"]["workload"][:3], d["config"]["fused_cfg"], d["config"]["triangulation"][:9], "us/scan %.1f"%r["avg_launch_us"], "frac %.3f"%r["frac"], "scans/s %.0f"%d["scans_per_s"], "clk", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])'

@@ -1,3 +1,4 @@
+# Round-end artefacts on one B200 (from the repo root: gpurun -- bash tools/gpu_round_artifacts.sh); needs a trace-enabled build in 3dscan_b200/lib_trace for the last line
 timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 timeout 120 python __graft_entry__.py smoke 2>&1 | tail -1
 timeout 400 python bench.py > gpurun_out/bench_r1_default.json 2> gpurun_out/bench_r1_default.err; tail -c 400 gpurun_out/bench_r1_default.json; tail -3 gpurun_out/bench_r1_default.err
