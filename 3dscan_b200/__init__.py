@@ -134,6 +134,10 @@ def cuda_lib():
     L.scan3d_write_pcd.argtypes = [vp, C.c_char_p]
     L.scan3d_launch_count.argtypes = [vp]
     L.scan3d_set_points_buffer.argtypes = [vp, vp, i64]
+    L.scan3d_pattern_bytes.argtypes = [C.POINTER(Config), i32]
+    L.scan3d_pattern_bytes.restype = i64
+    L.scan3d_generate_patterns.argtypes = [vp, i32, vp]
+    L.scan3d_generate_patterns_dev.argtypes = [vp, i32, vp]
     L.scan3d_peer_alloc.argtypes = [i32, i64, C.POINTER(vp), C.c_char_p]
     L.scan3d_peer_free.argtypes = [i32, vp]
     L.scan3d_peer_open.argtypes = [i32, C.c_char_p, C.POINTER(vp)]
@@ -388,6 +392,16 @@ class Scan3D:
 
     def device_point_count(self):
         return self.L.scan3d_device_point_count(self.h)
+
+    def generate_patterns(self, direction):
+        """generate_pattern() on the GPU: u8 [N + 2M][PH][PW] (fringe, Gray, inverse Gray) of one direction."""
+        M = self.cfg.M_v if direction == 0 else self.cfg.M_h
+        out = np.empty((self.cfg.N + 2 * M, self.cfg.PH, self.cfg.PW), np.uint8)
+        self._ck(self.L.scan3d_generate_patterns(self.h, int(direction), _ptr(out)))
+        return out
+
+    def generate_patterns_dev(self, direction, dev_ptr):
+        self._ck(self.L.scan3d_generate_patterns_dev(self.h, int(direction), C.c_void_p(dev_ptr)))
 
     def write_ply(self, path, binary=False):
         self._ck(self.L.scan3d_write_ply(self.h, path.encode(), 1 if binary else 0))

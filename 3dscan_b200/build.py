@@ -39,7 +39,7 @@ def _stale(target, deps):
 
 
 def _deps(folder, extra=()):
-    out = [os.path.join(folder, f) for f in os.listdir(folder)
+    out = [os.path.join(d, f) for d in (folder, os.path.join(HERE, "common")) for f in os.listdir(d)
            if f.endswith((".cu", ".cuh", ".h", ".cpp", ".hpp"))]
     out += list(extra)
     out.append(os.path.abspath(__file__))

@@ -6,10 +6,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
 #include "scan3d_internal.h"
+#include "../common/scan3d_pattern_profile.h"
 
 using namespace s3d;
 
@@ -202,7 +204,7 @@ void scan3d_destroy(scan3d_ctx* ctx)
     void* ptrs[] = {ctx->cam_lut, ctx->proj_lut, ctx->atan_tab, ctx->nstep_w, ctx->wrapped[0], ctx->wrapped[1],
                     ctx->unwrapped[0], ctx->unwrapped[1], ctx->code[0], ctx->code[1], ctx->mask[0],
                     ctx->mask[1], ctx->valid, ctx->cpmap, ctx->xyz, ctx->pts, ctx->pix, ctx->rgb,
-                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff};
+                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff, ctx->pattern_profiles};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -733,6 +735,61 @@ int scan3d_write_ply(scan3d_ctx* ctx, const char* path, int binary)
     }
     const bool ok = fclose(f) == 0;
     return ok ? SCAN3D_OK : fail(ctx, SCAN3D_ERR_IO, "PLY write failed");
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 1: projector patterns on the device
+// ------------------------------------------------------------------------------------------
+int64_t scan3d_pattern_bytes(const scan3d_config* c, int dir)
+{
+    if (!c || dir < 0 || dir > 1 || c->PW < 1 || c->PH < 1) return 0;
+    return (int64_t)(c->N + 2 * (dir == 0 ? c->M_v : c->M_h)) * c->PW * c->PH;
+}
+
+int scan3d_generate_patterns_dev(scan3d_ctx* ctx, int dir, uint8_t* patterns_dev)
+{
+    if (!ctx || !patterns_dev) return fail(ctx, SCAN3D_ERR_ARG, "null argument");
+    const scan3d_config& c = ctx->cfg;
+    if (dir < 0 || dir > 1 || c.PW < 1 || c.PH < 1) return fail(ctx, SCAN3D_ERR_ARG, "bad direction or projector size");
+    if (c.PW % 16 != 0 || ((uintptr_t)patterns_dev & 15)) return fail(ctx, SCAN3D_ERR_ARG, "PW and the destination must be multiples of 16");
+    CK(cudaSetDevice(ctx->device));
+    const int M = dir == 0 ? c.M_v : c.M_h, fw = dir == 0 ? c.fw_v : c.fw_h;
+    const int len = dir == 0 ? c.PW : c.PH, lenp = (len + 15) & ~15, np = c.N + 2 * M;
+    const size_t max_prof = (size_t)(16 + 2 * 15) * (((size_t)std::max(c.PW, c.PH) + 15) & ~(size_t)15);
+    if (!ctx->pattern_profiles) CK(dalloc(&ctx->pattern_profiles, 2 * max_prof));
+    uint8_t* d_prof = ctx->pattern_profiles + (size_t)dir * max_prof;
+    if (!ctx->have_profiles[dir]) {      // the profiles depend on the configuration only: once per context
+        std::vector<uint8_t> prof((size_t)np * lenp, 0);
+        for (int k = 0; k < c.N; k++) s3d_profile::pattern_profile(0, c.N, fw, k, len, &prof[(size_t)k * lenp]);
+        for (int k = 0; k < M; k++) {
+            s3d_profile::pattern_profile(1, M, fw, k, len, &prof[(size_t)(c.N + k) * lenp]);
+            s3d_profile::pattern_profile(2, M, fw, k, len, &prof[(size_t)(c.N + M + k) * lenp]);
+        }
+        CK(cudaMemcpyAsync(d_prof, prof.data(), prof.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));      // prof is a local
+        ctx->have_profiles[dir] = true;
+    }
+    CK(launch_expand_patterns(d_prof, lenp, np, patterns_dev, c.PW, c.PH, dir, ctx->stream));
+    ctx->launches++;
+    return SCAN3D_OK;
+}
+
+int scan3d_generate_patterns(scan3d_ctx* ctx, int dir, uint8_t* patterns_host)
+{
+    if (!ctx || !patterns_host) return fail(ctx, SCAN3D_ERR_ARG, "null argument");
+    const int64_t bytes = scan3d_pattern_bytes(&ctx->cfg, dir);
+    if (bytes <= 0) return fail(ctx, SCAN3D_ERR_ARG, "bad direction or projector size");
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* d = nullptr;
+    CK(cudaMalloc((void**)&d, (size_t)bytes));
+    int rc = scan3d_generate_patterns_dev(ctx, dir, d);
+    cudaError_t e = cudaSuccess;
+    if (rc == SCAN3D_OK) e = cudaMemcpyAsync(patterns_host, d, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, SCAN3D_ERR_CUDA, cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return SCAN3D_OK;
 }
 
 int scan3d_write_pcd(scan3d_ctx* ctx, const char* path)

@@ -28,6 +28,8 @@ struct scan3d_ctx {
     double2* proj_lut = nullptr;   // [PH][PW], only if the projector is distorted
     double* atan_tab = nullptr;    // hi[33] then lo[33]
     float* pts_ext = nullptr;      // scan3d_set_points_buffer: caller-owned (possibly peer) destination of the points
+    uint8_t* pattern_profiles = nullptr;   // scan3d_generate_patterns: 1-D profiles of both directions' patterns
+    bool have_profiles[2] = {false, false};
     uint8_t* roi_eff = nullptr;    // SCAN3D_FLAG_MODULATION_MASK: ROI && modulation criterion of the current direction
     double* nstep_w = nullptr;     // sin[64] then cos[64] (generic-N extension)
 
@@ -82,6 +84,8 @@ inline Shape shape_of(const scan3d_config& c)
 
 // ---- stage-wise kernels (any W, H) ----
 cudaError_t launch_mask(const Shape& s, const uint8_t* roi_full, uint8_t* mask, cudaStream_t st);
+cudaError_t launch_expand_patterns(const uint8_t* profiles, int profile_len, int n_patterns, uint8_t* out, int PW, int PH,
+                                   int dir, cudaStream_t st);
 cudaError_t launch_modulation_roi(const Shape& s, const uint8_t* fringe, const uint8_t* roi, uint8_t* roi_eff, cudaStream_t st);
 cudaError_t launch_wrapped(const Shape& s, int N, const uint8_t* fringe, const uint8_t* roi_full,
                            float* wrapped, const double* atan_tab, const double* nstep_w,

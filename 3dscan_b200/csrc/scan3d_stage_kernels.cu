@@ -65,6 +65,41 @@ cudaError_t launch_modulation_roi(const Shape& s, const uint8_t* fringe, const u
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// projector patterns (1/pattern_generator.cpp): a pattern is constant along its stripes, so each
+// image is its 1-D profile (host, exact libm: common/scan3d_pattern_profile.h) expanded across
+// the other axis.  Pure write stream: 16 bytes per thread, PW % 16 == 0.
+// ------------------------------------------------------------------------------------------
+constexpr int PATTERN_ROWS_PER_BLOCK = 32;
+__global__ void k_expand_patterns(const uint8_t* __restrict__ profiles, int profile_len, int n_patterns,
+                                  uint8_t* __restrict__ out, int PW, int PH, int dir)
+{
+    const int x16 = blockIdx.x * blockDim.x + threadIdx.x;       // 16-pixel group along the row
+    const int p = blockIdx.z;
+    if (x16 * 16 >= PW) return;
+    const uint8_t* prof = profiles + (size_t)p * profile_len;
+    const int y0 = blockIdx.y * PATTERN_ROWS_PER_BLOCK, y1 = min(PH, y0 + PATTERN_ROWS_PER_BLOCK);
+    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)p * PH + y0) * PW + 16 * x16);
+    const int pitch = PW / 16;
+    if (dir == 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(prof + 16 * x16);    // vertical stripes: value = f(column)
+        for (int y = y0; y < y1; y++, dst += pitch) __stcs(dst, v);
+    } else {
+        for (int y = y0; y < y1; y++, dst += pitch) {
+            const uint32_t b = prof[y] * 0x01010101u;                        // horizontal stripes: value = f(row)
+            __stcs(dst, make_uint4(b, b, b, b));
+        }
+    }
+}
+
+cudaError_t launch_expand_patterns(const uint8_t* profiles, int profile_len, int n_patterns, uint8_t* out, int PW, int PH,
+                                   int dir, cudaStream_t st)
+{
+    dim3 grid(cdiv(PW / 16, 128), cdiv(PH, PATTERN_ROWS_PER_BLOCK), n_patterns);
+    k_expand_patterns<<<grid, 128, 0, st>>>(profiles, profile_len, n_patterns, out, PW, PH, dir);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mask(const Shape& s, const uint8_t* roi_full, uint8_t* mask, cudaStream_t st)
 {
     dim3 grid(cdiv(s.W, 256), s.H);

@@ -17,6 +17,7 @@
 #endif
 
 #include "../../include/scan3d_host.h"
+#include "../common/scan3d_pattern_profile.h"
 
 namespace {
 
@@ -91,13 +92,7 @@ inline double fringe_shift(int N, int k, double pi)
     return 2.0 * PI_TRUE * k / N;   // extension: equally spaced over the true period
 }
 
-inline int gray_bit(int code_number, int i, int M)
-{
-    // B = binary digits of code_number, index 0 = MSB of an M-bit word; G0 = B0, Gi = B(i-1)^B(i)
-    const int b_i = (code_number >> (M - 1 - i)) & 1;
-    const int b_prev = i == 0 ? 0 : (code_number >> (M - i)) & 1;
-    return b_i ^ b_prev;
-}
+using s3d_profile::gray_bit;
 
 inline uint8_t clamp_u8(double v)
 {
@@ -134,26 +129,7 @@ void scan3d_scale_calibration(const scan3d_calib* in, double cs, double ps, scan
 int scan3d_synth_pattern_row(int kind, int n_or_m, int fw, int k, int length, uint8_t* out)
 {
     if (!out || fw < 1 || length < 1) return SCAN3D_ERR_ARG;
-    if (kind == 0) {
-        const int N = n_or_m;
-        for (int c = 0; c < length; c++) {
-            const float q = (float)c / (float)fw;
-            double arg;
-            // the reference's expressions, token for token (Pi is the textual macro 22.0/7.0)
-            if (N == 3) arg = q * 2.0 * 22.0 / 7.0 - 22.0 / 7.0 - ((22.0 / 7.0) / 2.0) + (22.0 / 7.0 / 2.0) * (float)k;
-            else if (N == 4) arg = q * (2.0 * 22.0 / 7.0) - 22.0 / 7.0 + (22.0 / 7.0 / 2.0) * (float)k;
-            else if (N == 5) arg = q * (2.0 * 22.0 / 7.0) - 22.0 / 7.0 - 2.0 * ((22.0 / 7.0) / 2) + ((22.0 / 7.0) / 2) * (float)k;
-            else arg = q * (2.0 * 22.0 / 7.0) - 22.0 / 7.0 + 2.0 * PI_TRUE * k / N;
-            const float t = 127.0f + 128.0f * cosf((float)arg);
-            out[c] = (unsigned char)t;
-        }
-        return SCAN3D_OK;
-    }
-    const int M = n_or_m;
-    for (int c = 0; c < length; c++) {
-        const int g = gray_bit(c / fw, k, M) * 255;
-        out[c] = (uint8_t)(kind == 1 ? g : 255 - g);
-    }
+    s3d_profile::pattern_profile(kind, n_or_m, fw, k, length, out);
     return SCAN3D_OK;
 }
 

@@ -195,6 +195,15 @@ int scan3d_peer_close(int device, void *dev_ptr);
 void *scan3d_device_point_pixels(scan3d_ctx *ctx);  /* u32[capacity]    */
 void *scan3d_device_point_count(scan3d_ctx *ctx);   /* u32[1] on device (for collectives) */
 
+/* generate_pattern() (1/pattern_generator.cpp:513): the projector patterns of one direction, in the
+ * order the capture stack uses -- fringe[N] (:291-397), Gray[M] (:56-197), inverse Gray[M]
+ * (:490-507) -- as u8 images [N + 2M][PH][PW], written by the GPU (PW % 16 == 0).  dir 0 =
+ * vertical stripes (value depends on the column), 1 = horizontal.  N = 3, 4, 5 follow the
+ * reference's expressions (bit-identical to its Generated_patterns images); other N use 2*pi*k/N. */
+int64_t scan3d_pattern_bytes(const scan3d_config *cfg, int dir);
+int scan3d_generate_patterns_dev(scan3d_ctx *ctx, int dir, uint8_t *patterns_dev);
+int scan3d_generate_patterns(scan3d_ctx *ctx, int dir, uint8_t *patterns_host);
+
 /* save_point_cloud()'s pcl::io::savePLYFile equivalent: "x y z red green blue" vertices,
  * ASCII (binary = 0, PCL's default) or binary_little_endian. */
 int scan3d_write_ply(scan3d_ctx *ctx, const char *path, int binary);

@@ -302,6 +302,35 @@ def test_c1_crop_through_gpu_matches_reference_images():
     ctx.close()
 
 
+@pytest.mark.parametrize("N,Mv,Mh,fw,PW,PH", [(3, 6, 5, 32, 1280, 720), (4, 7, 7, 8, 1024, 768), (5, 8, 8, 8, 1920, 1080), (8, 10, 10, 4, 4096, 3000)])
+def test_device_pattern_generator(N, Mv, Mh, fw, PW, PH):
+    """scan3d_generate_patterns (stage 1 on the GPU) against the host profiles of the same expressions,
+    and for the reference's own configuration against its stored Generated_patterns images."""
+    cfg = s3.make_config(64, 16, PW, PH, N, Mv, Mh, fw, fw, 2)
+    ctx = s3.Scan3D(cfg, 0, None)
+    for d, (M, length) in enumerate(((Mv, PW), (Mh, PH))):
+        got = ctx.generate_patterns(d)
+        assert got.shape == (N + 2 * M, PH, PW)
+        rows = [s3.synth_pattern_row(0, N, fw, k, length) for k in range(N)]
+        rows += [s3.synth_pattern_row(1, M, fw, k, length) for k in range(M)]
+        rows += [s3.synth_pattern_row(2, M, fw, k, length) for k in range(M)]
+        for p, r in enumerate(rows):
+            want = np.broadcast_to(r[None, :] if d == 0 else r[:, None], (PH, PW))
+            assert np.array_equal(got[p], want), (d, p)
+    if (N, fw, PW, PH) == (3, 32, 1280, 720):
+        import os
+        from helpers import GOLDEN
+        k = np.load(os.path.join(GOLDEN, "pattern_kat.npz"))          # rows/columns of the reference's pattern images
+        gv, gh = ctx.generate_patterns(0), ctx.generate_patterns(1)
+        for i in range(3):
+            assert np.array_equal(gv[i, 0], k["fringe_v_row0"][i]) and np.array_equal(gh[i, :, 0], k["fringe_h_col0"][i])
+        for i in range(6):
+            assert np.array_equal(gv[3 + i, 0], k["gray_v_row0"][i]) and np.array_equal(gv[9 + i, 0], k["inv_v_row0"][i])
+        for i in range(5):
+            assert np.array_equal(gh[3 + i, :, 0], k["gray_h_col0"][i]) and np.array_equal(gh[8 + i, :, 0], k["inv_h_col0"][i])
+    ctx.close()
+
+
 def test_ply_writer(tmp_path):
     W, H, PW, PH = 256, 64, 512, 512
     cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
