@@ -4,18 +4,26 @@
 // see DESIGN.md section 7):
 //
 //   * plane outputs (phases, fringe orders, valid, c_p_map) leave straight from registers as
-//     16-byte vector stores -- each thread owns 4 consecutive pixels, a warp writes 512 contiguous
-//     bytes per plane -- so nothing but the points is staged in shared memory;
+//     vector stores -- each thread owns 4 consecutive pixels -- so nothing but the points is
+//     staged in shared memory;
 //   * the input slot is therefore dead right after the integer phase: consumers hand it back at
-//     once and ONE slot per CTA keeps the loads a full FP64 phase ahead;
-//   * the triangulated points stay in registers until the block scan, then go to one of two small
-//     compacted-point buffers;
-//   * producer and epilogue are one "IO warp" running an event loop: issue the next tile's TMA bulk
-//     loads when the slot frees, publish a staged tile's count, advance a resumable decoupled
-//     look-back without ever blocking, stream resolved tiles out.
+//     once and ONE slot per CTA keeps the loads a full FP64 phase ahead; a tile is loaded by one
+//     2-D tensor-map TMA copy ([frames] x [tile bytes]);
+//   * a block scan of the valid bits gives every pixel its raster rank BEFORE the triangulation,
+//     which then writes each point straight to its rank in one of two small point buffers (a
+//     rolled loop: the unrolled version did not fit the instruction cache);
+//   * the tile's count is published before its triangulation, by the consumers, so the grid-wide
+//     prefix chain (decoupled look-back) runs ahead of the FP64 work;
+//   * work-list positions are drawn from a global counter: the CTAs of an SM run at different
+//     speeds, and equal static shares made the fast ones wait for the slow one's counts;
+//   * producer and epilogue are one "IO warp" running an event loop: issue the next tile's load
+//     when the slot frees, note a counted tile, advance a resumable look-back (walking back window
+//     after window while the words are there), stream staged tiles out.
 //
 //   CTA = CW consumer warps + 1 IO warp; shared memory per CTA = NF*T + ROI window + 2*12*T bytes
-//   (66 KB for the 12 MP config at CW = 6) -> 3 CTAs = 18 consumer warps per SM at 96 registers.
+//   (76.7 KB for the 12 MP config at CW = 7) -> 3 CTAs = 21 consumer warps per SM at 80 registers
+//   (the 16 K registers of an SM sub-partition bound the shape, see regs7).  History and
+//   measurements: DESIGN.md section 5.1, profiles/r1_optimisation_log.md.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>

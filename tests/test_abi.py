@@ -144,3 +144,17 @@ def test_bmp_and_ply_roundtrip(tmp_path):
     assert np.allclose(rows[:, :3], xyz, rtol=5e-8, atol=0)
     packed = (rgb[:, 0].astype(np.uint32) << 16) | (rgb[:, 1].astype(np.uint32) << 8) | rgb[:, 2]
     assert np.allclose(rows[:, 3], packed.view(np.float32).astype(np.float64), rtol=5e-8, atol=0)
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_gpu():
+    """Argument checks that run before any CUDA call."""
+    L = s3.cuda_lib()
+    cfg = s3.make_config(64, 16, 1280, 720, 3, 6, 5, 32, 32, 2)
+    assert L.scan3d_pattern_bytes(C.byref(cfg), 0) == (3 + 12) * 1280 * 720
+    assert L.scan3d_pattern_bytes(C.byref(cfg), 1) == (3 + 10) * 1280 * 720
+    assert L.scan3d_pattern_bytes(C.byref(cfg), 2) == 0
+    assert L.scan3d_generate_patterns(None, 0, None) != 0
+    assert L.scan3d_set_points_buffer(None, None, 0) != 0
+    p = C.c_void_p()
+    assert L.scan3d_peer_alloc(0, 0, C.byref(p), C.create_string_buffer(64)) != 0     # zero bytes
+    assert L.scan3d_peer_open(0, None, C.byref(p)) != 0
