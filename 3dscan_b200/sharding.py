@@ -32,13 +32,14 @@ def row_block(H_total, rank, world):
     return row0, rows
 
 
-def gather_points(points, count, dst=0, group=None, out=None):
+def gather_points(points, count, dst=0, group=None, out=None, aligned_staging=None):
     """Concatenate the ranks' compacted point lists, in rank order, on rank `dst`.
 
     points: [capacity, C] tensor on this rank (only the first `count` rows are valid)
     count : int, number of valid rows on this rank
     Returns (all_points, counts) on rank `dst` ([sum(counts), C] tensor, list of ints) and
     (None, counts) elsewhere.  `out` may preallocate the destination on rank `dst`.
+    aligned_staging: receive misaligned blocks through a staging block (default: on CUDA tensors).
     """
     if not dist.is_initialized():
         return points[:int(count)], [int(count)]
@@ -67,14 +68,15 @@ def gather_points(points, count, dst=0, group=None, out=None):
             result[offsets[dst]:offsets[dst + 1]].copy_(points[:counts[dst]])
         row_bytes = points.element_size() * (points[0].numel() if points.dim() > 1 else 1)
         staged = []
+        use_staging = dev.type == "cuda" if aligned_staging is None else bool(aligned_staging)
         for r in range(world):
             if r != dst and counts[r]:
                 target = result[offsets[r]:offsets[r + 1]]
-                if dev.type == "cuda" and (offsets[r] * row_bytes) % 16:
+                if use_staging and (offsets[r] * row_bytes) % 16:
                     # NCCL moves 16 bytes per thread; a receive address that is only 4-byte aligned
                     # (12 B points at an arbitrary offset) halves the transfer rate (measured 207 vs
                     # 440 GB/s).  Receive into an aligned staging block, then one device copy.
-                    stage = _staging(r, points.shape, points.dtype, dev)[:counts[r]]
+                    stage = _staging(r, counts[r], tuple(points.shape[1:]), points.dtype, dev)[:counts[r]]
                     staged.append((target, stage))
                     target = stage
                 ops.append(dist.P2POp(dist.irecv, target, r, group))
@@ -92,11 +94,14 @@ def gather_points(points, count, dst=0, group=None, out=None):
 _stage_cache = {}
 
 
-def _staging(peer, shape, dtype, dev):
-    key = (peer, tuple(shape), dtype, str(dev))
-    if key not in _stage_cache:
-        _stage_cache[key] = torch.empty(tuple(shape), dtype=dtype, device=dev)
-    return _stage_cache[key]
+def _staging(peer, rows, row_shape, dtype, dev):
+    """Per-peer receive block of at least `rows` rows (kept between calls, grown when a peer sends more)."""
+    key = (peer, tuple(row_shape), dtype, str(dev))
+    cur = _stage_cache.get(key)
+    if cur is None or cur.shape[0] < rows:
+        cur = torch.empty((max(rows, 2 * (cur.shape[0] if cur is not None else 0)),) + tuple(row_shape), dtype=dtype, device=dev)
+        _stage_cache[key] = cur
+    return cur
 
 
 def allgather_points(points, count, group=None):

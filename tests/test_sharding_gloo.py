@@ -44,6 +44,11 @@ def _worker(rank, world, port, q):
         got, _ = sh.gather_points(pts, n, dst=world - 1, out=out)
         if rank == world - 1:
             assert torch.equal(got, want) and got.data_ptr() == out.data_ptr()
+        # the aligned-staging route of the CUDA path (forced here), with the tensors sized exactly to
+        # each rank's own count: a peer may send more rows than this rank holds
+        got, _ = sh.gather_points(pts[:n].clone(), n, dst=0, aligned_staging=True)
+        if rank == 0:
+            assert torch.equal(got, want)
         allp, counts2 = sh.allgather_points(pts, n)
         assert counts2 == counts and torch.equal(allp, want)
         # frame-parallel: every scan is owned by exactly one rank
