@@ -284,8 +284,13 @@ def main():
     npix = W * H
     bpp = algorithmic_bytes_per_pixel(N, Mv, Mh, dirs)
 
-    from gpu_common import calibs, s3
-    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    # workload definition: the reference's calibration (tests/golden/calib_c1.json) scaled to the frame;
+    # nothing under oracle/ is imported on the B200 arm -- only the two CPU legs below load it
+    from helpers import load_calib_c1, scaled_calib
+    s3 = importlib.import_module("3dscan_b200")
+    cal_dict = scaled_calib(load_calib_c1(), W / 1600.0, PW / 1280.0)
+    cal_args = [cal_dict[k] for k in ("Kc", "dc", "Kp", "dp", "rc", "tc", "rp", "tp")]
+    cal = s3.make_calib(*cal_args)
     flags = 0 if args.exact_triangulation else s3.FLAG_FAST_TRIANGULATION
     cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs, flags=flags)
     config = {"workload": args.workload, "frame": [W, H], "projector": [PW, PH], "phase_steps": N,
@@ -303,6 +308,7 @@ def main():
         if rank != 0:
             return
         import oracle_ffi as o
+        ocal = o.make_calib(*cal_args)
         threads = host_threads()
         stack, roi = s3.synth_stack(cfg, cal, s3.default_synth_params(seed=0x3D5CA9))
         from gpu_common import run_oracle
@@ -466,6 +472,7 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         import oracle_ffi as o
+        ocal = o.make_calib(*cal_args)
         threads = host_threads()
         sec, runs = oracle_scan_seconds(cfg, ocal, host_stack.numpy(), host_roi.numpy(), threads, 8.0, 4)
         cpu = {"value": npix / sec / 1e6, "unit": "Mpix/s", "cores": threads, "kind": "port",

@@ -1,7 +1,7 @@
 """Diagnostics (not a test): where does the row-shard step spend its time?  torchrun, 2 GPUs."""
 import os, sys, time, importlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):  # run from the repo root
+for p in (ROOT, os.path.join(ROOT, "tests")):  # run from the repo root
     sys.path.insert(0, p)
 import numpy as np
 import torch, torch.distributed as dist
@@ -10,10 +10,11 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 s3 = importlib.import_module("3dscan_b200")
 sh = importlib.import_module("3dscan_b200.sharding")
-from gpu_common import calibs
+from helpers import load_calib_c1, scaled_calib
 import bench
 W, Ht, N, M, fw = 8192, 6144, 8, 10, 8
-cal, ocal, _ = calibs(W / 1600.0, W / 1280.0)
+_c = scaled_calib(load_calib_c1(), W / 1600.0, W / 1280.0)
+cal = s3.make_calib(*[_c[k] for k in ("Kc", "dc", "Kp", "dp", "rc", "tc", "rp", "tp")])
 row0, rows = sh.row_block(Ht, rank, world)
 cfg = s3.make_config(W, rows, W, Ht, N, M, M, fw, fw, 2, row0=row0, H_total=Ht, flags=s3.FLAG_FAST_TRIANGULATION)
 nf = s3.stack_planes(cfg)

@@ -8,12 +8,14 @@ Needs a library built with the trace hooks:
 import ctypes as C, importlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 os.environ.setdefault("SCAN3D_TRACE", "1")
-from gpu_common import calibs, s3
+from helpers import load_calib_c1, scaled_calib
+s3 = importlib.import_module("3dscan_b200")
 W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs = 4096, 3000, 4096, 3000, 8, 10, 10, 4, 4, 2
-cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+_c = scaled_calib(load_calib_c1(), W / 1600.0, PW / 1280.0)
+cal = s3.make_calib(*[_c[k] for k in ("Kc", "dc", "Kp", "dp", "rc", "tc", "rp", "tp")])
 cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs, flags=s3.FLAG_FAST_TRIANGULATION)
 stack, roi = s3.synth_stack(cfg, cal)
 ctx = s3.Scan3D(cfg, 0, cal)
