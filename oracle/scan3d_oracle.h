@@ -25,6 +25,9 @@
  *   undistort / normal-equation solve / c_p_map / XYZ / PLY : "parity unpinned" by any
  *                reference output (those blobs are missing from the reference tree);
  *                pinned only against cv2 4.13 + numpy restatements.
+ *   modulation criterion (o3d_check_I_mod_criteria): the reference keeps that branch commented
+ *                out, so no reference output can pin it -- "parity unpinned"; checked against
+ *                a literal numpy transcription on all 2^24 intensity triples.
  *
  * Layout: every image-sized plane here is ROW-MAJOR [H][W] (the reference uses
  * [col][row]; layout does not change any value).  c_p_map is [H*W][2] like the reference.
