@@ -70,6 +70,32 @@ def test_pattern_rows_match_reference_generated_patterns():
     for i in range(5):
         assert np.array_equal(s3.synth_pattern_row(1, 5, 32, i, 720), k["gray_h_col0"][i])
         assert np.array_equal(s3.synth_pattern_row(2, 5, 32, i, 720), k["inv_h_col0"][i])
+    # stale images of earlier 4-step (fw 16) and 5-step (fw 32) runs pin those expressions too
+    assert np.array_equal(s3.synth_pattern_row(0, 4, 16, 3, 1024), k["fringe4_k3_v_row0"])
+    assert np.array_equal(s3.synth_pattern_row(0, 4, 16, 3, 768), k["fringe4_k3_h_col0"])
+    assert np.array_equal(s3.synth_pattern_row(0, 5, 32, 4, 1024), k["fringe5_k4_v_row0"])
+    assert np.array_equal(s3.synth_pattern_row(0, 5, 32, 4, 768), k["fringe5_k4_h_col0"])
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference tree not mounted")
+def test_reference_pattern_images_are_their_profiles():
+    """The device generator expands 1-D profiles: every stored pattern image of the reference is
+    constant along its stripes and equals the profile of its configuration, full frame."""
+    from helpers import read_bmp8
+    g = REF + "Generated_patterns/"
+    cases = [(f"Fringe_patterns/{d}/Pattern_{k}.bmp", 0, 3, 32, k, d) for d in ("Vertical", "Horizontal") for k in range(3)]
+    cases += [(f"Fringe_patterns/{d}/Pattern_3.bmp", 0, 4, 16, 3, d) for d in ("Vertical", "Horizontal")]
+    cases += [(f"Fringe_patterns/{d}/Pattern_4.bmp", 0, 5, 32, 4, d) for d in ("Vertical", "Horizontal")]
+    for d, M in (("Vertical", 6), ("Horizontal", 5)):
+        for j in range(M):
+            cases.append((f"Coded_patterns/Gray_coded/{d}/Pattern_{j}.bmp", 1, M, 32, j, d))
+            cases.append((f"Coded_patterns/Gray_coded/{d}/inverse_Pattern_{j}.bmp", 2, M, 32, j, d))
+    for path, kind, n_or_m, fw, k, d in cases:
+        img = read_bmp8(g + path)
+        length = img.shape[1] if d == "Vertical" else img.shape[0]
+        r = s3.synth_pattern_row(kind, n_or_m, fw, k, length)
+        want = np.broadcast_to(r[None, :] if d == "Vertical" else r[:, None], img.shape)
+        assert np.array_equal(img, want), path
 
 
 def _cal():

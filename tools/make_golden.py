@@ -148,6 +148,12 @@ def main():
     for pre, key in (("", "gray"), ("inverse_", "inv")):
         pk[f"{key}_v_row0"] = np.stack([read_bmp8(gc + f"Vertical/{pre}Pattern_{i}.bmp")[0] for i in range(6)])
         pk[f"{key}_h_col0"] = np.stack([read_bmp8(gc + f"Horizontal/{pre}Pattern_{i}.bmp")[:, 0] for i in range(5)])
+    # Pattern_3 / Pattern_4 are left over from earlier 4-step (fw 16) and 5-step (fw 32) runs on a
+    # 1024x768 projector: they pin the 4- and 5-step expressions (k = 3 and k = 4)
+    pk["fringe4_k3_v_row0"] = read_bmp8(g + "Fringe_patterns/Vertical/Pattern_3.bmp")[0]
+    pk["fringe4_k3_h_col0"] = read_bmp8(g + "Fringe_patterns/Horizontal/Pattern_3.bmp")[:, 0]
+    pk["fringe5_k4_v_row0"] = read_bmp8(g + "Fringe_patterns/Vertical/Pattern_4.bmp")[0]
+    pk["fringe5_k4_h_col0"] = read_bmp8(g + "Fringe_patterns/Horizontal/Pattern_4.bmp")[:, 0]
     np.savez_compressed(os.path.join(OUT, "pattern_kat.npz"), **pk)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
