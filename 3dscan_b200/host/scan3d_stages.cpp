@@ -229,6 +229,31 @@ void save_point_cloud(unsigned cloud_index)
     fprintf(stderr, "Saved %lld data points to %s\n", (long long)n, (g_root + name).c_str());
 }
 
+void generate_pattern()
+{
+    // save_pattern_images (1/pattern_generator.cpp:436-479): Fringe_patterns/{Vertical,Horizontal}/Pattern_k.bmp,
+    // Coded_patterns/Gray_coded/{Vertical,Horizontal}/[inverse_]Pattern_j.bmp -- generated on the GPU
+    ensure_ctx();
+    const size_t pp = (size_t)g_cfg.PW * g_cfg.PH;
+    for (int d = 0; d < 2; d++) {
+        const int M = d == 0 ? g_cfg.M_v : g_cfg.M_h;
+        const char* dir = d == 0 ? "Vertical" : "Horizontal";
+        std::vector<uint8_t> img((size_t)scan3d_pattern_bytes(&g_cfg, d));
+        ck(scan3d_generate_patterns(g_ctx, d, img.data()), "scan3d_generate_patterns");
+        char name[160];
+        auto save = [&](const char* fmt, int idx, size_t plane) {
+            snprintf(name, sizeof(name), fmt, dir, idx);
+            if (scan3d_write_bmp8((g_root + name).c_str(), g_cfg.PW, g_cfg.PH, img.data() + plane * pp) != SCAN3D_OK)
+                die("generate_pattern", scan3d_host_last_error());
+        };
+        for (int k = 0; k < g_cfg.N; k++) save("/Generated_patterns/Fringe_patterns/%s/Pattern_%d.bmp", k, (size_t)k);
+        for (int j = 0; j < M; j++) {
+            save("/Generated_patterns/Coded_patterns/Gray_coded/%s/Pattern_%d.bmp", j, (size_t)(g_cfg.N + j));
+            save("/Generated_patterns/Coded_patterns/Gray_coded/%s/inverse_Pattern_%d.bmp", j, (size_t)(g_cfg.N + M + j));
+        }
+    }
+}
+
 void reconstruct_scan(unsigned cloud_index)
 {
     ensure_ctx();

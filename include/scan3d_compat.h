@@ -49,6 +49,8 @@ void scan3d_compat_shutdown();
 scan3d_ctx *scan3d_compat_ctx();
 
 /* ---- PROJECT_GLOBAL/intermodule_dependencies.h ---- */
+void generate_pattern();                      /* 1/pattern_generator.cpp:513: writes <root>/Generated_patterns/... (:436-479;
+                                                 the plain binary-coded set, which no later stage reads, is not written) */
 void load_matrices();                         /* 6/system_calibration.cpp:1526 */
 void compute_wrapped_phase(int pattern_type); /* 3/wrapped_phase.cpp:402 */
 void unwrap_phase(int pattern_type);          /* 4/phase_unwrap.cpp:367 (declared int, defined void) */

@@ -68,6 +68,20 @@ def test_reference_call_sequence(tmp_path):
     g("selected_region", C.c_void_p).value = sel.ctypes.data
 
     # ---- the reference's main() sequence ----
+    for sub in ("Fringe_patterns/Vertical", "Fringe_patterns/Horizontal", "Coded_patterns/Gray_coded/Vertical",
+                "Coded_patterns/Gray_coded/Horizontal"):
+        os.makedirs(f"{root}/Generated_patterns/{sub}", exist_ok=True)
+    getattr(L, "_Z16generate_patternv")()                      # stage 1 (m_tech_project_console.cpp: generate_pattern())
+    for dname, M, length, axis in (("Vertical", Mv, PW, 0), ("Horizontal", Mh, PH, 1)):
+        for k in range(N):
+            img = s3.read_bmp8(f"{root}/Generated_patterns/Fringe_patterns/{dname}/Pattern_{k}.bmp")
+            r = s3.synth_pattern_row(0, N, fw, k, length)
+            assert img.shape == (PH, PW) and np.array_equal(img, np.broadcast_to(r[None, :] if axis == 0 else r[:, None], (PH, PW)))
+        for j in range(M):
+            for kind, pre in ((1, ""), (2, "inverse_")):
+                img = s3.read_bmp8(f"{root}/Generated_patterns/Coded_patterns/Gray_coded/{dname}/{pre}Pattern_{j}.bmp")
+                r = s3.synth_pattern_row(kind, M, fw, j, length)
+                assert np.array_equal(img, np.broadcast_to(r[None, :] if axis == 0 else r[:, None], (PH, PW)))
     getattr(L, "_Z13load_matricesv")()
     cwp = getattr(L, "_Z21compute_wrapped_phasei"); cwp.argtypes = [C.c_int]
     uwp = getattr(L, "_Z12unwrap_phasei"); uwp.argtypes = [C.c_int]
@@ -103,4 +117,6 @@ def test_reference_call_sequence(tmp_path):
     rows = np.loadtxt(body.splitlines())
     assert rows.shape == (ref.count, 6)
     assert np.array_equal(rows[:, :3].astype(np.float32), ref.pts)
+    pcd = open(f"{root}/Point_cloud/point_cloud_0.pcd").read().splitlines()      # the reference writes both files
+    assert pcd[2] == "FIELDS x y z rgb" and pcd[9] == f"POINTS {ref.count}" and len(pcd) == 11 + ref.count
     getattr(L, "_Z22scan3d_compat_shutdownv")()

@@ -331,6 +331,19 @@ def test_device_pattern_generator(N, Mv, Mh, fw, PW, PH):
     ctx.close()
 
 
+def test_device_pattern_generator_4_and_5_step_reference_images():
+    """The reference tree also keeps one 4-step (k=3, fw 16) and one 5-step (k=4, fw 32) image of a
+    1024x768 projector: the device generator reproduces their first row / column."""
+    import os
+    from helpers import GOLDEN
+    k = np.load(os.path.join(GOLDEN, "pattern_kat.npz"))
+    for N, fw, idx, key in ((4, 16, 3, "fringe4_k3"), (5, 32, 4, "fringe5_k4")):
+        ctx = s3.Scan3D(s3.make_config(64, 16, 1024, 768, N, 6, 5, fw, fw, 2), 0, None)
+        assert np.array_equal(ctx.generate_patterns(0)[idx, 0], k[key + "_v_row0"])
+        assert np.array_equal(ctx.generate_patterns(1)[idx, :, 0], k[key + "_h_col0"])
+        ctx.close()
+
+
 def test_ply_writer(tmp_path):
     W, H, PW, PH = 256, 64, 512, 512
     cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
