@@ -138,6 +138,15 @@ def cuda_lib():
     L.scan3d_pattern_bytes.restype = i64
     L.scan3d_generate_patterns.argtypes = [vp, i32, vp]
     L.scan3d_generate_patterns_dev.argtypes = [vp, i32, vp]
+    f32 = C.c_float
+    L.scan3d_undistort_frames.argtypes = [vp, i32, vp, i32, vp]
+    L.scan3d_undistort_frames_dev.argtypes = [vp, i32, vp, i32, vp]
+    L.scan3d_get_undistort_map.argtypes = [vp, i32, vp, vp]
+    L.scan3d_roi_fill.argtypes = [vp, vp, vp, vp]
+    L.scan3d_roi_fill_dev.argtypes = [vp, vp, vp, vp]
+    L.scan3d_register_points.argtypes = [vp, vp, vp, i64, f32, f32, f32, f32]
+    L.scan3d_register_points_dev.argtypes = [vp, vp, vp, i64, f32, f32, f32, f32]
+    L.scan3d_register_rotation.argtypes = [f32, vp]
     L.scan3d_peer_alloc.argtypes = [i32, i64, C.POINTER(vp), C.c_char_p]
     L.scan3d_peer_free.argtypes = [i32, vp]
     L.scan3d_peer_open.argtypes = [i32, C.c_char_p, C.POINTER(vp)]
@@ -403,6 +412,57 @@ class Scan3D:
     def generate_patterns_dev(self, direction, dev_ptr):
         self._ck(self.L.scan3d_generate_patterns_dev(self.h, int(direction), C.c_void_p(dev_ptr)))
 
+    # -- either side of the path
+    def _kind_shape(self, device_kind):
+        return (self.cfg.H, self.cfg.W) if device_kind == 0 else (self.cfg.PH, self.cfg.PW)
+
+    def undistort_frames(self, frames, device_kind=0):
+        """cvUndistort2 of u8 frames [n][H][W] (camera, device_kind 0) or [n][PH][PW] (projector, 1)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        H, W = self._kind_shape(device_kind)
+        if frames.ndim != 3 or frames.shape[1:] != (H, W):
+            raise Scan3DError(f"frames must be [n][{H}][{W}] u8, got {frames.shape}")
+        out = np.empty_like(frames)
+        if frames.shape[0] == 0:
+            return out
+        self._ck(self.L.scan3d_undistort_frames(self.h, int(device_kind), _ptr(frames), frames.shape[0], _ptr(out)))
+        return out
+
+    def undistort_frames_dev(self, src_ptr, n_frames, dst_ptr, device_kind=0):
+        self._ck(self.L.scan3d_undistort_frames_dev(self.h, int(device_kind), C.c_void_p(src_ptr), int(n_frames),
+                                                    C.c_void_p(dst_ptr)))
+
+    def undistort_map(self, device_kind=0):
+        """cv::undistort's fixed-point map: (xy int16 [H][W][2], frac uint16 [H][W])."""
+        H, W = self._kind_shape(device_kind)
+        xy = np.empty((H, W, 2), np.int16)
+        fr = np.empty((H, W), np.uint16)
+        self._ck(self.L.scan3d_get_undistort_map(self.h, int(device_kind), _ptr(xy), _ptr(fr)))
+        return xy, fr
+
+    def roi_fill(self, outline):
+        """image_scissor's fill: (selected_region u8 [H_total][W], outline image after the in-place fill)."""
+        outline = np.ascontiguousarray(outline, np.uint8)
+        if outline.shape != (self.cfg.H_total, self.cfg.W):
+            raise Scan3DError(f"outline must be [{self.cfg.H_total}][{self.cfg.W}] u8, got {outline.shape}")
+        roi = np.empty_like(outline)
+        filled = np.empty_like(outline)
+        self._ck(self.L.scan3d_roi_fill(self.h, _ptr(outline), _ptr(roi), _ptr(filled)))
+        return roi, filled
+
+    def register_points(self, xyz, theta_deg, tx, ty, tz):
+        """register_point_clouds' transform of one cloud (f32 [n][3]) captured at turntable angle theta_deg."""
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        out = np.empty_like(xyz)
+        if xyz.shape[0] == 0:
+            return out
+        self._ck(self.L.scan3d_register_points(self.h, _ptr(xyz), _ptr(out), xyz.shape[0], theta_deg, tx, ty, tz))
+        return out
+
+    def register_points_dev(self, src_ptr, dst_ptr, n, theta_deg, tx, ty, tz):
+        self._ck(self.L.scan3d_register_points_dev(self.h, C.c_void_p(src_ptr), C.c_void_p(dst_ptr), int(n),
+                                                   theta_deg, tx, ty, tz))
+
     def write_ply(self, path, binary=False):
         self._ck(self.L.scan3d_write_ply(self.h, path.encode(), 1 if binary else 0))
 
@@ -427,6 +487,13 @@ class Scan3D:
         out = np.empty(y.shape, np.float32)
         self._ck(self.L.scan3d_debug_atan2(self.h, _ptr(y), _ptr(x), _ptr(out), y.size, mode))
         return out
+
+
+def register_rotation(theta_deg):
+    """The 4x4 float matrix register_point_clouds builds for turntable angle theta_deg (its Pi = 22/7)."""
+    R = np.empty(16, np.float32)
+    cuda_lib().scan3d_register_rotation(theta_deg, _ptr(R))
+    return R.reshape(4, 4)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -26,7 +26,8 @@ NVCC_FLAGS = [
 # they cost ~2 % of the kernel's instructions, so the default build leaves them out.
 if os.environ.get("SCAN3D_BUILD_TRACE") == "1":
     NVCC_FLAGS.append("-DS3D_TRACE=1")
-CU_SOURCES = ["scan3d_api.cu", "scan3d_stage_kernels.cu", "scan3d_fused_kernel.cu", "scan3d_fused_kernel7.cu"]
+CU_SOURCES = ["scan3d_api.cu", "scan3d_stage_kernels.cu", "scan3d_fused_kernel.cu", "scan3d_fused_kernel7.cu",
+              "scan3d_aux_kernels.cu", "scan3d_aux_api.cu"]
 HOST_SOURCES = ["scan3d_io.cpp", "scan3d_synth.cpp"]
 COMPAT_SOURCES = ["scan3d_stages.cpp"]
 

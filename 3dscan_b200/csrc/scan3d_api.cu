@@ -204,7 +204,8 @@ void scan3d_destroy(scan3d_ctx* ctx)
     void* ptrs[] = {ctx->cam_lut, ctx->proj_lut, ctx->atan_tab, ctx->nstep_w, ctx->wrapped[0], ctx->wrapped[1],
                     ctx->unwrapped[0], ctx->unwrapped[1], ctx->code[0], ctx->code[1], ctx->mask[0],
                     ctx->mask[1], ctx->valid, ctx->cpmap, ctx->xyz, ctx->pts, ctx->pix, ctx->rgb,
-                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff, ctx->pattern_profiles};
+                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff, ctx->pattern_profiles,
+                    ctx->undist_xy[0], ctx->undist_xy[1], ctx->undist_frac[0], ctx->undist_frac[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -256,6 +257,10 @@ int scan3d_set_calibration(scan3d_ctx* ctx, const scan3d_calib* cal)
     }
     if (ctx->cam_lut) { cudaFree(ctx->cam_lut); ctx->cam_lut = nullptr; }
     if (ctx->proj_lut) { cudaFree(ctx->proj_lut); ctx->proj_lut = nullptr; }
+    for (int k = 0; k < 2; k++) {   // cv::undistort maps belong to the previous calibration
+        if (ctx->undist_xy[k]) { cudaFree(ctx->undist_xy[k]); ctx->undist_xy[k] = nullptr; }
+        if (ctx->undist_frac[k]) { cudaFree(ctx->undist_frac[k]); ctx->undist_frac[k] = nullptr; }
+    }
     if (ctx->cfg.dirs == 2) {
         if (d.cam_distorted) {
             CK(dalloc(&ctx->cam_lut, npix(ctx)));

@@ -32,6 +32,8 @@ struct scan3d_ctx {
     bool have_profiles[2] = {false, false};
     uint8_t* roi_eff = nullptr;    // SCAN3D_FLAG_MODULATION_MASK: ROI && modulation criterion of the current direction
     double* nstep_w = nullptr;     // sin[64] then cos[64] (generic-N extension)
+    short2* undist_xy[2] = {nullptr, nullptr};     // cv::undistort's fixed-point map of the camera [0] / projector [1]
+    uint16_t* undist_frac[2] = {nullptr, nullptr}; // (scan3d_undistort_frames; built on first use per calibration)
 
     // planes (row-major [H][W])
     float* wrapped[2] = {nullptr, nullptr};
@@ -139,6 +141,15 @@ cudaError_t launch_fused(const scan3d_config& c, const FusedArgs& a, const Devic
 bool fused7_supported(const scan3d_config& c);
 cudaError_t launch_fused7(const scan3d_config& c, const FusedArgs& a, const DeviceCalib& cal,
                           int sm_count, cudaStream_t st);
+
+// ---- either side of the path (scan3d_aux_kernels.cu) ----
+cudaError_t launch_undistort_map(const double K[9], const double d[5], int W, int H, short2* map_xy, uint16_t* map_frac,
+                                 cudaStream_t st);
+cudaError_t launch_remap_frames(const uint8_t* src, uint8_t* dst, const short2* map_xy, const uint16_t* map_frac, int W,
+                                int H, int n_frames, int sm_count, cudaStream_t st);
+cudaError_t launch_roi_fill(const uint8_t* outline, int W, int H, uint8_t* roi, uint8_t* filled, cudaStream_t st);
+cudaError_t launch_register_points(const float* src, float* dst, long long n, const float R[16], float tx, float ty,
+                                   float tz, int sm_count, cudaStream_t st);
 
 // ---- debug / self-test ----
 cudaError_t launch_debug_atan2(const double* y, const double* x, float* out, int n, int mode,

@@ -231,4 +231,92 @@ int scan3d_write_pcd_points(const char* path, const float* xyz, const uint8_t* r
     return fclose(f) == 0 ? SCAN3D_OK : fail(SCAN3D_ERR_IO, "short write");
 }
 
+// pcl::io::loadPLYFile's job in register_point_clouds (9/register_point_clouds.cpp:66,87): vertex
+// positions and colours of a PLY written by scan3d_write_ply_points / PCL ("x y z" floats or doubles,
+// optional uchar "red green blue"), ascii or binary_little_endian.  Other vertex properties are skipped.
+int scan3d_read_ply_points(const char* path, float* xyz, uint8_t* rgb, int64_t capacity, int64_t* n_out)
+{
+    if (!path || !n_out) return fail(SCAN3D_ERR_ARG, "bad argument");
+    std::vector<uint8_t> b;
+    if (!slurp(path, b)) return fail(SCAN3D_ERR_IO, std::string("cannot read ") + path);
+    b.push_back(0);   // strtod below needs a terminator
+    struct Prop { std::string type, name; int size; };
+    std::vector<Prop> props;
+    size_t pos = 0;
+    bool in_vertex = false, binary = false, seen_end = false;
+    long long count = -1;
+    auto type_size = [](const std::string& t) {
+        if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+        if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+        if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+        if (t == "double" || t == "float64") return 8;
+        return 0;
+    };
+    while (pos < b.size()) {
+        size_t e = pos;
+        while (e < b.size() && b[e] != '\n') e++;
+        std::string line((const char*)&b[pos], e - pos);
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        pos = e + 1;
+        char a[64] = {0}, c[64] = {0}, d[64] = {0};
+        const int nf = sscanf(line.c_str(), "%63s %63s %63s", a, c, d);
+        if (nf >= 1 && !strcmp(a, "end_header")) { seen_end = true; break; }
+        if (nf >= 2 && !strcmp(a, "format")) {
+            if (!strcmp(c, "binary_little_endian")) binary = true;
+            else if (strcmp(c, "ascii")) return fail(SCAN3D_ERR_IO, std::string("unsupported PLY format in ") + path);
+        } else if (nf >= 3 && !strcmp(a, "element")) {
+            in_vertex = !strcmp(c, "vertex");
+            if (in_vertex) count = atoll(d);
+            else if (count < 0) return fail(SCAN3D_ERR_IO, "PLY: an element precedes the vertices");
+        } else if (nf >= 3 && !strcmp(a, "property") && in_vertex) {
+            if (!strcmp(c, "list")) return fail(SCAN3D_ERR_IO, "PLY: list property on vertices");
+            const int sz = type_size(c);
+            if (!sz) return fail(SCAN3D_ERR_IO, std::string("PLY: unknown property type ") + c);
+            props.push_back({c, d, sz});
+        }
+    }
+    if (!seen_end || count < 0) return fail(SCAN3D_ERR_IO, std::string("not a PLY vertex file: ") + path);
+    int ix = -1, iy = -1, iz = -1, ir = -1, ig = -1, ib = -1;
+    for (int k = 0; k < (int)props.size(); k++) {
+        const std::string& n = props[k].name;
+        if (n == "x") ix = k; else if (n == "y") iy = k; else if (n == "z") iz = k;
+        else if (n == "red" || n == "r") ir = k; else if (n == "green" || n == "g") ig = k;
+        else if (n == "blue" || n == "b") ib = k;
+    }
+    if (ix < 0 || iy < 0 || iz < 0) return fail(SCAN3D_ERR_IO, "PLY: no x/y/z properties");
+    *n_out = count;
+    if (!xyz) return SCAN3D_OK;   // size query
+    if (count > capacity) return fail(SCAN3D_ERR_ARG, "PLY: more vertices than the buffer holds");
+    std::vector<double> v(props.size());
+    for (long long i = 0; i < count; i++) {
+        for (size_t k = 0; k < props.size(); k++) {
+            if (binary) {
+                if (pos + props[k].size > b.size()) return fail(SCAN3D_ERR_IO, "PLY: truncated");
+                const uint8_t* q = &b[pos];
+                const std::string& t = props[k].type;
+                if (t == "float" || t == "float32") { float f; memcpy(&f, q, 4); v[k] = f; }
+                else if (t == "double" || t == "float64") { double f; memcpy(&f, q, 8); v[k] = f; }
+                else if (props[k].size == 1) v[k] = (t[0] == 'u') ? (double)q[0] : (double)(int8_t)q[0];
+                else if (props[k].size == 2) v[k] = (t[0] == 'u') ? (double)rd16(q) : (double)(int16_t)rd16(q);
+                else v[k] = (t[0] == 'u') ? (double)rd32(q) : (double)(int32_t)rd32(q);
+                pos += props[k].size;
+            } else {
+                while (pos < b.size() && (b[pos] == ' ' || b[pos] == '\n' || b[pos] == '\r' || b[pos] == '\t')) pos++;
+                if (pos >= b.size()) return fail(SCAN3D_ERR_IO, "PLY: truncated");
+                char* endp = nullptr;
+                v[k] = strtod((const char*)&b[pos], &endp);
+                if (endp == (const char*)&b[pos]) return fail(SCAN3D_ERR_IO, "PLY: bad number");
+                pos = (size_t)(endp - (const char*)b.data());
+            }
+        }
+        xyz[3 * i] = (float)v[ix]; xyz[3 * i + 1] = (float)v[iy]; xyz[3 * i + 2] = (float)v[iz];
+        if (rgb) {
+            rgb[3 * i] = ir >= 0 ? (uint8_t)v[ir] : 0;
+            rgb[3 * i + 1] = ig >= 0 ? (uint8_t)v[ig] : 0;
+            rgb[3 * i + 2] = ib >= 0 ? (uint8_t)v[ib] : 0;
+        }
+    }
+    return SCAN3D_OK;
+}
+
 }  // extern "C"

@@ -254,6 +254,60 @@ void generate_pattern()
     }
 }
 
+void register_point_clouds(unsigned num_point_clouds, float tx, float ty, float tz, float rot_step)
+{
+    ensure_ctx();
+    // first pass: total size (9/register_point_clouds.cpp:63-68)
+    std::vector<int64_t> sizes(num_point_clouds, 0);
+    int64_t total = 0;
+    char name[64];
+    for (unsigned i = 0; i < num_point_clouds; i++) {
+        snprintf(name, sizeof(name), "/Point_cloud/point_cloud_%u.ply", i);
+        if (scan3d_read_ply_points((g_root + name).c_str(), nullptr, nullptr, 0, &sizes[i]) != SCAN3D_OK)
+            die("register_point_clouds", scan3d_host_last_error());
+        total += sizes[i];
+    }
+    fprintf(stderr, "\nregistred cloud width:%lld", (long long)total);
+    std::vector<float> xyz((size_t)total * 3);
+    std::vector<uint8_t> rgb((size_t)total * 3);
+    float theta = 0.0f;                       // :78
+    int64_t prev_last_point_id = 0;
+    for (unsigned i = 0; i < num_point_clouds; i++) {
+        snprintf(name, sizeof(name), "/Point_cloud/point_cloud_%u.ply", i);
+        float* dst = xyz.data() + 3 * prev_last_point_id;
+        int64_t n = 0;
+        if (scan3d_read_ply_points((g_root + name).c_str(), dst, rgb.data() + 3 * prev_last_point_id, sizes[i], &n) != SCAN3D_OK)
+            die("register_point_clouds", scan3d_host_last_error());
+        ck(scan3d_register_points(g_ctx, dst, dst, n, theta, tx, ty, tz), "scan3d_register_points");   // :93-137
+        fprintf(stderr, "\nRotating by :%f", theta);
+        theta += rot_step;                    // :141
+        prev_last_point_id += n;
+    }
+    if (scan3d_write_ply_points((g_root + "/Point_cloud/registered_point_cloud.ply").c_str(), xyz.data(), rgb.data(), total, 0) != SCAN3D_OK)
+        die("register_point_clouds", scan3d_host_last_error());
+}
+
+void image_scissor_fill(const unsigned char* internal_image)
+{
+    ensure_ctx();
+    std::vector<uint8_t> roi(npix()), filled(npix());
+    ck(scan3d_roi_fill(g_ctx, internal_image, roi.data(), filled.data()), "scan3d_roi_fill");
+    static std::vector<int> region;   // m_tech_project_console.cpp:183 allocates (and leaks) a new plane per call
+    region.assign(npix(), 0);
+    selected_region = region.data();
+    const int W = Camera_imagewidth, H = Camera_imageheight;
+    for (int r = 0; r < H; r++)
+        for (int c = 0; c < W; c++) selected_region[(size_t)c * H + r] = roi[(size_t)r * W + c];
+    if (scan3d_write_bmp8((g_root + "/i1.bmp").c_str(), W, H, filled.data()) != SCAN3D_OK)
+        die("image_scissor_fill", scan3d_host_last_error());
+}
+
+void undistort_capture(const unsigned char* cap, unsigned char* undist_cap, int device_kind)
+{
+    ensure_ctx();
+    ck(scan3d_undistort_frames(g_ctx, device_kind, cap, 1, undist_cap), "scan3d_undistort_frames");
+}
+
 void reconstruct_scan(unsigned cloud_index)
 {
     ensure_ctx();

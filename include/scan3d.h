@@ -21,6 +21,15 @@
  *   load_matrices() / read_parameters()             scan3d_set_calibration
  *        6/system_calibration.cpp:1526, 7/triangulation.cpp:149
  *   (all five calls above, one scan)                scan3d_reconstruct[_dev]
+ *   either side of the path:
+ *   cvUndistort2 in the capture loop                scan3d_undistort_frames[_dev]
+ *        2/project_pattern.cpp:220,234,372-427
+ *   image_scissor()'s region fill                   scan3d_roi_fill[_dev]
+ *        M_tech_project_console/m_tech_project_console.cpp:186-229
+ *   void register_point_clouds(...)                 scan3d_register_points[_dev]
+ *        9/register_point_clouds.cpp:22
+ *   void generate_pattern()                         scan3d_generate_patterns[_dev]
+ *        1/pattern_generator.cpp:513
  *
  * Data contract
  *   - Every image-sized plane is ROW-MAJOR [H][W] (the reference's globals are [col][row];
@@ -210,6 +219,40 @@ int scan3d_write_ply(scan3d_ctx *ctx, const char *path, int binary);
 /* save_point_cloud()'s pcl::io::savePCDFileASCII equivalent (8/save_point_cloud.cpp:212): PCD v0.7,
  * "x y z rgb" per point, 8 significant digits, rgb packed into a float as PCL 1.6 does. */
 int scan3d_write_pcd(scan3d_ctx *ctx, const char *path);
+
+/* ---- either side of the path --------------------------------------- */
+/* cvUndistort2(cap, undist_cap, K, d) as the capture loop applies it to every captured camera frame
+ * and every projected pattern (2/project_pattern.cpp:220,234,372-427): OpenCV 2.4's cv::undistort,
+ * i.e. the 5-fractional-bit map of initUndistortRectifyMap (built in stripes of max(1, 4096/W) rows)
+ * and cv::remap's fixed-point bilinear blend with a constant 0 border -- bit-identical to OpenCV.
+ * device_kind 0 = camera (Kc, dc; frames [n][H][W]), 1 = projector (Kp, dp; frames [n][PH][PW]).
+ * The map is built on the GPU once per calibration and reused for every frame (the reference
+ * rebuilds it per image).  src and dst must not overlap.  Needs scan3d_set_calibration. */
+int scan3d_undistort_frames(scan3d_ctx *ctx, int device_kind, const uint8_t *src_host, int n_frames,
+                            uint8_t *dst_host);
+int scan3d_undistort_frames_dev(scan3d_ctx *ctx, int device_kind, const uint8_t *src_dev, int n_frames,
+                                uint8_t *dst_dev);
+/* that map, for diffing against cv::initUndistortRectifyMap(CV_16SC2): xy = int16 [H][W][2] (source
+ * column, row), frac = uint16 [H][W] (fy*32 + fx).  Either destination may be NULL. */
+int scan3d_get_undistort_map(scan3d_ctx *ctx, int device_kind, int16_t *xy_host, uint16_t *frac_host);
+
+/* image_scissor()'s scan-line fill (M_tech_project_console/m_tech_project_console.cpp:186-229): from
+ * the lasso outline the user drew (internal_image, non-zero = outline, u8 [H_total][W]) to
+ * selected_region (u8 [H_total][W], 1 = selected): every zero pixel strictly between the first and the
+ * last outline pixel of its row.  filled (optional) receives the outline image after the reference's
+ * in-place fill -- what it saves as i1.jpg; filled_dev may equal outline_dev. */
+int scan3d_roi_fill(scan3d_ctx *ctx, const uint8_t *outline_host, uint8_t *roi_host, uint8_t *filled_host);
+int scan3d_roi_fill_dev(scan3d_ctx *ctx, const uint8_t *outline_dev, uint8_t *roi_dev, uint8_t *filled_dev);
+
+/* register_point_clouds()'s per-cloud transform (9/register_point_clouds.cpp:93-137): rotate the
+ * cloud captured at turntable angle theta_deg about the Y axis through the pivot (tx,ty,tz), in the
+ * reference's float arithmetic (its Pi = 22/7 included).  xyz = f32 [n][3]; dst may equal src. */
+int scan3d_register_points(scan3d_ctx *ctx, const float *src_host, float *dst_host, int64_t n,
+                           float theta_deg, float tx, float ty, float tz);
+int scan3d_register_points_dev(scan3d_ctx *ctx, const float *src_dev, float *dst_dev, int64_t n,
+                               float theta_deg, float tx, float ty, float tz);
+/* the 4x4 float matrix R it uses (row-major), for diffing */
+int scan3d_register_rotation(float theta_deg, float R[16]);
 
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t scan3d_launch_count(const scan3d_ctx *ctx);

@@ -57,6 +57,17 @@ void unwrap_phase(int pattern_type);          /* 4/phase_unwrap.cpp:367 (declare
 void compute_c_p_map();                       /* 5/compute_correspondance.cpp:630 */
 void triangulate();                           /* 7/triangulation.cpp:1444 */
 void save_point_cloud(unsigned cloud_index);  /* 8/save_point_cloud.cpp:26 */
+/* 9/register_point_clouds.cpp:22 (called at m_tech_project_console.cpp:408): reads
+ * <root>/Point_cloud/point_cloud_<i>.ply for i < num_point_clouds, rotates cloud i by i*rot_step degrees
+ * about Y through (tx,ty,tz) on the GPU, writes <root>/Point_cloud/registered_point_cloud.ply */
+void register_point_clouds(unsigned num_point_clouds, float tx, float ty, float tz, float rot_step);
+/* the non-interactive half of image_scissor() (m_tech_project_console.cpp:183-231): from the lasso
+ * outline (internal_image, row-major u8 [Camera_imageheight][Camera_imagewidth], non-zero = drawn) to
+ * the selected_region global; saves the filled outline as <root>/i1.bmp (the reference writes i1.jpg) */
+void image_scissor_fill(const unsigned char *internal_image);
+/* cvUndistort2(cap, undist_cap, K, d) of the capture loop (2/project_pattern.cpp:220,234,372-427) for one
+ * 8-bit image: device_kind 0 = camera frame, 1 = projector pattern; needs load_matrices() */
+void undistort_capture(const unsigned char *cap, unsigned char *undist_cap, int device_kind);
 /* the whole sequence above in one fused pass (no reference counterpart) */
 void reconstruct_scan(unsigned cloud_index);
 

@@ -11,6 +11,7 @@
  *   scan3d_synth_pattern_row                      1/pattern_generator.cpp:56-197,291-397,490-507
  *   scan3d_write_ply_points                       pcl::io::savePLYFile at 8/save_point_cloud.cpp:217
  *   scan3d_write_pcd_points                       pcl::io::savePCDFileASCII at 8/save_point_cloud.cpp:212
+ *   scan3d_read_ply_points                        pcl::io::loadPLYFile at 9/register_point_clouds.cpp:66,87
  */
 #ifndef SCAN3D_HOST_H
 #define SCAN3D_HOST_H
@@ -37,6 +38,10 @@ int scan3d_load_captured_set(const char *root, const scan3d_config *cfg, uint8_t
 int scan3d_write_ply_points(const char *path, const float *xyz, const uint8_t *rgb, int64_t n, int binary);
 /* ASCII PCD v0.7, FIELDS x y z rgb (rgb packed into a float as PCL 1.6's PointXYZRGB does) */
 int scan3d_write_pcd_points(const char *path, const float *xyz, const uint8_t *rgb, int64_t n);
+/* pcl::io::loadPLYFile's job in register_point_clouds (9/register_point_clouds.cpp:66,87): positions
+ * (and uchar red/green/blue when present) of an ascii or binary_little_endian PLY.  xyz = NULL only
+ * queries *n_out. */
+int scan3d_read_ply_points(const char *path, float *xyz, uint8_t *rgb, int64_t capacity, int64_t *n_out);
 const char *scan3d_host_last_error(void);
 
 /* ---- synthetic captures ---- */

@@ -15,10 +15,9 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libscan3d_oracle.so")
-    src = os.path.join(_HERE, "scan3d_oracle.c")
-    hdr = os.path.join(_HERE, "scan3d_oracle.h")
+    deps = [os.path.join(_HERE, f) for f in ("scan3d_oracle.c", "scan3d_oracle_f4.c", "scan3d_oracle.h")]
     stale = (not os.path.exists(so)) or any(
-        os.path.getmtime(f) > os.path.getmtime(so) for f in (src, hdr))
+        os.path.getmtime(f) > os.path.getmtime(so) for f in deps)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return so
@@ -266,3 +265,44 @@ def reconstruct(cfg, cal, fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi,
         r.pts = r.pts[:r.count]
         r.pix = r.pix[:r.count]
     return r
+
+
+# ---- either side of the path (scan3d_oracle_f4.c) -------------------------------------------
+
+def undistort_map(K, d, W, H):
+    """cv::undistort's fixed-point map: (xy int16 [H][W][2], frac uint16 [H][W])."""
+    mxy = np.empty((H, W, 2), np.int16)
+    mf = np.empty((H, W), np.uint16)
+    lib().o3d_undistort_map(_p(_d(K, 9)), _p(_d(d, 5)), W, H, _p(mxy), _p(mf))
+    return mxy, mf
+
+
+def undistort_frames(frames, K, d):
+    """cvUndistort2 on [n][H][W] u8 frames."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, H, W = frames.shape
+    out = np.empty_like(frames)
+    lib().o3d_undistort_frames(_p(frames), n, W, H, _p(_d(K, 9)), _p(_d(d, 5)), _p(out))
+    return out
+
+
+def roi_fill(outline):
+    """image_scissor's fill: returns (roi u8 [H][W], outline after the in-place fill)."""
+    o = np.ascontiguousarray(outline, np.uint8).copy()
+    H, W = o.shape
+    roi = np.empty((H, W), np.uint8)
+    lib().o3d_roi_fill(_p(o), W, H, _p(roi))
+    return roi, o
+
+
+def register_rotation(theta_deg):
+    R = np.empty(16, np.float32)
+    lib().o3d_register_rotation(C.c_float(theta_deg), _p(R))
+    return R.reshape(4, 4)
+
+
+def register_points(xyz, theta_deg, tx, ty, tz):
+    xyz = np.ascontiguousarray(xyz, np.float32).copy()
+    lib().o3d_register_points(_p(xyz), C.c_int64(xyz.shape[0]), C.c_float(theta_deg), C.c_float(tx),
+                              C.c_float(ty), C.c_float(tz))
+    return xyz

@@ -163,6 +163,21 @@ void o3d_reconstruct_ex(const o3d_config *cfg, const o3d_calib *cal, const uint8
                         const uint8_t *gray_h, const uint8_t *inv_h, const uint8_t *roi,
                         int modulation, o3d_outputs *out, int threads);
 
+/* ---- either side of the path (scan3d_oracle_f4.c) ---- */
+/* cvUndistort2 (2/project_pattern.cpp:220 ...): fixed-point map of cv::undistort, the bilinear
+ * remap, and both applied to n_frames 8-bit images [n][H][W]. */
+void o3d_undistort_map(const double K[9], const double d[5], int W, int H, int16_t *map_xy,
+                       uint16_t *map_frac);
+void o3d_remap_bilinear(const uint8_t *src, int W, int H, const int16_t *map_xy,
+                        const uint16_t *map_frac, uint8_t *dst);
+void o3d_undistort_frames(const uint8_t *src, int n_frames, int W, int H, const double K[9],
+                          const double d[5], uint8_t *dst);
+/* image_scissor's scan-line fill (m_tech_project_console.cpp:186-229); outline is modified in place. */
+void o3d_roi_fill(uint8_t *outline, int W, int H, uint8_t *roi);
+/* register_point_clouds' per-cloud transform (9/register_point_clouds.cpp:92-127), in place. */
+void o3d_register_rotation(float theta_deg, float R[16]);
+void o3d_register_points(float *xyz, int64_t n, float theta_deg, float tx, float ty, float tz);
+
 int o3d_max_threads(void);
 
 #ifdef __cplusplus

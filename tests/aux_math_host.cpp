@@ -1,0 +1,56 @@
+// Host build of 3dscan_b200/common/scan3d_aux_math.h (the very expressions the CUDA kernels of
+// scan3d_aux_kernels.cu evaluate), so that the CPU test suite can compare them with the oracle
+// without a GPU.  Built by tests/test_aux_math_host.py with g++ -O2 -ffp-contract=off.
+#include <stddef.h>
+
+#include "../3dscan_b200/common/scan3d_aux_math.h"
+
+extern "C" {
+
+void s3a_host_undistort_map(const double* K, const double* d, int W, int H, int16_t* xy, uint16_t* frac)
+{
+    for (int row = 0; row < H; row++)   // k_undistort_map: one thread per row
+        s3a::undistort_map_row(K, d, W, H, row, xy + (size_t)row * W * 2, frac + (size_t)row * W);
+}
+
+static inline int tap(const uint8_t* src, int W, int H, int x, int y)
+{
+    return ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) ? (int)src[(size_t)y * W + x] : 0;
+}
+
+void s3a_host_remap(const uint8_t* src, int W, int H, const int16_t* xy, const uint16_t* frac, uint8_t* dst)
+{
+    for (size_t p = 0; p < (size_t)W * H; p++) {   // k_remap_frames: one thread per pixel (group)
+        const int x = xy[2 * p], y = xy[2 * p + 1];
+        dst[p] = s3a::bilinear_u8(tap(src, W, H, x, y), tap(src, W, H, x + 1, y), tap(src, W, H, x, y + 1),
+                                  tap(src, W, H, x + 1, y + 1), frac[p]);
+    }
+}
+
+void s3a_host_register_rotation(float theta_deg, float* R) { s3a::register_rotation(theta_deg, R); }
+
+void s3a_host_register_points(float* xyz, long long n, float theta_deg, float tx, float ty, float tz)
+{
+    float R[16];
+    s3a::register_rotation(theta_deg, R);
+    for (long long k = 0; k < n; k++) s3a::register_point(R, tx, ty, tz, xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]);
+}
+
+void s3a_host_roi_fill(const uint8_t* outline, int W, int H, uint8_t* roi, uint8_t* filled)
+{
+    for (int row = 0; row < H; row++) {   // k_roi_fill: first / last outline pixel of the row, then the closed form
+        const uint8_t* o = outline + (size_t)row * W;
+        int first = 0x7fffffff, last = -1;
+        for (int c = 0; c < W; c++)
+            if (o[c] != 0) {
+                if (c < first) first = c;
+                if (c > last) last = c;
+            }
+        for (int c = 0; c < W; c++) {
+            const bool in = o[c] == 0 && c > first && c < last;
+            roi[(size_t)row * W + c] = in ? 1 : 0;
+            if (filled) filled[(size_t)row * W + c] = in ? 255 : o[c];
+        }
+    }
+}
+}

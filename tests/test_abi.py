@@ -184,3 +184,44 @@ def test_new_entry_points_reject_bad_arguments_without_a_gpu():
     p = C.c_void_p()
     assert L.scan3d_peer_alloc(0, 0, C.byref(p), C.create_string_buffer(64)) != 0     # zero bytes
     assert L.scan3d_peer_open(0, None, C.byref(p)) != 0
+
+
+def test_ply_reader_round_trip(tmp_path):
+    """scan3d_read_ply_points (pcl::io::loadPLYFile's job in 9/register_point_clouds.cpp:66,87) reads back what
+    scan3d_write_ply_points wrote, ascii and binary, bit for bit (%.9g round-trips a float)."""
+    H = s3.host_lib()
+    H.scan3d_write_ply_points.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    H.scan3d_read_ply_points.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    rng = np.random.default_rng(12)
+    xyz = (rng.normal(size=(777, 3)) * [1e-3, 50, 4e5]).astype(np.float32)
+    rgb = rng.integers(0, 256, (777, 3), dtype=np.uint8)
+    for binary in (0, 1):
+        path = str(tmp_path / f"c{binary}.ply").encode()
+        assert H.scan3d_write_ply_points(path, xyz.ctypes.data_as(C.c_void_p), rgb.ctypes.data_as(C.c_void_p), 777, binary) == 0
+        n = C.c_int64()
+        assert H.scan3d_read_ply_points(path, None, None, 0, C.byref(n)) == 0 and n.value == 777
+        x2 = np.empty_like(xyz)
+        c2 = np.empty_like(rgb)
+        assert H.scan3d_read_ply_points(path, x2.ctypes.data_as(C.c_void_p), c2.ctypes.data_as(C.c_void_p), 777, C.byref(n)) == 0
+        assert np.array_equal(x2.view(np.uint32), xyz.view(np.uint32)) and np.array_equal(c2, rgb)
+        assert H.scan3d_read_ply_points(path, x2.ctypes.data_as(C.c_void_p), None, 10, C.byref(n)) == -4   # buffer too small
+    # a PCL-style header: doubles, an extra property, no colours
+    p = tmp_path / "pcl.ply"
+    p.write_text("ply\nformat ascii 1.0\nelement vertex 2\nproperty double x\nproperty double y\nproperty double z\n"
+                 "property float curvature\nend_header\n1.5 2.5 -3 0.1\n4 5 6 0.2\n")
+    x3 = np.empty((2, 3), np.float32)
+    c3 = np.empty((2, 3), np.uint8)
+    n = C.c_int64()
+    assert H.scan3d_read_ply_points(str(p).encode(), x3.ctypes.data_as(C.c_void_p), c3.ctypes.data_as(C.c_void_p), 2, C.byref(n)) == 0
+    assert np.array_equal(x3, np.array([[1.5, 2.5, -3], [4, 5, 6]], np.float32)) and not c3.any()
+    assert H.scan3d_read_ply_points(str(tmp_path / "missing.ply").encode(), None, None, 0, C.byref(n)) == -5
+
+
+def test_aux_entries_reject_bad_arguments_without_gpu():
+    L = s3.cuda_lib()
+    assert L.scan3d_undistort_frames(None, 0, None, 1, None) == -4
+    assert L.scan3d_roi_fill(None, None, None, None) == -4
+    assert L.scan3d_register_points(None, None, None, 0, 0.0, 0.0, 0.0, 0.0) == -4
+    R = np.empty(16, np.float32)
+    assert L.scan3d_register_rotation(36.0, R.ctypes.data_as(C.c_void_p)) == 0      # host arithmetic (libm), no GPU needed
+    assert np.array_equal(R.reshape(4, 4), o.register_rotation(36.0))

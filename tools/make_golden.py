@@ -15,6 +15,10 @@ importable); the GPU box has neither, so the outputs are committed:
                               transpose/gemm/invert/gemm/gemm triangulation chain.
   tests/golden/pattern_kat.npz first row / column of the reference's Generated_patterns
                               (stage-1 conventions used by the synthetic generator).
+  tests/golden/f4_kat.npz     either side of the path: cv2.undistort of small random
+                              images (pins the cvUndistort2 restatement), the float cv2.gemm chain of
+                              register_point_clouds, and the per-row extent of the reference's stored
+                              i1.jpg (image_scissor's filled outline).  `make_golden.py f4` makes only this.
 """
 import json
 import os
@@ -81,8 +85,53 @@ def load_calib():
     return c
 
 
+def make_f4():
+    import cv2
+    cal = load_calib()
+    rng = np.random.default_rng(20261018)
+    kat = {"cv2_version": np.array(cv2.__version__)}
+    cases = [(320, 240, cal["Kc"] * np.array([[0.2], [0.2], [1.0]]), cal["dc"]),                    # C1 calibration, scaled
+             (256, 96, cal["Kc"] * np.array([[0.16], [0.16], [1.0]]), cal["dc"] * 6),
+             (200, 150, np.array([[180.0, 0.4, 97.3], [0, 184.0, 80.1], [0, 0, 1]]), np.array([-0.31, 0.12, -0.002, 0.001, -0.03])),
+             (4100, 5, np.array([[3600.0, 0, 2050.5], [0, 3610.0, 2.0], [0, 0, 1]]), np.array([0.0813, -0.1102, 0.0013, -0.0007, 0.021])),
+             (1280 // 4, 720 // 4, cal["Kp"] * np.array([[0.25], [0.25], [1.0]]), cal["dp"])]         # projector: no distortion
+    kat["n_undistort"] = np.array(len(cases))
+    for i, (W, H, K, d) in enumerate(cases):
+        src = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        kat[f"und_K{i}"], kat[f"und_d{i}"], kat[f"und_src{i}"] = K, d, src
+        kat[f"und_dst{i}"] = cv2.undistort(src, K, d)
+    # 9/register_point_clouds.cpp:93-137 with cv2.gemm standing in for cvMatMul (same unrolled float path)
+    theta = np.float32(36.0)
+    a = float(theta) * 22.0 / 7.0 / 180.0      # the float promotes to double, as in C
+    R = np.zeros((4, 4), np.float32)
+    R[0, 0] = np.cos(a); R[0, 2] = -1.0 * np.sin(a); R[2, 0] = np.sin(a); R[2, 2] = np.cos(a)
+    R[1, 1] = 1.0; R[3, 3] = 1.0
+    pts = (rng.normal(size=(2048, 3)) * [120, 80, 300] + [10, -20, 900]).astype(np.float32)
+    t = np.array([12.5, -3.25, 903.1], np.float32)
+    out = np.empty_like(pts)
+    for k in range(len(pts)):
+        p = np.array([[pts[k, 0]], [pts[k, 1]], [pts[k, 2]], [1.0]], np.float32)
+        p[0, 0] -= t[0]; p[1, 0] -= t[1]; p[2, 0] -= t[2]
+        q = cv2.gemm(R, p, 1.0, None, 0.0)
+        q[0, 0] += t[0]; q[1, 0] += t[1]; q[2, 0] += t[2]
+        out[k] = q[:3, 0]
+    kat["reg_theta"], kat["reg_t"], kat["reg_R"], kat["reg_pts"], kat["reg_out"] = np.array(theta), t, R, pts, out
+    # image_scissor's filled outline as the reference stored it (JPEG -> threshold)
+    m = cv2.imread(REF + "i1.jpg", 0) > 127
+    cols = np.arange(m.shape[1])
+    kat["i1_shape"] = np.array(m.shape)
+    kat["i1_count"] = m.sum(1).astype(np.int32)
+    kat["i1_first"] = np.where(m.any(1), np.where(m, cols, m.shape[1]).min(1), 0).astype(np.int32)
+    kat["i1_last"] = np.where(m.any(1), np.where(m, cols, -1).max(1), -1).astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "f4_kat.npz"), **kat)
+
+
 def main():
     import cv2
+    if len(sys.argv) > 1 and sys.argv[1] == "f4":
+        make_f4()
+        print("f4_kat.npz", os.path.getsize(os.path.join(OUT, "f4_kat.npz")))
+        return
     os.makedirs(OUT, exist_ok=True)
     sl = (slice(CROP_R0, CROP_R1), slice(CROP_C0, CROP_C1))
 
@@ -155,6 +204,7 @@ def main():
     pk["fringe5_k4_v_row0"] = read_bmp8(g + "Fringe_patterns/Vertical/Pattern_4.bmp")[0]
     pk["fringe5_k4_h_col0"] = read_bmp8(g + "Fringe_patterns/Horizontal/Pattern_4.bmp")[:, 0]
     np.savez_compressed(os.path.join(OUT, "pattern_kat.npz"), **pk)
+    make_f4()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
