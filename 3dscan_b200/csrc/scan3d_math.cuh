@@ -15,6 +15,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#if !defined(__CUDACC__)
+// host build of this header (CPU tests only): the including translation unit provides the CUDA
+// intrinsics used below as plain IEEE host functions (tests/cuda_host_shim.h)
+double s3d_host_rcp_seed(double x);
+#endif
+
 namespace s3d {
 
 // "Pi" as the reference's macro expands inside each expression.
@@ -42,10 +48,25 @@ __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a,
 //   [66..71] quadrant constants {K_hi, K_lo} for k = 0 (none), 1 (pi/2), 2 (pi)
 constexpr int ATAN_TAB_DOUBLES = 72;
 
+// rcp.approx.ftz.f64: a ~20-bit reciprocal seed (only the high word of the operand is looked at, the
+// low word of the result is zero).  The host build (tests/fused_math_host.cpp) substitutes a seed
+// of the same quality; after the corrections below the seed's low bits do not reach the result.
+__device__ __forceinline__ double rcp_seed(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#elif !defined(__CUDACC__)
+    return s3d_host_rcp_seed(x);
+#else
+    return x;   // nvcc's host pass only parses this function, nothing calls it there
+#endif
+}
+
 __device__ __forceinline__ double fast_div(double num, double den)
 {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));   // ~20 good bits
+    double r = rcp_seed(den);                                  // ~20 good bits
     r = fma(r, fma(-den, r, 1.0), r);                          // ~40
     const double t = num * r;
     return fma(fma(-den, t, num), r, t);                       // residual correction: ~1 ulp
@@ -425,8 +446,7 @@ __device__ __forceinline__ void triangulate_point_fast(const double* __restrict_
     const double c12 = fma(S01, S02, -S00 * S12);
     const double c22 = fma(S00, S11, -S01 * S01);
     const double det = fma(S02, c02, fma(S01, c01, S00 * c00));
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(det));
+    double r = rcp_seed(det);
     r = fma(r, fma(-det, r, 1.0), r);
     r = fma(r, fma(-det, r, 1.0), r);
     r = det != 0.0 ? r : 0.0;   // cvInvert returns a zero matrix for a singular input
