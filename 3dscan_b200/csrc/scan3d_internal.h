@@ -157,6 +157,5 @@ cudaError_t launch_debug_atan2(const double* y, const double* x, float* out, int
 
 cudaError_t launch_debug_divcheck(unsigned long long* bad, cudaStream_t st);
 
-void fill_atan_table(double* hi33_lo33);
 
 }  // namespace s3d

@@ -13,6 +13,7 @@
 //   PROJECT_GLOBAL/global_cv.h:62                 #define Pi 22.0/7.0 (textual)
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #if !defined(__CUDACC__)
@@ -47,6 +48,22 @@ __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a,
 //   [0..32]  hi(atan(i/32))      [33..65] lo(atan(i/32))
 //   [66..71] quadrant constants {K_hi, K_lo} for k = 0 (none), 1 (pi/2), 2 (pi)
 constexpr int ATAN_TAB_DOUBLES = 72;
+
+// host side: fills that table (long-double atanl split into hi + lo)
+inline void fill_atan_table(double* t)
+{
+    for (int i = 0; i <= 32; i++) {
+        const long double c = (long double)i / 32.0L;
+        const long double a = atanl(c);
+        const double hi = (double)a;
+        t[i] = hi;
+        t[33 + i] = (double)(a - (long double)hi);
+    }
+    // quadrant constants {hi, lo}: 0, pi/2, pi
+    t[66] = 0.0; t[67] = 0.0;
+    t[68] = 1.57079632679489655800e+00; t[69] = 6.12323399573676603587e-17;
+    t[70] = 3.14159265358979311600e+00; t[71] = 1.22464679914735317720e-16;
+}
 
 // rcp.approx.ftz.f64: a ~20-bit reciprocal seed (only the high word of the operand is looked at, the
 // low word of the result is zero).  The host build (tests/fused_math_host.cpp) substitutes a seed

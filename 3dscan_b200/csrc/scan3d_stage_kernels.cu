@@ -9,21 +9,6 @@ namespace s3d {
 
 static inline unsigned cdiv(long a, long b) { return (unsigned)((a + b - 1) / b); }
 
-void fill_atan_table(double* t)
-{
-    for (int i = 0; i <= 32; i++) {
-        const long double c = (long double)i / 32.0L;
-        const long double a = atanl(c);
-        const double hi = (double)a;
-        t[i] = hi;
-        t[33 + i] = (double)(a - (long double)hi);
-    }
-    // quadrant constants {hi, lo}: 0, pi/2, pi
-    t[66] = 0.0; t[67] = 0.0;
-    t[68] = 1.57079632679489655800e+00; t[69] = 6.12323399573676603587e-17;
-    t[70] = 3.14159265358979311600e+00; t[71] = 1.22464679914735317720e-16;
-}
-
 // ------------------------------------------------------------------------------------------
 // mask: ROI -> valid after the raster recurrence (3/wrapped_phase.cpp:106-115 + :266-279)
 // ------------------------------------------------------------------------------------------
