@@ -125,3 +125,43 @@ def test_atan2_on_every_3_and_4_step_argument_pair(shim):
     shim.s3d_host_atan2_to_float(_p(y), _p(x), y.size, _p(out))
     want = np.arctan2(y, x).astype(np.float32)
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
+
+
+from helpers import REF, have_reference, read_bmp8  # noqa: E402
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference tree not mounted")
+def test_reference_scan_full_frame_through_the_kernel_arithmetic(shim):
+    """configs[0]: the reference's own 1600x1200 capture (3-step, 6/5 Gray bits, fw 32, its calibration files),
+    whole frame: the stored wrapped-phase image gives the mask, the stored unwrapped-phase images must come out of
+    the kernel arithmetic bit for bit (358 580 pixels x 2 directions), and c_p_map / validity / points equal the oracle."""
+    base = REF + "Captured_patterns/"
+    planes = []
+    gold = {}
+    for name, M in (("Vertical", 6), ("Horizontal", 5)):
+        planes += [read_bmp8(f"{base}Fringe_patterns/{name}/Undistorted/Gray_captured_image_{i}.bmp") for i in range(3)]
+        planes += [read_bmp8(f"{base}Coded_patterns/Gray_coded/{name}/Undistorted/Gray_captured_image_{i}.bmp") for i in range(M)]
+        planes += [read_bmp8(f"{base}Coded_patterns/Gray_coded/{name}/Undistorted/inverse_Gray_captured_image_{i}.bmp") for i in range(M)]
+        gold[name] = (read_bmp8(REF + f"Wrapped_phase_images/{name}/Wrapped_phase_image.bmp"),
+                      read_bmp8(REF + f"Unwrapped_phase_images/Gray_coded/{name}/Unwrapped_phase_{name.lower()}.bmp"))
+    stack = np.stack(planes)
+    roi = (gold["Vertical"][0] != 0).astype(np.uint8)
+    assert int(roi.sum()) == 358580
+    c = load_calib_c1()
+    cfg = dict(W=1600, H=1200, PW=1280, PH=720, N=3, M_v=6, M_h=5, fw_v=32, fw_h=32, dirs=2)
+    r = run_host(shim, cfg, c, stack, roi, exact=True, mask_is_final=True)
+    valid = roi.astype(np.int32)
+    m = valid == 1
+    assert np.array_equal(o.unwrapped_image(r.unw_v, valid, 40)[m], gold["Vertical"][1][m])
+    assert np.array_equal(o.unwrapped_image(r.unw_h, valid, 23)[m], gold["Horizontal"][1][m])
+    # stages 5-8 against the oracle on the same planes
+    cp, ovalid = o.compute_c_p_map(r.unw_v, r.unw_h, valid, valid, 32, 32, 1280, 720)
+    assert np.array_equal(r.valid.astype(np.int32), ovalid)
+    assert np.array_equal(r.cpmap.astype(np.int64)[ovalid.ravel() == 1], cp[ovalid.ravel() == 1])
+    Ac = o.compute_A(c["Kc"], c["rc"], c["tc"])
+    Ap = o.compute_A(c["Kp"], c["rp"], c["tp"])
+    xyz = o.triangulate(Ac, Ap, o.undistort_lut(c["Kc"], c["dc"], 1600, 1200), o.undistort_lut(c["Kp"], c["dp"], 1280, 720),
+                        cp, ovalid, 1280, 720)
+    pts, _, _ = o.compact(xyz, ovalid)
+    assert r.count == len(pts) > 300000
+    assert np.array_equal(r.pts.view(np.uint32), pts.view(np.uint32))
