@@ -169,4 +169,31 @@ void s3d_host_atan2_to_float(const double* y, const double* x, int n, float* out
     fill_atan_table(atan_tab);
     for (int i = 0; i < n; i++) out[i] = atan2_to_float(y[i], x[i], (float)y[i], (float)x[i], atan_tab);
 }
+
+// the stage kernels' wrapped phase (k_wrapped: wrapped_phase<N, false>; N = 0 is the generic-N extension with the
+// sin / cos weights scan3d_create() computes) for n pixels; I = [N][n] samples
+int s3d_host_stage_wrapped_phase(const uint8_t* I, int N, int n, float* out)
+{
+    double atan_tab[ATAN_TAB_DOUBLES], w[128];
+    fill_atan_table(atan_tab);
+    memset(w, 0, sizeof(w));
+    for (int k = 0; k < N && k < 64; k++) {          // scan3d_create()
+        const double a = 2.0 * 3.14159265358979323846 * (double)k / (double)N;
+        w[k] = sin(a);
+        w[64 + k] = cos(a);
+    }
+    if (N < 3 || N > 16) return -1;
+    for (int p = 0; p < n; p++) {
+        int v[16];
+        for (int k = 0; k < N; k++) v[k] = I[(size_t)k * n + p];
+        switch (N) {
+            case 3: out[p] = wrapped_phase<3, false>(v, w, w + 64, N, atan_tab, atan_tab + 33); break;
+            case 4: out[p] = wrapped_phase<4, false>(v, w, w + 64, N, atan_tab, atan_tab + 33); break;
+            case 5: out[p] = wrapped_phase<5, false>(v, w, w + 64, N, atan_tab, atan_tab + 33); break;
+            case 8: out[p] = wrapped_phase<8, false>(v, w, w + 64, N, atan_tab, atan_tab + 33); break;
+            default: out[p] = wrapped_phase<0, false>(v, w, w + 64, N, atan_tab, atan_tab + 33); break;
+        }
+    }
+    return 0;
+}
 }

@@ -165,3 +165,21 @@ def test_reference_scan_full_frame_through_the_kernel_arithmetic(shim):
     pts, _, _ = o.compact(xyz, ovalid)
     assert r.count == len(pts) > 300000
     assert np.array_equal(r.pts.view(np.uint32), pts.view(np.uint32))
+
+
+@pytest.mark.parametrize("N", [3, 4, 5, 6, 7, 8, 12, 16])
+def test_stage_kernel_wrapped_phase_all_step_counts(shim, N):
+    """k_wrapped's arithmetic (the per-stage path, incl. the generic-N extension) against the oracle on random and
+    extreme samples: saturated, black, equal frames (atan2(0, 0)), single bright frame."""
+    rng = np.random.default_rng(N)
+    n = 200_000
+    I = rng.integers(0, 256, (N, n), dtype=np.uint8)
+    I[:, :256] = np.arange(256, dtype=np.uint8)[None, :]          # all frames equal: t1 = t2 = 0
+    I[:, 256:512] = 0
+    I[0, 256:512] = np.arange(256, dtype=np.uint8)               # one bright frame
+    I[:, 512:768] = 255
+    I[N - 1, 512:768] = np.arange(256, dtype=np.uint8)
+    out = np.empty(n, np.float32)
+    assert shim.s3d_host_stage_wrapped_phase(_p(np.ascontiguousarray(I)), N, n, _p(out)) == 0
+    want, _ = o.wrapped_phase(I.reshape(N, 1, n), np.ones((1, n), np.int32), want_dbg=False)
+    assert np.array_equal(out.view(np.uint32), want.ravel().view(np.uint32))
