@@ -414,7 +414,7 @@ def main():
     achieved = bpp * npix / per_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload), "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                "kernel": "s3d::k_fused<%d,%d>" % (N, dirs), "algorithmic_bytes_per_launch": bpp * npix,
+                "kernel": ("s3d::k_fused<%d,%d>" if os.environ.get("SCAN3D_FUSED_IMPL") == "6" else "s3d::k_fused7<%d,%d,...>") % (N, dirs), "algorithmic_bytes_per_launch": bpp * npix,
                 "avg_launch_us": per_launch_s * 1e6, "launches_per_scan": launches / (args.steps * args.batch), "frac_of_8TBs_nominal": achieved / 8000.0}
 
     # ---- e2e: host-buffer entry, pinned input, H2D + kernel + D2H of the point cloud per scan
