@@ -26,6 +26,9 @@ NVCC_FLAGS = [
 # they cost ~2 % of the kernel's instructions, so the default build leaves them out.
 if os.environ.get("SCAN3D_BUILD_TRACE") == "1":
     NVCC_FLAGS.append("-DS3D_TRACE=1")
+# SCAN3D_BUILD_DEFS="-DS3D_VAR_X=1 ...": experimental kernel variants (tools/build_variants.py builds them into
+# their own SCAN3D_LIBDIR; the default build defines none of them)
+NVCC_FLAGS += [d for d in os.environ.get("SCAN3D_BUILD_DEFS", "").split() if d.startswith("-D")]
 CU_SOURCES = ["scan3d_api.cu", "scan3d_stage_kernels.cu", "scan3d_fused_kernel.cu", "scan3d_fused_kernel7.cu",
               "scan3d_aux_kernels.cu", "scan3d_aux_api.cu"]
 HOST_SOURCES = ["scan3d_io.cpp", "scan3d_synth.cpp"]

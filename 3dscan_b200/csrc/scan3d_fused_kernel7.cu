@@ -93,6 +93,27 @@ constexpr int regs7(int cw, int minb)
     return r > 255 ? 255 : (r / 8) * 8;
 }
 
+#if S3D_VAR_COLD_OUTLINE
+// mask recurrence for the 4 pixels of a thread next to a ROI edge or the frame border (rare): out of line
+static __device__ __noinline__ uint32_t mask_slow7(const uint8_t* sroi, int roi_row, int lp0, int xt, int y, int W, int H_total)
+{
+    uint32_t mbits = 0;
+    const uint32_t centre = *reinterpret_cast<const uint32_t*>(sroi + 2 * roi_row + lp0 + ROI_HALO);
+    if (centre != 0) {
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+            const int x = xt + j;
+            auto inv = [&](int gx, int gy) { return sroi[(gy - y + 2) * roi_row + (lp0 + j + (gx - x) + ROI_HALO)] == 0; };
+            bool v = !inv(x, y);
+            const bool border = x == 0 || y == 0 || x == W - 1 || y == H_total - 1;
+            if (v && !border) v = !mask_trigger(x, y, W, H_total, inv);
+            mbits |= (v ? 1u : 0u) << j;
+        }
+    }
+    return mbits;
+}
+#endif
+
 template <int N, int DIRS, int CW, int MINB, bool EXACT>
 __global__ void __launch_bounds__((CW + 1) * 32) __maxnreg__(regs7(CW, MINB))
 k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal, const __grid_constant__ CUtensorMap stack_map)
@@ -386,6 +407,9 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     }
                 if (any_zero == 0) { mbits = 0xf; fast = true; }
             }
+#if S3D_VAR_COLD_OUTLINE
+            if (!fast) mbits = mask_slow7(sroi, G.roi_row, lp0, xt, y, W, a.H_total);
+#else
             if (!fast) {
                 const uint32_t centre = *reinterpret_cast<const uint32_t*>(sroi + 2 * G.roi_row + lp0 + ROI_HALO);
                 if (centre != 0) {
@@ -402,6 +426,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     }
                 }
             }
+#endif
             if (mbits) {
                 fringe_terms<N>(sw, 0, WPF, tid, Tv);
                 gray_bits(sw, N, N + a.M_v, a.M_v, WPF, tid, gvA, gvB);
@@ -431,10 +456,28 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 int r_cv[2], r_ch[2];
                 int2 r_cp[2];
                 uint32_t vb = 0;
+#if S3D_VAR_TERM_ROTATE
+                // second pass: pixels 2,3 move into the lanes of pixels 0,1, so that every lane selection below
+                // is a compile-time one (the per-term run-time selects were ~100 of the pass's 589 instructions)
+                if (h) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        Tv.t[k][0] = Tv.t[k][1];
+                        if (DIRS == 2) Th.t[k][0] = Th.t[k][1];
+                    }
+                    gvA >>= 16; gvB >>= 16; ghA >>= 16; ghB >>= 16;
+                    mbits >>= 2;
+                }
+#endif
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
+#if S3D_VAR_TERM_ROTATE
+                    const int j = u;
+                    const int x = xt + 2 * h + u;
+#else
                     const int j = 2 * h + u;
                     const int x = xt + j;
+#endif
                     const bool m = (mbits >> j) & 1u;
                     const int cv = code_of(gvA, gvB, j, a.M_v);
                     const float wv = add_pi(phase_of<N>(Tv, j, tab));                    // 4/phase_unwrap.cpp:290

@@ -10,6 +10,9 @@
 // ~1 ulp in double afterwards, so the float outputs agree except when a value sits within ~2^-50 of a float
 // rounding boundary (the GPU tests count those cases on the device itself: none on 2^24 + 8 M inputs).
 #pragma once
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
