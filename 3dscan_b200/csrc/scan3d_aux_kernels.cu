@@ -10,6 +10,24 @@
 #include "scan3d_internal.h"
 #include "../common/scan3d_aux_math.h"
 
+// Experimental variants of k_remap_frames (tools/build_variants.py; off in the default build):
+//   S3D_VAR_REMAP_UNROLL=n  frame loop unrolled n times (loads of n frames in flight per thread)
+//   S3D_VAR_REMAP_WINDOW    two aligned 8-byte loads per source row instead of 8 one-byte gathers when a thread's
+//                           4 pixels allow it (scan3d_aux_math.h, "windowed gather"; 96 % of the groups at 12 MP)
+#ifndef S3D_VAR_REMAP_UNROLL
+#define S3D_VAR_REMAP_UNROLL 1
+#endif
+#ifndef S3D_VAR_REMAP_WINDOW
+#define S3D_VAR_REMAP_WINDOW 0
+#endif
+#define S3D_PRAGMA_(x) _Pragma(#x)
+#if S3D_VAR_REMAP_UNROLL > 1
+#define S3D_UNROLL_N_(n) S3D_PRAGMA_(unroll n)
+#define S3D_FRAME_UNROLL S3D_UNROLL_N_(S3D_VAR_REMAP_UNROLL)
+#else
+#define S3D_FRAME_UNROLL
+#endif
+
 namespace s3d {
 
 struct AuxCalib {
@@ -62,6 +80,26 @@ __global__ void __launch_bounds__(256) k_remap_frames(const uint8_t* __restrict_
                 fr[k] = map_frac[p + k];
             }
         }
+#if S3D_VAR_REMAP_WINDOW
+        if (VEC == 4) {
+            int16_t xy16[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { xy16[2 * k] = xy[k].x; xy16[2 * k + 1] = xy[k].y; }
+            const s3a::RemapGroup grp = s3a::remap_group_prepare(xy16, W, H, (W & 7) == 0 && ((uintptr_t)src & 7) == 0);
+            if (grp.fast) {
+                S3D_FRAME_UNROLL
+                for (int f = 0; f < n_frames; f++) {
+                    const uint8_t* s = src + (size_t)f * plane + grp.base;
+                    const uint2 a0 = __ldg(reinterpret_cast<const uint2*>(s)), a1 = __ldg(reinterpret_cast<const uint2*>(s + 8));
+                    const uint2 b0 = __ldg(reinterpret_cast<const uint2*>(s + W)), b1 = __ldg(reinterpret_cast<const uint2*>(s + W + 8));
+                    const uint32_t r0[4] = {a0.x, a0.y, a1.x, a1.y}, r1[4] = {b0.x, b0.y, b1.x, b1.y};
+                    *reinterpret_cast<uint32_t*>(dst + (size_t)f * plane + p) = s3a::remap_group_blend(grp, r0, r1, fr);
+                }
+                continue;
+            }
+        }
+#endif
+        S3D_FRAME_UNROLL
         for (int f = 0; f < n_frames; f++) {
             const uint8_t* s = src + (size_t)f * plane;
             uint32_t packed = 0;

@@ -2,6 +2,7 @@
 // scan3d_aux_kernels.cu evaluate), so that the CPU test suite can compare them with the oracle
 // without a GPU.  Built by tests/test_aux_math_host.py with g++ -O2 -ffp-contract=off.
 #include <stddef.h>
+#include <string.h>
 
 #include "../3dscan_b200/common/scan3d_aux_math.h"
 
@@ -25,6 +26,35 @@ void s3a_host_remap(const uint8_t* src, int W, int H, const int16_t* xy, const u
         dst[p] = s3a::bilinear_u8(tap(src, W, H, x, y), tap(src, W, H, x + 1, y), tap(src, W, H, x, y + 1),
                                   tap(src, W, H, x + 1, y + 1), frac[p]);
     }
+}
+
+// k_remap_frames with S3D_VAR_REMAP_WINDOW: groups of 4 pixels, window path when the group allows it.
+// Returns the number of groups that took the window path.
+long long s3a_host_remap_window(const uint8_t* src, int W, int H, const int16_t* xy, const uint16_t* frac, uint8_t* dst)
+{
+    const size_t plane = (size_t)W * H;
+    long long n_fast = 0;
+    for (size_t p = 0; p + 4 <= plane; p += 4) {
+        const s3a::RemapGroup g = s3a::remap_group_prepare(xy + 2 * p, W, H, W % 8 == 0);
+        int fr[4];
+        for (int k = 0; k < 4; k++) fr[k] = frac[p + k];
+        uint32_t packed = 0;
+        if (g.fast) {
+            uint32_t r0[4], r1[4];
+            memcpy(r0, src + g.base, 16);          // the kernel: two 8-byte loads per row
+            memcpy(r1, src + g.base + W, 16);
+            packed = s3a::remap_group_blend(g, r0, r1, fr);
+            n_fast++;
+        } else {
+            for (int k = 0; k < 4; k++) {
+                const int x = xy[2 * (p + k)], y = xy[2 * (p + k) + 1];
+                packed |= (uint32_t)s3a::bilinear_u8(tap(src, W, H, x, y), tap(src, W, H, x + 1, y), tap(src, W, H, x, y + 1),
+                                                     tap(src, W, H, x + 1, y + 1), fr[k]) << (8 * k);
+            }
+        }
+        memcpy(dst + p, &packed, 4);
+    }
+    return n_fast;
 }
 
 void s3a_host_register_rotation(float theta_deg, float* R) { s3a::register_rotation(theta_deg, R); }

@@ -7,6 +7,11 @@ timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/variant_defa
 for d in 3dscan_b200/lib_var_*/; do
   v=$(basename $d); v=${v#lib_var_}
   echo "== $v"
+  case $v in remap*)
+    SCAN3D_LIBDIR=$PWD/$d timeout 100 python tools/gpu_aux_check.py 2>&1 | tail -1
+    SCAN3D_LIBDIR=$PWD/$d timeout 100 python tools/bench_aux.py 2>/dev/null | grep remap_frames | tee gpurun_out/variant_$v.jsonl
+    continue;;
+  esac
   SCAN3D_LIBDIR=$PWD/$d timeout 600 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -2
   SCAN3D_LIBDIR=$PWD/$d timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/variant_$v.json 2>/dev/null
   SCAN3D_LIBDIR=$PWD/$d timeout 200 python bench.py --exact-triangulation --no-e2e --no-cpu-baseline > gpurun_out/variant_${v}_exact.json 2>/dev/null
