@@ -158,3 +158,23 @@ def test_roi_fill_pinned_by_the_reference_i1_rows():
     roi, filled = o.roi_fill(outline)
     assert np.array_equal((filled != 0).sum(1), count)
     assert np.array_equal(roi.sum(1)[ys], np.maximum(count[ys] - 2, 0))
+
+
+from helpers import REF, have_reference, read_bmp8  # noqa: E402
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference tree not mounted")
+def test_the_one_surviving_cvUndistort2_output_of_the_reference(shim):
+    """6/system_calibration.cpp:1559-1560 stores cvUndistort2(virtual checkerboard, proj_intrinsic_mat, proj_dist_vect).
+    The stored image is the 1024x768 checkerboard of an earlier projector and equals its input pixel for pixel, which
+    is what the reference's distortion-free projector calibration must give (the fixed-point map lands on integer
+    source pixels with zero fractions); oracle and kernel arithmetic reproduce it."""
+    src = read_bmp8(REF + "Projector_calibration/Virtual_calibration_rig/Checkerboard.bmp")
+    stored = read_bmp8(REF + "Undistorted_projector_image.bmp")
+    assert src.shape == stored.shape == (768, 1024)
+    c = load_calib_c1()
+    assert not c["dp"].any()
+    assert np.array_equal(o.undistort_frames(src[None], c["Kp"], c["dp"])[0], stored)
+    xy, fr = _host_map(shim, c["Kp"].reshape(3, 3), c["dp"], 1024, 768)
+    assert not fr.any()
+    assert np.array_equal(_host_remap(shim, src, xy, fr), stored)
