@@ -178,3 +178,30 @@ def test_the_one_surviving_cvUndistort2_output_of_the_reference(shim):
     xy, fr = _host_map(shim, c["Kp"].reshape(3, 3), c["dp"], 1024, 768)
     assert not fr.any()
     assert np.array_equal(_host_remap(shim, src, xy, fr), stored)
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference tree not mounted")
+def test_registration_of_the_reference_test_cloud(shim):
+    """Point_cloud/test data/point_cloud_2.ply is the one cloud the reference tree still holds (binary PLY, 103 959
+    vertices with alpha, written by MeshLab): the host library's reader takes it, and register_point_clouds'
+    transform of it (third turntable view: theta = 2 * rot_step) is the same in the oracle and the kernel arithmetic."""
+    import importlib
+    s3 = importlib.import_module("3dscan_b200")
+    Hl = s3.host_lib()
+    Hl.scan3d_read_ply_points.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    path = (REF + "Point_cloud/test data/point_cloud_2.ply").encode()
+    n = C.c_int64()
+    assert Hl.scan3d_read_ply_points(path, None, None, 0, C.byref(n)) == 0 and n.value == 103959
+    xyz = np.empty((n.value, 3), np.float32)
+    rgb = np.empty((n.value, 3), np.uint8)
+    assert Hl.scan3d_read_ply_points(path, _p(xyz), _p(rgb), n.value, C.byref(n)) == 0
+    raw = open(path, "rb").read()
+    rec = np.frombuffer(raw[raw.index(b"end_header\n") + 11:][:16 * n.value],
+                        np.dtype([("xyz", "<f4", 3), ("rgba", "u1", 4)]))
+    assert np.array_equal(xyz, rec["xyz"]) and np.array_equal(rgb, rec["rgba"][:, :3])
+    theta, t = 2 * 36.0, (70.0, 30.0, 10.0)
+    want = o.register_points(xyz, theta, *t)
+    mine = xyz.copy()
+    shim.s3a_host_register_points(_p(mine), C.c_longlong(len(mine)), C.c_float(theta), C.c_float(t[0]), C.c_float(t[1]), C.c_float(t[2]))
+    assert np.array_equal(mine.view(np.uint32), want.view(np.uint32))
+    assert not np.array_equal(mine, xyz)
