@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs tests/test_gpu_zaux.py's checks without pytest/torch start-up (a few seconds on the GPU box):
-    gpurun --timeout 120 -- 'python tools/gpu_aux_check.py > gpurun_out/aux_check.log 2>&1'
+    gpurun --timeout 120 -- 'python tests/aux_check_runner.py > gpurun_out/aux_check.log 2>&1'
 """
 import os
 import pathlib
@@ -9,7 +9,7 @@ import tempfile
 import time
 import traceback
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 

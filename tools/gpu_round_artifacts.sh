@@ -11,6 +11,6 @@ SCAN3D_FUSED_DYN=0 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpur
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 1 --warmup 3 --batch 2 --ring 2 --no-e2e --no-cpu-baseline > gpurun_out/launches_r1.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_fused7 -s 3 -c 1 -o gpurun_out/fused_r1_final python bench.py --steps 1 --warmup 3 --batch 2 --ring 2 --no-e2e --no-cpu-baseline > gpurun_out/fused_r1_final.log 2>&1
 SCAN3D_LIBDIR=$PWD/3dscan_b200/lib_trace SCAN3D_TRACE=1 timeout 200 python tools/trace_fused.py > gpurun_out/trace_r1.txt 2>&1; tail -9 gpurun_out/trace_r1.txt
-timeout 60 python tools/gpu_aux_check.py > gpurun_out/aux_check.log 2>&1; tail -1 gpurun_out/aux_check.log
+timeout 60 python tests/aux_check_runner.py > gpurun_out/aux_check.log 2>&1; tail -1 gpurun_out/aux_check.log
 timeout 60 python tools/bench_aux.py > gpurun_out/bench_aux.jsonl 2> gpurun_out/bench_aux.err; cat gpurun_out/bench_aux.jsonl
 ls -la gpurun_out | tail -5

@@ -8,7 +8,7 @@ for d in 3dscan_b200/lib_var_*/; do
   v=$(basename $d); v=${v#lib_var_}
   echo "== $v"
   case $v in remap*)
-    SCAN3D_LIBDIR=$PWD/$d timeout 100 python tools/gpu_aux_check.py 2>&1 | tail -1
+    SCAN3D_LIBDIR=$PWD/$d timeout 100 python tests/aux_check_runner.py 2>&1 | tail -1
     SCAN3D_LIBDIR=$PWD/$d timeout 100 python tools/bench_aux.py 2>/dev/null | grep remap_frames | tee gpurun_out/variant_$v.jsonl
     continue;;
   esac
