@@ -93,6 +93,12 @@ constexpr int regs7(int cw, int minb)
     return r > 255 ? 255 : (r / 8) * 8;
 }
 
+// back-off of the IO warp's event loop between empty polls (experimental knob, tools/build_variants.py: the three
+// IO warps of an SM issue ~10 % of the kernel's instructions, most of them polling)
+#ifndef S3D_VAR_IO_SLEEP_NS
+#define S3D_VAR_IO_SLEEP_NS 250
+#endif
+
 #if S3D_VAR_COLD_OUTLINE
 // mask recurrence for the 4 pixels of a thread next to a ROI edge or the frame border (rare): out of line
 static __device__ __noinline__ uint32_t mask_slow7(const uint8_t* sroi, int roi_row, int lp0, int xt, int y, int W, int H_total)
@@ -369,7 +375,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     }
                 }
             }
-            if (!progressed) __nanosleep(250);
+            if (!progressed) __nanosleep(S3D_VAR_IO_SLEEP_NS);
         }
         return;
     }
