@@ -225,3 +225,18 @@ def test_aux_entries_reject_bad_arguments_without_gpu():
     R = np.empty(16, np.float32)
     assert L.scan3d_register_rotation(36.0, R.ctypes.data_as(C.c_void_p)) == 0      # host arithmetic (libm), no GPU needed
     assert np.array_equal(R.reshape(4, 4), o.register_rotation(36.0))
+
+
+def test_compat_library_exports_the_reference_named_functions():
+    """libscan3d_compat.so carries the reference's own stage functions with C++ linkage
+    (PROJECT_GLOBAL/intermodule_dependencies.h:10-25 + the capture / scissor / registration entries)."""
+    s3.cuda_lib(); s3.host_lib()            # its dependencies, resolved through $ORIGIN
+    L = C.CDLL(os.path.join(ROOT, "3dscan_b200", "lib", "libscan3d_compat.so"))
+    for sym in ("_Z16generate_patternv", "_Z13load_matricesv", "_Z21compute_wrapped_phasei", "_Z12unwrap_phasei",
+                "_Z15compute_c_p_mapv", "_Z11triangulatev", "_Z16save_point_cloudj", "_Z16reconstruct_scanj",
+                "_Z21register_point_cloudsjffff", "_Z18image_scissor_fillPKh", "_Z17undistort_capturePKhPhi",
+                "_Z18scan3d_compat_initPKciiiii", "_Z22scan3d_compat_shutdownv", "_Z17scan3d_compat_ctxv"):
+        assert hasattr(L, sym), sym
+    for glob in ("selected_region", "valid_map", "code_vertical", "unwrapped_phi_horizontal", "c_p_map", "intersection_points",
+                 "number_of_patterns_fringe", "fringe_width_pixels_vertical", "Camera_imagewidth"):
+        C.c_void_p.in_dll(L, glob)
