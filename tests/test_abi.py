@@ -240,3 +240,23 @@ def test_compat_library_exports_the_reference_named_functions():
     for glob in ("selected_region", "valid_map", "code_vertical", "unwrapped_phi_horizontal", "c_p_map", "intersection_points",
                  "number_of_patterns_fringe", "fringe_width_pixels_vertical", "Camera_imagewidth"):
         C.c_void_p.in_dll(L, glob)
+
+
+def test_reference_main_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/m_tech_console.cpp links against the three libraries; without a CUDA device it must stop with the
+    library's error instead of computing anything on the CPU."""
+    import subprocess
+    libdir = os.path.join(ROOT, "3dscan_b200", "lib")
+    exe = str(tmp_path / "m_tech_console")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "m_tech_console.cpp"), "-L", libdir, "-lscan3d_compat",
+                           "-lscan3d_host", "-lscan3d", "-Wl,-rpath," + libdir, "-o", exe])
+    assert subprocess.run([exe], capture_output=True).returncode == 2          # usage
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return
+    except ImportError:
+        pass
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode != 0 and "scan3d_create" in r.stderr

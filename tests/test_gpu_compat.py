@@ -120,3 +120,65 @@ def test_reference_call_sequence(tmp_path):
     pcd = open(f"{root}/Point_cloud/point_cloud_0.pcd").read().splitlines()      # the reference writes both files
     assert pcd[2] == "FIELDS x y z rgb" and pcd[9] == f"POINTS {ref.count}" and len(pcd) == 11 + ref.count
     getattr(L, "_Z22scan3d_compat_shutdownv")()
+
+
+def test_reference_main_program(tmp_path):
+    """examples/m_tech_console.cpp -- the reference's main() (m_tech_project_console.cpp:244-412) minus camera and
+    mouse -- built against libscan3d_compat.so and run as a program on a reference-layout tree at the reference's own
+    configuration (1600x1200 camera, 1280x720 projector, 3-step, 6/5 Gray bits, fw 32): two views, then
+    register_point_clouds.  Every PLY it leaves behind is compared with the oracle."""
+    import subprocess
+    W, H, PW, PH, N, Mv, Mh, fw = 1600, 1200, 1280, 720, 3, 6, 5, 32
+    cal, ocal, c = calibs()
+    cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fw, fw, 2)
+    stack, _ = s3.synth_stack(cfg, cal)
+    d = s3.split_stack(cfg, stack)
+    root = str(tmp_path / "M_tech_project_console")
+    for key, name in (("v", "Vertical"), ("h", "Horizontal")):
+        for i, img in enumerate(d["fringe_" + key]):
+            _bmp(f"{root}/Captured_patterns/Fringe_patterns/{name}/Undistorted/Gray_captured_image_{i}.bmp", img)
+        for i, img in enumerate(d["gray_" + key]):
+            _bmp(f"{root}/Captured_patterns/Coded_patterns/Gray_coded/{name}/Undistorted/Gray_captured_image_{i}.bmp", img)
+        for i, img in enumerate(d["inv_" + key]):
+            _bmp(f"{root}/Captured_patterns/Coded_patterns/Gray_coded/{name}/Undistorted/inverse_Gray_captured_image_{i}.bmp", img)
+    _xml(f"{root}/Camera_calibration/Matrices/cam_intrinsic_mat.xml", "cam_intrinsic_mat", c["Kc"], 3, 3)
+    _xml(f"{root}/Camera_calibration/Matrices/cam_distortion_vect.xml", "cam_distortion_vect", c["dc"], 5, 1)
+    _xml(f"{root}/Projector_calibration/Matrices/proj_intrinsic_mat.xml", "proj_intrinsic_mat", c["Kp"], 3, 3)
+    _xml(f"{root}/Projector_calibration/Matrices/proj_distortion_vect.xml", "proj_distortion_vect", c["dp"], 5, 1)
+    t = f"{root}/Triangulation"
+    _xml(f"{t}/Camera_extrinsic_parametrs/world_to_cam_rot_vect.xml", "world_to_cam_rot_vect", c["rc"], 3, 1)
+    _xml(f"{t}/Camera_extrinsic_parametrs/world_to_cam_trans_vect.xml", "world_to_cam_trans_vect", c["tc"], 3, 1)
+    _xml(f"{t}/Projector_extrinsic_parametrs/world_to_proj_rot_vect.xml", "world_to_proj_rot_vect", c["rp"], 3, 1)
+    _xml(f"{t}/Projector_extrinsic_parametrs/world_to_proj_trans_vect.xml", "world_to_proj_trans_vect", c["tp"], 3, 1)
+    os.makedirs(f"{root}/Point_cloud", exist_ok=True)
+    for sub in ("Fringe_patterns/Vertical", "Fringe_patterns/Horizontal", "Coded_patterns/Gray_coded/Vertical",
+                "Coded_patterns/Gray_coded/Horizontal"):
+        os.makedirs(f"{root}/Generated_patterns/{sub}", exist_ok=True)
+    # the lasso outline image_scissor() would have recorded: two strokes, the fill selects what lies between them
+    outline = np.zeros((H, W), np.uint8)
+    outline[500:700, 600] = 255
+    outline[500:700, 1000] = 255
+    _bmp(f"{root}/i1_outline.bmp", outline)
+    roi, _ = o.roi_fill(outline)
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "m_tech_console")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-I", os.path.join(repo, "include"),
+                           os.path.join(repo, "examples", "m_tech_console.cpp"), "-L", LIBDIR, "-lscan3d_compat",
+                           "-lscan3d_host", "-lscan3d", "-Wl,-rpath," + LIBDIR, "-o", exe])
+    tx, ty, tz, step = 10.0, -5.0, 300.0, 36.0
+    subprocess.check_call([exe, root, "2", str(step), str(tx), str(ty), str(tz)], timeout=300)
+
+    ref = run_oracle(cfg, ocal, stack, roi)
+    assert ref.count > 50000
+
+    def ply_xyz(path):
+        body = open(path).read().split("end_header\n")[1]
+        return np.loadtxt(body.splitlines(), dtype=np.float64)[:, :3].astype(np.float32)
+
+    for i in (0, 1):
+        assert np.array_equal(ply_xyz(f"{root}/Point_cloud/point_cloud_{i}.ply"), ref.pts)
+    reg = ply_xyz(f"{root}/Point_cloud/registered_point_cloud.ply")
+    want = np.concatenate([o.register_points(ref.pts, 0.0, tx, ty, tz), o.register_points(ref.pts, step, tx, ty, tz)])
+    assert np.array_equal(reg.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(s3.read_bmp8(f"{root}/i1.bmp") != 0, (roi != 0) | (outline != 0))
