@@ -95,6 +95,10 @@ constexpr int regs7(int cw, int minb)
 
 // back-off of the IO warp's event loop between empty polls (experimental knob, tools/build_variants.py: the three
 // IO warps of an SM issue ~10 % of the kernel's instructions, most of them polling)
+// S3D_VAR_PASS_UNROLL=1: both 2-pixel decode passes unrolled (8 independent FP64 chains per thread, ~600 more instructions)
+#ifndef S3D_VAR_PASS_UNROLL
+#define S3D_VAR_PASS_UNROLL 0
+#endif
 #ifndef S3D_VAR_IO_SLEEP_NS
 #define S3D_VAR_IO_SLEEP_NS 250
 #endif
@@ -456,7 +460,11 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
             // directions interleave in the FP64 pipe); the pass loop is rolled to keep the
             // consumer loop inside the instruction cache.
             const size_t g = (size_t)p0 + lp0;
+#if S3D_VAR_PASS_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int h = 0; h < 2; h++) {
                 float r_unwv[2], r_unwh[2];
                 int r_cv[2], r_ch[2];

@@ -18,6 +18,7 @@ VARIANTS = {
     "rowsel": "-DS3D_VAR_ROWSEL_RCP=1",
     "rot": "-DS3D_VAR_TERM_ROTATE=1",
     "all": "-DS3D_VAR_COLD_OUTLINE=1 -DS3D_VAR_ROWSEL_RCP=1 -DS3D_VAR_TERM_ROTATE=1",
+    "pass4": "-DS3D_VAR_PASS_UNROLL=1",
     "io500": "-DS3D_VAR_IO_SLEEP_NS=500",
     "io1000": "-DS3D_VAR_IO_SLEEP_NS=1000",
     # capture-side remap (scan3d_aux_kernels.cu; timed by tools/bench_aux.py, checked by tests/aux_check_runner.py)
