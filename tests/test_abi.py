@@ -260,3 +260,12 @@ def test_reference_main_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
         pass
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert r.returncode != 0 and "scan3d_create" in r.stderr
+
+
+def test_colour_bmp_loads_as_the_grey_image_opencv_returns(tmp_path):
+    """cvLoadImage(file, CV_LOAD_IMAGE_GRAYSCALE) on a 24-bit BMP (3/wrapped_phase.cpp:44, 4/phase_unwrap.cpp:78-90):
+    scan3d_read_bmp8 gives the same bytes as cv2.imread(..., IMREAD_GRAYSCALE) (fixed-point BGR weights, padded rows)."""
+    g = np.load(os.path.join(GOLDEN, "f4_kat.npz"))
+    p = tmp_path / "colour.bmp"
+    p.write_bytes(g["bmp24_bytes"].tobytes())
+    assert np.array_equal(s3.read_bmp8(str(p)), g["bmp24_grey"])

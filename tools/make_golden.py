@@ -123,6 +123,15 @@ def make_f4():
     kat["i1_count"] = m.sum(1).astype(np.int32)
     kat["i1_first"] = np.where(m.any(1), np.where(m, cols, m.shape[1]).min(1), 0).astype(np.int32)
     kat["i1_last"] = np.where(m.any(1), np.where(m, cols, -1).max(1), -1).astype(np.int32)
+    # cvLoadImage(..., CV_LOAD_IMAGE_GRAYSCALE) of a colour BMP (3/wrapped_phase.cpp:44, 4/phase_unwrap.cpp:78-90): the
+    # file bytes of a small 24-bit BMP (odd width: padded rows) and the grey image cv2.imread returns for it
+    import tempfile
+    col = rng.integers(0, 256, (9, 33, 3), dtype=np.uint8)
+    col[0, :16] = np.array([[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255], [1, 1, 1], [254, 254, 254], [128, 127, 129]] * 2, np.uint8)
+    path = os.path.join(tempfile.mkdtemp(), "colour.bmp")
+    assert cv2.imwrite(path, col)
+    kat["bmp24_bytes"] = np.frombuffer(open(path, "rb").read(), np.uint8)
+    kat["bmp24_grey"] = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
     np.savez_compressed(os.path.join(OUT, "f4_kat.npz"), **kat)
 
 
