@@ -1,4 +1,6 @@
-// scan3d_fused_kernel.cu -- the hot path: ONE persistent kernel that takes the captured pattern
+// scan3d_fused_kernel.cu -- FIRST GENERATION of the fused kernel (selected with SCAN3D_FUSED_IMPL=6, kept as the
+// measured baseline of DESIGN.md section 7; the default is k_fused7 in scan3d_fused_kernel7.cu) plus the work-list
+// kernels both generations share.  ONE persistent kernel that takes the captured pattern
 // stack to absolute phase maps, fringe orders, c_p_map, validity and the raster-ordered compacted
 // point cloud, reading every input byte once and writing every contract output once.
 //

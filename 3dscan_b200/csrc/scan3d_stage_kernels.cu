@@ -1,6 +1,6 @@
 // scan3d_stage_kernels.cu -- one plain kernel per reference stage (any frame shape).  These back
 // the stage-by-stage C ABI (scan3d_compute_wrapped_phase ... scan3d_compact_points) and are the
-// shape-generic path; the benchmarked single-pass kernel lives in scan3d_fused_kernel.cu.
+// shape-generic path; the benchmarked single-pass kernel lives in scan3d_fused_kernel7.cu.
 #include <math.h>
 
 #include "scan3d_internal.h"
