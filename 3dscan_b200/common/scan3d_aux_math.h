@@ -193,6 +193,44 @@ S3A_HD uint32_t remap_group_blend(const RemapGroup& g, const uint32_t* row0, con
     return packed;
 }
 
+// ---- tiled staging (experimental remap variant, S3D_VAR_REMAP_TILED) ---------------------------------------
+// A CTA owns an output tile of TILE_H x TILE_W pixels.  The source pixels its taps touch form a bounding box that
+// is barely larger than the tile (the map is close to the identity); per frame that box is staged in shared
+// memory with aligned 16-byte copies and the taps are gathered from there.  The box is frame-independent.
+constexpr int REMAP_TILE_W = 256, REMAP_TILE_H = 8;      // output tile
+constexpr int REMAP_BOX_W = 288, REMAP_BOX_H = 16;       // staging buffer (bytes per row, rows)
+
+struct RemapBox {
+    int ok;         // 1: the box fits the buffer (it may reach outside the image: those vectors are staged as zeros,
+                    //    which is cv::remap's constant border)
+    int x0, y0;     // first staged source column (multiple of 16) and row
+    int w, rows;    // staged bytes per row (multiple of 16, <= REMAP_BOX_W) and rows (<= REMAP_BOX_H)
+};
+
+// minx..maxx / miny..maxy: extremes of the map's integer source coordinates (sx, sy) over the tile's pixels
+S3A_HD RemapBox remap_tile_box(int minx, int maxx, int miny, int maxy, int W, int H)
+{
+    RemapBox b;
+    b.x0 = minx & ~15;
+    b.y0 = miny;
+    b.w = ((maxx + 1 - b.x0 + 1) + 15) & ~15;      // taps reach column maxx + 1
+    b.rows = maxy + 1 - miny + 1;                   // ... and row maxy + 1
+    b.ok = (W % 16 == 0) && b.w <= REMAP_BOX_W && b.rows <= REMAP_BOX_H && b.w > 0 && b.rows > 0;
+    (void)H;
+    return b;
+}
+
+// is the 16-byte vector at staged row r, vector column c inside the image?  (x0 and W are multiples of 16, so a
+// vector is inside or outside as a whole)
+S3A_HD bool remap_box_vector_inside(const RemapBox& b, int r, int c, int W, int H)
+{
+    const int y = b.y0 + r, x = b.x0 + 16 * c;
+    return y >= 0 && y < H && x >= 0 && x + 16 <= W;
+}
+
+// offset of source pixel (sx, sy) inside the staging buffer (row pitch REMAP_BOX_W)
+S3A_HD int remap_box_offset(const RemapBox& b, int sx, int sy) { return (sy - b.y0) * REMAP_BOX_W + (sx - b.x0); }
+
 // register_point_clouds' rotation about Y for a cloud captured at turntable angle theta (degrees,
 // float): R(0,0) = R(2,2) = (float)cos(theta*Pi/180.0), R(0,2) = (float)(-1.0f*sin(...)),
 // R(2,0) = (float)sin(...), with the reference's Pi = 22.0/7.0 (global_cv.h:62, expanded textually:

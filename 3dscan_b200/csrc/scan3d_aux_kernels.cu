@@ -20,6 +20,14 @@
 #ifndef S3D_VAR_REMAP_WINDOW
 #define S3D_VAR_REMAP_WINDOW 0
 #endif
+//   S3D_VAR_REMAP_TILED     2-D output tiles, the tile's source box staged in shared memory per frame with 16-byte
+//                           cp.async copies (double-buffered over the frame loop), taps gathered from shared memory
+#ifndef S3D_VAR_REMAP_TILED
+#define S3D_VAR_REMAP_TILED 0
+#endif
+#ifndef S3D_VAR_REMAP_TILED_MINB
+#define S3D_VAR_REMAP_TILED_MINB 3      // CTAs per SM the tiled kernel is compiled for (3: 80 registers, 76 B of spill; 2: 128, none)
+#endif
 #define S3D_PRAGMA_(x) _Pragma(#x)
 #if S3D_VAR_REMAP_UNROLL > 1
 #define S3D_UNROLL_N_(n) S3D_PRAGMA_(unroll n)
@@ -118,6 +126,127 @@ __global__ void __launch_bounds__(256) k_remap_frames(const uint8_t* __restrict_
     }
 }
 
+#if S3D_VAR_REMAP_TILED
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One CTA (256 threads) per output tile of REMAP_TILE_H x REMAP_TILE_W pixels; thread t owns the 4-pixel groups
+// (row t/64, columns 4*(t%64)..+3) and (row t/64 + 4, same columns).  W % 16 == 0.
+__global__ void __launch_bounds__(256, S3D_VAR_REMAP_TILED_MINB) k_remap_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                      const short2* __restrict__ map_xy, const uint16_t* __restrict__ map_frac,
+                                                      int W, int H, int n_frames)
+{
+    __shared__ __align__(16) uint8_t box[2][s3a::REMAP_BOX_H * s3a::REMAP_BOX_W];
+    __shared__ int ext[4];   // min sx, max sx, min sy, max sy over the tile
+    const size_t plane = (size_t)W * H;
+    const int tiles_x = (W + s3a::REMAP_TILE_W - 1) / s3a::REMAP_TILE_W;
+    const int tx0 = (blockIdx.x % tiles_x) * s3a::REMAP_TILE_W, ty0 = (blockIdx.x / tiles_x) * s3a::REMAP_TILE_H;
+    const int t = threadIdx.x;
+    short2 xy[2][4];
+    int fr[2][4];
+    bool have[2];
+    size_t pix[2];
+    int lo_x = 0x7fffffff, hi_x = -0x7fffffff, lo_y = 0x7fffffff, hi_y = -0x7fffffff;
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+        const int x = tx0 + 4 * (t & 63), y = ty0 + (t >> 6) + 4 * g;
+        have[g] = x < W && y < H;     // W % 4 == 0: a group is inside or outside as a whole
+        pix[g] = (size_t)y * W + x;
+        if (have[g]) {
+            const int4 m = __ldg(reinterpret_cast<const int4*>(map_xy + pix[g]));
+            const int mm[4] = {m.x, m.y, m.z, m.w};
+            const uint2 f = __ldg(reinterpret_cast<const uint2*>(map_frac + pix[g]));
+            fr[g][0] = f.x & 0xffff; fr[g][1] = f.x >> 16; fr[g][2] = f.y & 0xffff; fr[g][3] = f.y >> 16;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                xy[g][k].x = (short)(mm[k] & 0xffff);
+                xy[g][k].y = (short)(mm[k] >> 16);
+                lo_x = min(lo_x, (int)xy[g][k].x); hi_x = max(hi_x, (int)xy[g][k].x);
+                lo_y = min(lo_y, (int)xy[g][k].y); hi_y = max(hi_y, (int)xy[g][k].y);
+            }
+        }
+    }
+    if (t == 0) { ext[0] = 0x7fffffff; ext[1] = -0x7fffffff; ext[2] = 0x7fffffff; ext[3] = -0x7fffffff; }
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+        lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+    }
+    if ((t & 31) == 0) { atomicMin(&ext[0], lo_x); atomicMax(&ext[1], hi_x); atomicMin(&ext[2], lo_y); atomicMax(&ext[3], hi_y); }
+    __syncthreads();
+    const s3a::RemapBox b = s3a::remap_tile_box(ext[0], ext[1], ext[2], ext[3], W, H);
+
+    if (!b.ok) {   // strong distortion (the box does not fit): per-tap gathers from global memory, as k_remap_frames
+        for (int f = 0; f < n_frames; f++) {
+            const uint8_t* s = src + (size_t)f * plane;
+#pragma unroll
+            for (int g = 0; g < 2; g++) {
+                if (!have[g]) continue;
+                uint32_t packed = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int x = xy[g][k].x, y = xy[g][k].y;
+                    packed |= (uint32_t)s3a::bilinear_u8(tap(s, W, H, x, y), tap(s, W, H, x + 1, y), tap(s, W, H, x, y + 1),
+                                                         tap(s, W, H, x + 1, y + 1), fr[g][k]) << (8 * k);
+                }
+                *reinterpret_cast<uint32_t*>(dst + (size_t)f * plane + pix[g]) = packed;
+            }
+        }
+        return;
+    }
+
+    const int vec_per_row = b.w >> 4, n_vec = b.rows * vec_per_row;
+    auto stage = [&](int f, int buf) {
+        const uint8_t* s = src + (size_t)f * plane;
+        for (int v = t; v < n_vec; v += 256) {
+            const int r = v / vec_per_row, c = v - r * vec_per_row;
+            uint8_t* d = &box[buf][r * s3a::REMAP_BOX_W + 16 * c];
+            if (s3a::remap_box_vector_inside(b, r, c, W, H))
+                cp_async16(d, s + (long long)(b.y0 + r) * W + (b.x0 + 16 * c));
+            else
+                *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);     // constant border
+        }
+        cp_async_commit();
+    };
+    int off[2][4];
+#pragma unroll
+    for (int g = 0; g < 2; g++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) off[g][k] = have[g] ? s3a::remap_box_offset(b, xy[g][k].x, xy[g][k].y) : 0;
+
+    stage(0, 0);
+    for (int f = 0; f < n_frames; f++) {
+        const int buf = f & 1;
+        if (f + 1 < n_frames) {
+            stage(f + 1, buf ^ 1);     // the other buffer was released by the barrier that closed frame f - 1
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const uint8_t* sb = box[buf];
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            if (!have[g]) continue;
+            uint32_t packed = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint8_t* p = sb + off[g][k];
+                packed |= (uint32_t)s3a::bilinear_u8(p[0], p[1], p[s3a::REMAP_BOX_W], p[s3a::REMAP_BOX_W + 1], fr[g][k]) << (8 * k);
+            }
+            *reinterpret_cast<uint32_t*>(dst + (size_t)f * plane + pix[g]) = packed;
+        }
+        __syncthreads();
+    }
+}
+#endif
+
 // One CTA per row.  The reference's nested search (start pixel, next non-zero pixel, fill between,
 // restart AT the end pixel) fills every zero pixel that lies strictly between the first and the last
 // non-zero pixel of the row; outline pixels themselves stay unselected.
@@ -187,6 +316,13 @@ cudaError_t launch_remap_frames(const uint8_t* src, uint8_t* dst, const short2* 
                                 int H, int n_frames, int sm_count, cudaStream_t st)
 {
     const size_t plane = (size_t)W * H;
+#if S3D_VAR_REMAP_TILED
+    if (W % 16 == 0 && (((uintptr_t)src | (uintptr_t)dst) % 16 == 0)) {
+        const int tiles = ((W + s3a::REMAP_TILE_W - 1) / s3a::REMAP_TILE_W) * ((H + s3a::REMAP_TILE_H - 1) / s3a::REMAP_TILE_H);
+        k_remap_tiled<<<tiles, 256, 0, st>>>(src, dst, map_xy, map_frac, W, H, n_frames);
+        return cudaGetLastError();
+    }
+#endif
     const bool vec = (plane % 4 == 0) && (((uintptr_t)src | (uintptr_t)dst) % 4 == 0);
     const size_t groups = vec ? plane / 4 : plane;
     size_t blocks = (groups + 255) / 256;

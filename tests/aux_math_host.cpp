@@ -57,6 +57,50 @@ long long s3a_host_remap_window(const uint8_t* src, int W, int H, const int16_t*
     return n_fast;
 }
 
+// k_remap_tiled (S3D_VAR_REMAP_TILED): per output tile the source box from the map's extremes, the box staged in a
+// buffer with the kernel's pitch, taps gathered from the buffer; tiles whose box does not qualify take the per-tap path.
+// Returns the number of tiles that were staged.
+long long s3a_host_remap_tiled(const uint8_t* src, int W, int H, const int16_t* xy, const uint16_t* frac, uint8_t* dst)
+{
+    using namespace s3a;
+    static uint8_t box[REMAP_BOX_H * REMAP_BOX_W];
+    long long staged = 0;
+    for (int ty0 = 0; ty0 < H; ty0 += REMAP_TILE_H)
+        for (int tx0 = 0; tx0 < W; tx0 += REMAP_TILE_W) {
+            int lo_x = 0x7fffffff, hi_x = -0x7fffffff, lo_y = 0x7fffffff, hi_y = -0x7fffffff;
+            for (int y = ty0; y < ty0 + REMAP_TILE_H && y < H; y++)
+                for (int x = tx0; x < tx0 + REMAP_TILE_W && x < W; x++) {
+                    const int sx = xy[2 * ((size_t)y * W + x)], sy = xy[2 * ((size_t)y * W + x) + 1];
+                    lo_x = sx < lo_x ? sx : lo_x; hi_x = sx > hi_x ? sx : hi_x;
+                    lo_y = sy < lo_y ? sy : lo_y; hi_y = sy > hi_y ? sy : hi_y;
+                }
+            const RemapBox b = remap_tile_box(lo_x, hi_x, lo_y, hi_y, W, H);
+            if (b.ok) {
+                staged++;
+                memset(box, 0xAA, sizeof(box));      // anything not staged must never be read
+                for (int r = 0; r < b.rows; r++)
+                    for (int c = 0; c < b.w / 16; c++) {
+                        uint8_t* d = box + r * REMAP_BOX_W + 16 * c;
+                        if (remap_box_vector_inside(b, r, c, W, H)) memcpy(d, src + (long long)(b.y0 + r) * W + (b.x0 + 16 * c), 16);
+                        else memset(d, 0, 16);
+                    }
+            }
+            for (int y = ty0; y < ty0 + REMAP_TILE_H && y < H; y++)
+                for (int x = tx0; x < tx0 + REMAP_TILE_W && x < W; x++) {
+                    const size_t p = (size_t)y * W + x;
+                    const int sx = xy[2 * p], sy = xy[2 * p + 1];
+                    if (b.ok) {
+                        const uint8_t* q = box + remap_box_offset(b, sx, sy);
+                        dst[p] = bilinear_u8(q[0], q[1], q[REMAP_BOX_W], q[REMAP_BOX_W + 1], frac[p]);
+                    } else {
+                        dst[p] = bilinear_u8(tap(src, W, H, sx, sy), tap(src, W, H, sx + 1, sy), tap(src, W, H, sx, sy + 1),
+                                             tap(src, W, H, sx + 1, sy + 1), frac[p]);
+                    }
+                }
+        }
+    return staged;
+}
+
 void s3a_host_register_rotation(float theta_deg, float* R) { s3a::register_rotation(theta_deg, R); }
 
 void s3a_host_register_points(float* xyz, long long n, float theta_deg, float tx, float ty, float tz)

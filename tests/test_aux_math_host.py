@@ -88,6 +88,27 @@ def test_window_gather_variant_matches_oracle(shim):
             assert n_fast == 0
 
 
+def test_tiled_staging_variant_matches_oracle(shim):
+    """The experimental tiled remap (S3D_VAR_REMAP_TILED: the tile's source box staged in a buffer, taps gathered from
+    it) gives the same pixels; with the reference's calibration almost every tile qualifies for staging."""
+    shim.s3a_host_remap_tiled.restype = C.c_longlong
+    rng = np.random.default_rng(7)
+    c = load_calib_c1()
+    K12 = c["Kc"].reshape(3, 3) * np.array([[2.56], [2.56], [1.0]])
+    cases = [(1600, 1200, c["Kc"].reshape(3, 3), c["dc"], 0.99), (4096, 64, K12, c["dc"], 0.9),
+             (640, 480, c["Kc"].reshape(3, 3) * np.array([[0.4], [0.4], [1.0]]), c["dc"] * 8, 0.0),
+             (800, 48, np.array([[700.0, 0.7, 400.0], [0, 705.0, 20.0], [0, 0, 1]]), np.array([-0.3, 0.1, 0.01, -0.01, 0.0]), 0.0),
+             (1280, 720, c["Kp"].reshape(3, 3), c["dp"], 0.95)]
+    for W, H, K, d, min_staged in cases:
+        xy, fr = _host_map(shim, K, d, W, H)
+        img = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        out = np.zeros_like(img)
+        staged = shim.s3a_host_remap_tiled(_p(img), W, H, _p(xy), _p(fr), _p(out))
+        assert np.array_equal(out, o.undistort_frames(img[None], K, d)[0]), (W, H)
+        tiles = -(-W // 256) * -(-H // 8)
+        assert staged >= min_staged * tiles, (W, H, staged, tiles)
+
+
 def test_oracle_undistort_matches_cv2_golden(shim):
     g = np.load(os.path.join(GOLDEN, "f4_kat.npz"))
     for i in range(int(g["n_undistort"])):

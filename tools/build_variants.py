@@ -24,6 +24,8 @@ VARIANTS = {
     # capture-side remap (scan3d_aux_kernels.cu; timed by tools/bench_aux.py, checked by tests/aux_check_runner.py)
     "remapu2": "-DS3D_VAR_REMAP_UNROLL=2",
     "remapwin": "-DS3D_VAR_REMAP_WINDOW=1 -DS3D_VAR_REMAP_UNROLL=2",
+    "remaptile": "-DS3D_VAR_REMAP_TILED=1",
+    "remaptile2": "-DS3D_VAR_REMAP_TILED=1 -DS3D_VAR_REMAP_TILED_MINB=2",
 }
 KERNEL = "k_fused7ILi8ELi2ELi7ELi3ELb0"
 
