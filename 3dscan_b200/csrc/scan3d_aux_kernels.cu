@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(256, S3D_VAR_REMAP_TILED_MINB) k_remap_tiled(c
 #pragma unroll
         for (int k = 0; k < 4; k++) off[g][k] = have[g] ? s3a::remap_box_offset(b, xy[g][k].x, xy[g][k].y) : 0;
 
+    if (n_frames <= 0) return;
     stage(0, 0);
     for (int f = 0; f < n_frames; f++) {
         const int buf = f & 1;
