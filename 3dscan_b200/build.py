@@ -29,7 +29,7 @@ if os.environ.get("SCAN3D_BUILD_TRACE") == "1":
 # SCAN3D_BUILD_DEFS="-DS3D_VAR_X=1 ...": experimental kernel variants (tools/build_variants.py builds them into
 # their own SCAN3D_LIBDIR; the default build defines none of them)
 NVCC_FLAGS += [d for d in os.environ.get("SCAN3D_BUILD_DEFS", "").split() if d.startswith("-D")]
-CU_SOURCES = ["scan3d_api.cu", "scan3d_stage_kernels.cu", "scan3d_fused_kernel.cu", "scan3d_fused_kernel7.cu",
+CU_SOURCES = ["scan3d_api.cu", "scan3d_stage_kernels.cu", "scan3d_fused_kernel.cu", "scan3d_fused_kernel7.cu", "scan3d_fused_kernel8.cu",
               "scan3d_aux_kernels.cu", "scan3d_aux_api.cu"]
 HOST_SOURCES = ["scan3d_io.cpp", "scan3d_synth.cpp"]
 COMPAT_SOURCES = ["scan3d_stages.cpp"]
@@ -56,18 +56,23 @@ def build_cuda(force=False, verbose=False):
     hdr = os.path.join(HERE, "..", "include", "scan3d.h")
     if not (force or _stale(so, _deps(CSRC, [hdr]))):
         return so
-    objs = []
-    for src in CU_SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(LIB, src.replace(".cu", ".o"))
         cmd = [NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
+        # registers / spills of every kernel, without ptxas' timing lines (the log is diffable between builds)
         with open(os.path.join(LIB, src + ".ptxas.log"), "w") as f:
-            f.write(r.stderr)
+            f.write("".join(l + "\n" for l in r.stderr.splitlines() if "Compile time" not in l))
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed on " + src)
-        objs.append(obj)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(CU_SOURCES), os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, CU_SOURCES))
     cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
            "-ccbin", "/usr/bin/g++", "-o", so] + objs
     subprocess.check_call(cmd)

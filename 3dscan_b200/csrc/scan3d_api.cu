@@ -155,6 +155,8 @@ int scan3d_create(const scan3d_config* cfg, int device, scan3d_ctx** out)
             CK(dalloc(&ctx->trace, (size_t)1024 * 64 * 8));
             CK(cudaMemsetAsync(ctx->trace, 0, (size_t)1024 * 64 * 8 * 8, ctx->stream));
         }
+        CK(dalloc(&ctx->sched_ctr, 4));
+        CK(cudaMemsetAsync(ctx->sched_ctr, 0, 16, ctx->stream));
         CK(dalloc(&ctx->tile_flags, (size_t)ntiles + 16));
         CK(dalloc(&ctx->tile_list, (size_t)ntiles + 16));
         CK(dalloc(&ctx->atan_tab, (size_t)ATAN_TAB_DOUBLES));
@@ -204,7 +206,7 @@ void scan3d_destroy(scan3d_ctx* ctx)
     void* ptrs[] = {ctx->cam_lut, ctx->proj_lut, ctx->atan_tab, ctx->nstep_w, ctx->wrapped[0], ctx->wrapped[1],
                     ctx->unwrapped[0], ctx->unwrapped[1], ctx->code[0], ctx->code[1], ctx->mask[0],
                     ctx->mask[1], ctx->valid, ctx->cpmap, ctx->xyz, ctx->pts, ctx->pix, ctx->rgb,
-                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff, ctx->pattern_profiles,
+                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->sched_ctr, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff, ctx->pattern_profiles,
                     ctx->undist_xy[0], ctx->undist_xy[1], ctx->undist_frac[0], ctx->undist_frac[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -505,11 +507,20 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     }
     a.W = c.W; a.H = c.H; a.row0 = c.row0; a.H_total = c.H_total; a.PW = c.PW; a.PH = c.PH;
     a.N = c.N; a.M_v = c.M_v; a.M_h = c.M_h; a.fw_v = c.fw_v; a.fw_h = c.fw_h;
-    const char* impl = getenv("SCAN3D_FUSED_IMPL");
-    const bool use7 = (!impl || atoi(impl) != 6) && fused7_supported(c);
-    if (use7) CK(launch_fused7(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
-    else CK(launch_fused(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
-    ctx->launches += 3;   // work-list flags, work-list scan, persistent fused kernel
+    static const int impl = getenv("SCAN3D_FUSED_IMPL") ? atoi(getenv("SCAN3D_FUSED_IMPL")) : 8;
+    if (impl >= 8 && fused8_supported(c)) {
+        a.sched_ctr = ctx->sched_ctr;
+        a.pos_base = ctx->sched_base;
+        uint32_t advance = 0;
+        CK(launch_fused8(c, a, ctx->dcal, ctx->sm_count, &ctx->tmaps, &advance, ctx->stream));
+        ctx->sched_base += advance;
+        ctx->launches += 1;   // the one persistent kernel
+    } else {
+        const bool use7 = impl != 6 && fused7_supported(c);
+        if (use7) CK(launch_fused7(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
+        else CK(launch_fused(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
+        ctx->launches += 3;   // work-list flags, work-list scan, persistent fused kernel
+    }
     ctx->have_wrapped[0] = ctx->have_wrapped[1] = false;
     ctx->have_unwrapped[0] = true;
     ctx->have_unwrapped[1] = c.dirs == 2;

@@ -1,5 +1,6 @@
 // scan3d_internal.h -- context layout and kernel launcher declarations (not part of the ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -9,6 +10,16 @@
 #include "scan3d_math.cuh"
 
 #define S3D_PLANE_MASK_H 10   // internal: valid_map_horizontal when the stage API is used
+
+namespace s3d {
+// k_fused8: tensor maps of the last few capture stacks (a map depends on the stack's address only)
+struct Fused8Cache {
+    static constexpr int SLOTS = 8;
+    const uint8_t* stack[SLOTS] = {};
+    alignas(64) CUtensorMap map[SLOTS];
+    int next = 0;
+};
+}  // namespace s3d
 
 struct scan3d_ctx {
     scan3d_config cfg{};
@@ -56,6 +67,9 @@ struct scan3d_ctx {
     int* tile_list = nullptr;
     unsigned long long* trace = nullptr;       // SCAN3D_TRACE=1: per-CTA pipeline timeline
     uint32_t epoch = 0;
+    uint32_t* sched_ctr = nullptr;             // k_fused8: work-position counter, never reset ...
+    uint32_t sched_base = 0;                   // ... its value at the next launch (advances by n_tiles + grid per launch)
+    s3d::Fused8Cache tmaps;
 
     // staging for the host-buffer entries
     uint8_t* d_stack = nullptr;
@@ -123,6 +137,8 @@ struct FusedArgs {
     int* tile_list;               // [n_tiles] ids of those tiles, raster order
     int* n_list;                  // [1]; n_list[n_tiles + 8] is the dynamic scheduler's counter
     int dynamic;                  // v7: draw work-list positions from that counter instead of b, b+G, ...
+    uint32_t* sched_ctr;          // v8: work-position counter (monotonic across launches)
+    uint32_t pos_base;            // v8: the counter's value when this launch starts
     int use_tmap;                 // v7: tile loads are one 2-D tensor copy (set by the launcher)
     unsigned long long* trace;    // optional timeline buffer (SCAN3D_TRACE), else null
     const double2* cam_lut; const double2* proj_lut;
@@ -141,6 +157,12 @@ cudaError_t launch_fused(const scan3d_config& c, const FusedArgs& a, const Devic
 bool fused7_supported(const scan3d_config& c);
 cudaError_t launch_fused7(const scan3d_config& c, const FusedArgs& a, const DeviceCalib& cal,
                           int sm_count, cudaStream_t st);
+
+// third cut (scan3d_fused_kernel8.cu, the default): one launch per scan, no consumer barrier.  *advance = how far
+// the launch moves the context's work-position counter
+bool fused8_supported(const scan3d_config& c);
+cudaError_t launch_fused8(const scan3d_config& c, const FusedArgs& a, const DeviceCalib& cal, int sm_count,
+                          Fused8Cache* cache, uint32_t* advance, cudaStream_t st);
 
 // ---- either side of the path (scan3d_aux_kernels.cu) ----
 cudaError_t launch_undistort_map(const double K[9], const double d[5], int W, int H, short2* map_xy, uint16_t* map_frac,

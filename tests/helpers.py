@@ -32,6 +32,11 @@ def load_c1_crop():
     return dict(np.load(os.path.join(GOLDEN, "c1_crop.npz")))
 
 
+def load_c1_full():
+    """The reference's whole captured scan (tools/make_golden.py c1full)."""
+    return dict(np.load(os.path.join(GOLDEN, "c1_full.npz")))
+
+
 def read_bmp8(path):
     b = open(path, "rb").read()
     off = int.from_bytes(b[10:14], "little")

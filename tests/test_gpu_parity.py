@@ -1,12 +1,14 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the
 same seeded inputs.  Bar (BASELINE.json north_star): Gray codes / fringe orders / validity
 bit-exact; unwrapped phase within 1e-4 rad; 3-D points within 1e-5 relative."""
+import os
+
 import numpy as np
 import pytest
 
 import oracle_ffi as o
 from gpu_common import calibs, compare, run_oracle, s3
-from helpers import load_c1_crop
+from helpers import load_c1_crop, load_c1_full
 
 pytestmark = pytest.mark.gpu
 
@@ -332,6 +334,44 @@ def test_c1_crop_through_gpu_matches_reference_images():
     m[:, 0] = m[:, -1] = False
     img = o.unwrapped_image(unw, m.astype(np.int32), 40)
     assert np.array_equal(img[m], d["golden_unwrapped_v"][m])
+    print(st)
+    ctx.close()
+
+
+def test_c1_full_capture_through_gpu_matches_reference_images():
+    """BASELINE.json configs[0] at its own size: the reference's whole 1600x1200 captured scan (28 frames,
+    tests/golden/c1_full.npz) through scan3d_reconstruct -- both stored unwrapped-phase images and the
+    wrapped-phase image come out bit for bit, everything else equals the oracle on the same input."""
+    d = load_c1_full()
+    H, W = d["golden_wrapped_v"].shape
+    assert (W, H) == (1600, 1200)
+    cal, ocal, _ = calibs()
+    cfg = s3.make_config(W, H, 1280, 720, 3, 6, 5, 32, 32, 2)
+    ctx = _ctx(cfg, cal)
+    roi = (d["golden_wrapped_v"] != 0).astype(np.uint8)   # the reference's post-recurrence mask
+    stack = np.concatenate([d["fringe_v"], d["gray_v"], d["inv_v"], d["fringe_h"], d["gray_h"], d["inv_h"]])
+    ref = run_oracle(cfg, ocal, stack, roi)
+    n = ctx.reconstruct(stack, roi)
+    assert ctx.launch_count() == 1 or os.environ.get("SCAN3D_FUSED_IMPL") in ("6", "7")   # the single-pass kernel, one launch
+    st = compare(cfg, ref, ctx)
+    assert st["unw_v_nonidentical"] == 0 and st["unw_h_nonidentical"] == 0 and st["pts_nonidentical"] == 0
+    assert n == ref.count and n > 300000
+    for k, key, codes in ((0, "v", 40), (1, "h", 23)):
+        unw = ctx.plane(s3.PLANE_UNWRAPPED_V + k)
+        m = (ref.valid_v if k == 0 else ref.valid_h) == 1
+        if k == 0:
+            m[:, 0] = m[:, -1] = False
+        else:
+            m[0, :] = m[-1, :] = False
+        img = o.unwrapped_image(unw, m.astype(np.int32), codes)
+        assert np.array_equal(img[m], d["golden_unwrapped_" + key][m]), key
+    # stage entry on the full frame: the stored wrapped-phase image
+    for k, key in ((0, "v"), (1, "h")):
+        ctx.compute_wrapped_phase(k, d["fringe_" + key], roi)
+        w = ctx.plane(s3.PLANE_WRAPPED_V + k)
+        m = roi == 1
+        dbg = (128.0 + 127.0 * (w.astype(np.float64) / (22.0 / 7.0))).astype(np.float32).astype(np.int32).astype(np.uint8)
+        assert np.array_equal(dbg[m], d["golden_wrapped_" + key][m])
     print(st)
     ctx.close()
 

@@ -8,6 +8,8 @@ importable); the GPU box has neither, so the outputs are committed:
                               fringe/Gray/inverse-Gray u8 stacks for both directions, plus the
                               matching crops of the reference's stored Wrapped_phase_image.bmp
                               and Unwrapped_phase_*.bmp (the stage-3/4 golden outputs).
+  tests/golden/c1_full.npz    the same scan uncropped (1600x1200, 28 frames + the four stored images), for the
+                              full-frame GPU test; `make_golden.py c1full` makes only this.
   tests/golden/calib_c1.json  the 8 calibration matrices (stage-7 input) + Relative_geometry
                               KAT (6/system_calibration.cpp:1489-1504 output).
   tests/golden/opencv_kat.npz known answers computed with cv2 4.13 for the OpenCV arithmetic
@@ -135,8 +137,23 @@ def make_f4():
     np.savez_compressed(os.path.join(OUT, "f4_kat.npz"), **kat)
 
 
+def make_c1_full():
+    """tests/golden/c1_full.npz: the reference's whole 1600x1200 captured scan (28 grey frames, both directions)
+    and its stored stage-3/4 images, losslessly packed -- the GPU box has no /root/reference."""
+    d = {"config": np.array([3, 6, 5, 32, 32, 40, 23, 1280, 720])}  # N,M_v,M_h,fw_v,fw_h,codes_v,codes_h,PW,PH
+    for name, M, key in (("Vertical", 6, "v"), ("Horizontal", 5, "h")):
+        fr, g, gi, gw, gu = load_c1_direction(name, M)
+        d[f"fringe_{key}"], d[f"gray_{key}"], d[f"inv_{key}"] = fr, g, gi
+        d[f"golden_wrapped_{key}"], d[f"golden_unwrapped_{key}"] = gw, gu
+    np.savez_compressed(os.path.join(OUT, "c1_full.npz"), **d)
+
+
 def main():
     import cv2
+    if len(sys.argv) > 1 and sys.argv[1] == "c1full":
+        make_c1_full()
+        print("c1_full.npz", os.path.getsize(os.path.join(OUT, "c1_full.npz")))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "f4":
         make_f4()
         print("f4_kat.npz", os.path.getsize(os.path.join(OUT, "f4_kat.npz")))
