@@ -36,6 +36,20 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
         : "memory");
     return done != 0;
 }
+// non-blocking probe: for a warp whose lanes look at DIFFERENT barriers (try_wait would suspend the whole warp
+// on the slowest lane's barrier)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 // (A non-blocking mbarrier.test_wait probe in the IO warp's event loop measured 4-10 % SLOWER than
 // try_wait, whose hardware suspend keeps the polling warp out of the issue slots.)
 // poll with back-off so that a waiting warp does not steal issue slots from the computing ones

@@ -29,7 +29,9 @@
 
 namespace s3d {
 
-constexpr int FIXED8 = 64 /*8 mbarriers*/ + ATAN_TAB_DOUBLES * 8 + 16 /*ctl*/ + 64 /*cnts[2][8]*/ + 64 /*base[2][8]*/ + 32 /*pos ring[8]*/;
+constexpr int ROI8_ROW = 128 + 2 * ROI_HALO;     // one warp's ROI window row: its 128 pixels + halo
+constexpr int FIXED8 = 24 * 8 /*mbarriers: full[8] free[8] counted[2] prefix[2] (+4 spare)*/ + 64 /*cnts[2][8]*/ + 64 /*base[2][8]*/ +
+                       32 /*pos ring[8]*/ + 32 /*sub-tile mask ring[8]*/;
 
 static int num_frames8(const scan3d_config& c)
 {
@@ -38,7 +40,7 @@ static int num_frames8(const scan3d_config& c)
 static size_t smem8(const scan3d_config& c, int cw)
 {
     const int T = 128 * cw;
-    return (size_t)num_frames8(c) * T + 4 * (T + 2 * ROI_HALO) + (c.dirs == 2 ? 2 * 12 * T + 2 * (T / 4) : 0) + FIXED8;
+    return (size_t)num_frames8(c) * T + (size_t)cw * 4 * ROI8_ROW + (c.dirs == 2 ? 2 * 12 * T + 2 * cw * 16 : 0) + FIXED8;
 }
 
 struct Plan8 {
@@ -84,24 +86,23 @@ __global__ void __launch_bounds__((CW + 1) * 32) __maxnreg__(regs8(CW, MINB))
 k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal, const __grid_constant__ CUtensorMap stack_map)
 {
     constexpr int T = 128 * CW;
-    constexpr int WPF = T / 4;
-    constexpr int ROI_ROW = T + 2 * ROI_HALO;
     constexpr bool fastdiv = true;   // host verified (else this kernel is not used)
+    static_assert(CW <= 8, "per-warp state is kept in 8-entry rows");
 
     extern __shared__ __align__(128) uint8_t smem[];
     const int NF = DIRS == 2 ? 2 * N + 2 * (a.M_v + a.M_h) : N + 2 * a.M_v;
-    uint8_t* slot = smem;
-    uint8_t* sroi = smem + (size_t)NF * T;
-    float* cxb = reinterpret_cast<float*>(sroi + 4 * ROI_ROW);                      // [2][CW][3*128]
-    uint8_t* vfl = reinterpret_cast<uint8_t*>(cxb + (DIRS == 2 ? 2 * 3 * T : 0));    // [2][T/4] 4 valid bits per thread (pix / rgb extras)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(vfl + (DIRS == 2 ? 2 * (T / 4) : 0));
-    double* tab = reinterpret_cast<double*>(bars + 8);
-    volatile int* ctl = reinterpret_cast<volatile int*>(tab + ATAN_TAB_DOUBLES);   // [0] position of the tile in the slot, [1] its sub-tile mask
-    volatile uint32_t* cnts = reinterpret_cast<volatile uint32_t*>(const_cast<int*>(ctl) + 4);    // [2][8] survivors per warp
-    volatile uint32_t* base = cnts + 16;                                                          // [2][8] global point offset per warp
-    volatile int* posr = reinterpret_cast<volatile int*>(const_cast<uint32_t*>(base) + 16);       // [8] positions of the tiles in flight
-    const uint32_t bar_full = smem_u32(bars), bar_free = smem_u32(bars + 1), bar_counted = smem_u32(bars + 2),
-                   bar_prefix = smem_u32(bars + 4);
+    uint8_t* slot = smem;                                                          // [CW][NF][128]: one sub-slot per warp
+    uint8_t* sroi = smem + (size_t)NF * T;                                         // [CW][4][ROI8_ROW]
+    float* cxb = reinterpret_cast<float*>(sroi + CW * 4 * ROI8_ROW);                // [2][CW][3*128] points
+    uint32_t* vbal = reinterpret_cast<uint32_t*>(cxb + (DIRS == 2 ? 2 * 3 * T : 0));   // [2][CW][4] ballots of the valid bits
+    uint64_t* bars = reinterpret_cast<uint64_t*>(vbal + (DIRS == 2 ? 2 * CW * 4 : 0));
+    volatile uint32_t* cnts = reinterpret_cast<volatile uint32_t*>(bars + 24);     // [2][8] survivors per warp
+    volatile uint32_t* base = cnts + 16;                                           // [2][8] global point offset per warp
+    volatile int* posr = reinterpret_cast<volatile int*>(const_cast<uint32_t*>(base) + 16);   // [8] work positions of the CTA's tiles (-1: end)
+    volatile int* subr = posr + 8;                                                 // [8] their sub-tile masks
+    const uint32_t bar_full = smem_u32(bars), bar_free = smem_u32(bars + 8), bar_counted = smem_u32(bars + 16),
+                   bar_prefix = smem_u32(bars + 18);
+    const double* __restrict__ tab = a.atan_tab;    // 72 doubles, read through L1 (the shared memory is full)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int W = a.W;
@@ -109,8 +110,10 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
     const int n_tiles = a.n_tiles;
 
     if (tid == 0) {
-        mbar_init(bar_full, 1);
-        mbar_init(bar_free, CW);
+        for (int w = 0; w < CW; w++) {
+            mbar_init(bar_full + 8 * w, 1);
+            mbar_init(bar_free + 8 * w, 1);
+        }
         mbar_init(bar_counted, CW);
         mbar_init(bar_counted + 8, CW);
         mbar_init(bar_prefix, 1);
@@ -118,120 +121,136 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
-    for (int i = tid; i < ATAN_TAB_DOUBLES; i += (CW + 1) * 32) tab[i] = a.atan_tab[i];
     __syncthreads();
 
     if (warp == CW) {
         // ================================ IO WARP ================================
         const unsigned long long tag = (unsigned long long)(a.epoch & 0x3fffffffu) << 34;
         const long long roi_total = (long long)W * a.H_total;
-        int load_it = 0;                         // tiles loaded so far
+        int kw = 0;                              // lane w: sub-tiles handed to consumer warp w so far
+        bool done_w = lane >= CW;                // lane w: warp w got its end marker
+        int drawn = 0;                           // tiles (and the end marker) drawn by this CTA
+        int n_real = 0;                          // ... of which real tiles
+        bool end_drawn = false;
         int agg_it = 0;                          // next tile whose count gets published
         int epi_it = 0;                          // next tile whose place in the raster order gets resolved
-        bool ended = false;
         bool resolving = false;
         int look = 0;
         uint32_t excl = 0;
         uint32_t tot[2] = {0, 0}, woff[2] = {0, 0};
         int epos[2] = {0, 0};
-        while (!ended || (DIRS == 2 && epi_it < load_it)) {
+        for (;;) {
+            const bool all_done = __all_sync(0xffffffffu, done_w);
+            if (all_done && !(DIRS == 2 && epi_it < n_real)) break;
             bool progressed = false;
-            // ---- (1) the slot is free again: draw work until a tile with ROI pixels turns up, load it ----
-            if (!ended && __any_sync(0xffffffffu, mbar_try(bar_free, (load_it & 1) ^ 1))) {
+            // ---- (1) consumer warps whose sub-slot is free: hand each the next tile's sub-tile ----
+            unsigned ready = __ballot_sync(0xffffffffu, !done_w && mbar_test(bar_free + 8 * lane, (kw & 1) ^ 1));
+            while (ready) {
                 progressed = true;
-                int pos;
-                uint32_t sub = 0;                // 128-pixel sub-tiles that hold ROI pixels
-                int p0 = 0, wt = 0;
-                for (;;) {
-                    pos = 0;
-                    if (lane == 0) pos = (int)(atomicAdd(a.sched_ctr, 1u) - a.pos_base);
-                    pos = __shfl_sync(0xffffffffu, pos, 0);
-                    if (pos >= n_tiles) { pos = -1; break; }
-                    p0 = pos * T;
-                    wt = min(T, plane - p0);
-                    const uint8_t* r = a.roi + (size_t)a.row0 * W + p0;
-                    sub = 0;
-                    for (int o = 0; o < T; o += 512) {
-                        const int off = o + 16 * lane;
-                        uint4 v = make_uint4(0, 0, 0, 0);
-                        if (off < wt) v = __ldg(reinterpret_cast<const uint4*>(r + off));
-                        const unsigned m = __ballot_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0);
-                        // 8 lanes = 128 bytes = one sub-tile
+                const int w = __ffs(ready) - 1;
+                ready &= ready - 1;
+                const int k = __shfl_sync(0xffffffffu, kw, w);
+                if (k == drawn) {
+                    // the first warp to get here draws the CTA's next tile: work positions until one with ROI pixels turns up
+                    int pos = -1;
+                    uint32_t sub = 0;
+                    while (!end_drawn) {
+                        pos = 0;
+                        if (lane == 0) pos = (int)(atomicAdd(a.sched_ctr, 1u) - a.pos_base);
+                        pos = __shfl_sync(0xffffffffu, pos, 0);
+                        if (pos >= n_tiles) { pos = -1; end_drawn = true; break; }
+                        const int p0 = pos * T, wt = min(T, plane - p0);
+                        const uint8_t* r = a.roi + (size_t)a.row0 * W + p0;
+                        // whoever draws position p pulls the ROI bytes of position p + grid into L2: that is about where
+                        // the draws will be one tile period from now
+                        if (lane < CW && pos + (int)gridDim.x < n_tiles && 128 * lane < plane - p0 - (int)gridDim.x * T)
+                            prefetch_l2(r + (size_t)gridDim.x * T + 128 * lane);
+                        sub = 0;
+                        for (int o = 0; o < T; o += 512) {
+                            const int off = o + 16 * lane;
+                            uint4 v = make_uint4(0, 0, 0, 0);
+                            if (off < wt) v = __ldg(reinterpret_cast<const uint4*>(r + off));
+                            const unsigned m = __ballot_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0);
+                            // 8 lanes = 128 bytes = one sub-tile
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if ((m >> (8 * k)) & 0xffu) sub |= 1u << (o / 128 + k);
-                    }
-                    // the first and the last tile always take the regular route (prefix seed / final count)
-                    if (sub != 0 || pos == 0 || pos == n_tiles - 1) break;
-                    // no selected pixel: constant outputs, zero count, next draw
-                    const uint4 z = make_uint4(0, 0, 0, 0), m1 = make_uint4(~0u, ~0u, ~0u, ~0u);
-                    for (int i = lane; i < wt / 4; i += 32) {
-                        reinterpret_cast<uint4*>(a.unw_v + p0)[i] = z;
-                        if (DIRS == 2) reinterpret_cast<uint4*>(a.unw_h + p0)[i] = z;
-                    }
-                    for (int i = lane; i < wt / 8; i += 32) {
-                        reinterpret_cast<uint4*>(a.code_v + p0)[i] = m1;
-                        if (DIRS == 2) reinterpret_cast<uint4*>(a.code_h + p0)[i] = m1;
-                    }
-                    for (int i = lane; i < wt / 16; i += 32) reinterpret_cast<uint4*>(a.valid + p0)[i] = z;
-                    if (DIRS == 2) {
-                        for (int i = lane; i < wt / 2; i += 32) reinterpret_cast<uint4*>(a.cpmap + p0)[i] = z;
-                        if (lane == 0) {
-                            // count 0 goes out at once; it is a prefix already when the predecessor's is known
-                            const unsigned long long w = ld_state(a.tile_state + pos - 1);
-                            const bool pre = (w >> 34) == (tag >> 34) && ((w >> 32) & 3ull) == 2;
-                            st_state(a.tile_state + pos, pre ? w : (tag | (1ull << 32)));
+                            for (int q = 0; q < 4; q++)
+                                if ((m >> (8 * q)) & 0xffu) sub |= 1u << (o / 128 + q);
+                        }
+                        // the first and the last tile always take the regular route (prefix seed / final count)
+                        if (sub != 0 || pos == 0 || pos == n_tiles - 1) break;
+                        // no selected pixel: constant outputs, zero count, next draw
+                        const uint4 z = make_uint4(0, 0, 0, 0), m1 = make_uint4(~0u, ~0u, ~0u, ~0u);
+                        for (int i = lane; i < wt / 4; i += 32) {
+                            reinterpret_cast<uint4*>(a.unw_v + p0)[i] = z;
+                            if (DIRS == 2) reinterpret_cast<uint4*>(a.unw_h + p0)[i] = z;
+                        }
+                        for (int i = lane; i < wt / 8; i += 32) {
+                            reinterpret_cast<uint4*>(a.code_v + p0)[i] = m1;
+                            if (DIRS == 2) reinterpret_cast<uint4*>(a.code_h + p0)[i] = m1;
+                        }
+                        for (int i = lane; i < wt / 16; i += 32) reinterpret_cast<uint4*>(a.valid + p0)[i] = z;
+                        if (DIRS == 2) {
+                            for (int i = lane; i < wt / 2; i += 32) reinterpret_cast<uint4*>(a.cpmap + p0)[i] = z;
+                            if (lane == 0) {
+                                // count 0 goes out at once; it is a prefix already when the predecessor's is known
+                                const unsigned long long ws = ld_state(a.tile_state + pos - 1);
+                                const bool pre = (ws >> 34) == (tag >> 34) && ((ws >> 32) & 3ull) == 2;
+                                st_state(a.tile_state + pos, pre ? ws : (tag | (1ull << 32)));
+                            }
                         }
                     }
+                    if (lane == 0) {
+                        posr[drawn & 7] = pos;
+                        subr[drawn & 7] = (int)sub;
+                    }
+                    __syncwarp();
+                    drawn++;
+                    if (pos >= 0) n_real++;
                 }
-                if (pos >= 0) {
-                    const long long gbase = (long long)a.row0 * W + p0 - ROI_HALO;
+                const int pos = posr[k & 7];
+                const bool has = pos >= 0 && ((subr[k & 7] >> w) & 1);
+                const uint32_t bfull = bar_full + 8 * w;
+                if (!has) {
+                    // end marker, or a sub-tile without ROI pixels: nothing to load
+                    if (lane == 0) mbar_arrive(bfull);
+                } else {
+                    const int p0w = pos * T + 128 * w, wtw = min(128, plane - p0w);
+                    const long long gbase = (long long)a.row0 * W + p0w - ROI_HALO;
                     long long seg0 = 0, seg1 = 0;
                     uint32_t roi_tx = 0;
                     if (lane < 4) {
                         seg0 = max(gbase + (long long)(lane - 2) * W, 0LL);
-                        seg1 = min(gbase + (long long)(lane - 2) * W + wt + 2 * ROI_HALO, roi_total);
+                        seg1 = min(gbase + (long long)(lane - 2) * W + wtw + 2 * ROI_HALO, roi_total);
                         if (seg1 > seg0) roi_tx = (uint32_t)(seg1 - seg0);
                     }
                     uint32_t roi_sum = roi_tx;
                     roi_sum += __shfl_xor_sync(0xffffffffu, roi_sum, 1);
                     roi_sum += __shfl_xor_sync(0xffffffffu, roi_sum, 2);
                     roi_sum = __shfl_sync(0xffffffffu, roi_sum, 0);
-                    if (!a.use_tmap) sub = (1u << CW) - 1;
-                    if (lane == 0) {
-                        ctl[0] = pos;
-                        ctl[1] = (int)sub;
-                        posr[load_it & 7] = pos;
-                        const uint32_t frame_tx = a.use_tmap ? (uint32_t)NF * 128u * __popc(sub) : (uint32_t)NF * wt;
-                        mbar_expect_tx(bar_full, frame_tx + roi_sum);
-                    }
+                    if (lane == 0) mbar_expect_tx(bfull, (uint32_t)NF * (a.use_tmap ? 128u : (uint32_t)wtw) + roi_sum);
                     __syncwarp();
-                    const uint32_t dst = smem_u32(slot);
+                    const uint32_t dst = smem_u32(slot) + w * NF * 128;
                     if (a.use_tmap) {
-                        // sub-tile w = [NF frames] x [128 B] as one 2-D tensor copy (64-bit elements; bytes past
-                        // the end of a frame are zero-filled): lands as a dense [NF][128] block at w * NF * 128
-                        if (lane < CW && ((sub >> lane) & 1u))
-                            tensor_g2s_2d(dst + lane * NF * 128, &stack_map, (p0 >> 3) + 16 * lane, 0, bar_full);
+                        // [NF frames] x [128 B] as one 2-D tensor copy (64-bit elements; bytes past the end of a frame
+                        // are zero-filled): lands as a dense [NF][128] block
+                        if (lane == 0) tensor_g2s_2d(dst, &stack_map, p0w >> 3, 0, bfull);
                     } else {
-                        const uint8_t* src = a.stack + p0;
-                        for (int f = lane; f < NF; f += 32) bulk_g2s(dst + f * T, src + (size_t)f * plane, (uint32_t)wt, bar_full);
+                        const uint8_t* src = a.stack + p0w;
+                        for (int f = lane; f < NF; f += 32) bulk_g2s(dst + f * 128, src + (size_t)f * plane, (uint32_t)wtw, bfull);
                     }
                     if (roi_tx)
-                        bulk_g2s(smem_u32(sroi) + lane * ROI_ROW + (uint32_t)(seg0 - (gbase + (long long)(lane - 2) * W)),
-                                 a.roi + seg0, roi_tx, bar_full);
-                    load_it++;
-                } else {
-                    if (lane == 0) {
-                        ctl[0] = -1;
-                        mbar_arrive(bar_full);
-                    }
-                    ended = true;
+                        bulk_g2s(smem_u32(sroi) + (w * 4 + lane) * ROI8_ROW + (uint32_t)(seg0 - (gbase + (long long)(lane - 2) * W)),
+                                 a.roi + seg0, roi_tx, bfull);
+                }
+                if (lane == w) {
+                    kw++;
+                    done_w = pos < 0;
                 }
             }
             if (DIRS == 2) {
                 // ---- (2) every warp of a tile has reported its survivors: the tile's count goes out at once
                 //      (its triangulation is still running; every later tile's look-back needs it) ----
-                if (agg_it < load_it && agg_it < epi_it + 2 &&
+                if (agg_it < n_real && agg_it < epi_it + 2 &&
                     __any_sync(0xffffffffu, mbar_try(bar_counted + 8 * (agg_it & 1), (agg_it >> 1) & 1))) {
                     progressed = true;
                     const int b = agg_it & 1;
@@ -260,18 +279,18 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
 #pragma unroll 1
                         for (int hop = 0; hop < 24; hop++) {
                             const int idx = look - lane;
-                            unsigned long long w = tag | (2ull << 32);   // virtual tile < 0: prefix 0
-                            if (idx >= 0) w = ld_state(a.tile_state + idx);
-                            const bool ready = (w >> 34) == (tag >> 34) && ((w >> 32) & 3ull) != 0;
-                            const bool is_prefix = ready && ((w >> 32) & 3ull) == 2;
-                            const unsigned rm = __ballot_sync(0xffffffffu, ready);
+                            unsigned long long ws = tag | (2ull << 32);   // virtual tile < 0: prefix 0
+                            if (idx >= 0) ws = ld_state(a.tile_state + idx);
+                            const bool okw = (ws >> 34) == (tag >> 34) && ((ws >> 32) & 3ull) != 0;
+                            const bool is_prefix = okw && ((ws >> 32) & 3ull) == 2;
+                            const unsigned rm = __ballot_sync(0xffffffffu, okw);
                             const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
                             // needed lanes: from the nearest tile up to the first known prefix
                             const int stop = pm ? __ffs(pm) - 1 : 31;
                             const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
                             if ((rm & need) != need) break;            // a needed count is not out yet
                             progressed = true;
-                            uint32_t v = lane <= stop ? (uint32_t)w : 0;
+                            uint32_t v = lane <= stop ? (uint32_t)ws : 0;
 #pragma unroll
                             for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                             excl += v;
@@ -293,12 +312,18 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     }
                 }
             }
-            if (!progressed) __nanosleep(250);
+            if (!progressed) __nanosleep(200);
         }
         return;
     }
 
     // ================================ CONSUMERS ================================
+    // Every warp runs its own pipeline over the CTA's tile sequence: sub-slot, ROI window, point buffers and the
+    // full / free barriers are the warp's own; the warps of a CTA only meet in the tile's count (bar_counted).
+    const uint32_t my_full = bar_full + 8 * warp, my_free = bar_free + 8 * warp;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(slot + (size_t)warp * NF * 128);
+    const uint8_t* sroi_w = sroi + warp * 4 * ROI8_ROW;
+
     // streams the warp's n_pts points of tile number k of this CTA (they sit in buffer k & 1) to their place
     // in the raster order: gb = global index of the warp's first point
     auto drain = [&](int k, uint32_t gb, uint32_t n_pts) {
@@ -308,7 +333,9 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
         const int n = 3 * (int)n_pts;
         for (int i = lane; i < n; i += 32) dst[i] = src[i];
         if (a.pix || a.rgb) {
-            const uint32_t vb = vfl[b * (T / 4) + tid];
+            const uint32_t* vb4 = vbal + (b * CW + warp) * 4;
+            const uint32_t vb = ((vb4[0] >> lane) & 1u) | (((vb4[1] >> lane) & 1u) << 1) | (((vb4[2] >> lane) & 1u) << 2) |
+                                (((vb4[3] >> lane) & 1u) << 3);
             const int pix0 = posr[k & 7] * T + 4 * tid;
             const uint32_t c = __popc(vb);
             uint32_t incl = c;
@@ -334,20 +361,17 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
 
     int it = 0;
     for (;; it++) {
-        if (!mbar_try(bar_full, it & 1))
-            while (!mbar_try(bar_full, it & 1)) __nanosleep(64);
-        const int pos = ctl[0];
+        if (!mbar_try(my_full, it & 1))
+            while (!mbar_try(my_full, it & 1)) __nanosleep(64);
+        const int pos = posr[it & 7];
         if (pos < 0) break;
-        const bool loaded = (ctl[1] >> warp) & 1;       // this warp's 128 pixels hold ROI pixels and were loaded
+        const bool loaded = (subr[it & 7] >> warp) & 1;       // this warp's 128 pixels hold ROI pixels and were loaded
         const int p0 = pos * T, wt = min(T, plane - p0);
-        const int lp0 = 4 * tid;
+        const int lp0 = 4 * tid, lpw = 4 * lane;
         const bool active = lp0 < wt;
         const int row = (p0 + lp0) / W;
         const int xt = (p0 + lp0) - row * W;
         const int y = a.row0 + row;
-        // the warp's sub-tile: a dense [NF][128 B] block (tensor-map route) or a column of the [NF][T] tile
-        const uint32_t* sw = reinterpret_cast<const uint32_t*>(slot) + (a.use_tmap ? warp * NF * 32 : warp * 32);
-        const int wpf = a.use_tmap ? 32 : WPF;
 
         // ---------------- integer phase: mask, fringe terms, Gray bits ----------------
         uint32_t mbits = 0;
@@ -362,19 +386,19 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 for (int r = 0; r < 4; r++)
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
-                        const uint32_t v = *reinterpret_cast<const uint32_t*>(sroi + r * ROI_ROW + (lp0 + ROI_HALO - 4) + 4 * c);
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(sroi_w + r * ROI8_ROW + (lpw + ROI_HALO - 4) + 4 * c);
                         any_zero |= (v - 0x01010101u) & ~v & 0x80808080u;
                     }
                 if (any_zero == 0) { mbits = 0xf; fast = true; }
             }
             if (!fast) {
-                const uint32_t centre = *reinterpret_cast<const uint32_t*>(sroi + 2 * ROI_ROW + lp0 + ROI_HALO);
+                const uint32_t centre = *reinterpret_cast<const uint32_t*>(sroi_w + 2 * ROI8_ROW + lpw + ROI_HALO);
                 if (centre != 0) {
 #pragma unroll 1
                     for (int j = 0; j < 4; j++) {
                         const int x = xt + j;
                         auto inv = [&](int gx, int gy) {
-                            return sroi[(gy - y + 2) * ROI_ROW + (lp0 + j + (gx - x) + ROI_HALO)] == 0;
+                            return sroi_w[(gy - y + 2) * ROI8_ROW + (lpw + j + (gx - x) + ROI_HALO)] == 0;
                         };
                         bool v = !inv(x, y);
                         const bool border = x == 0 || y == 0 || x == W - 1 || y == a.H_total - 1;
@@ -384,19 +408,18 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 }
             }
             if (mbits) {
-                fringe_terms<N>(sw, 0, wpf, lane, Tv);
-                gray_bits(sw, N, N + a.M_v, a.M_v, wpf, lane, gvA, gvB);
+                fringe_terms<N>(sw, 0, 32, lane, Tv);
+                gray_bits(sw, N, N + a.M_v, a.M_v, 32, lane, gvA, gvB);
                 if (DIRS == 2) {
                     const int fh = N + 2 * a.M_v;
-                    fringe_terms<N>(sw, fh, wpf, lane, Th);
-                    gray_bits(sw, fh + N, fh + N + a.M_h, a.M_h, wpf, lane, ghA, ghB);
+                    fringe_terms<N>(sw, fh, 32, lane, Th);
+                    gray_bits(sw, fh + N, fh + N + a.M_h, a.M_h, 32, lane, ghA, ghB);
                 }
             }
         }
-        // this warp is done with the slot: the IO warp may refill it once every warp has arrived
+        // the warp is done with its sub-slot: the next tile's sub-tile can come in
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_free);
-
+        if (lane == 0) mbar_arrive(my_free);
         // ---------------- FP64 phase (registers only) ----------------
         uint32_t vbits = 0;
         int4 cp01 = make_int4(0, 0, 0, 0), cp23 = cp01;   // the 4 pixels' correspondences, for the triangulation below
@@ -504,11 +527,21 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 cnts[b * 8 + warp] = wtotal;
                 mbar_arrive(bar_counted + 8 * b);
             }
+
             if (it >= 2) {
                 drain(it - 2, gb_prev, n_prev);
                 __syncwarp();
             }
-            vfl[b * (T / 4) + tid] = (uint8_t)vbits;
+            if (a.pix || a.rgb) {
+                // the threads' valid bits as 4 ballots, for the pixel indices / colours that go with the points
+                uint32_t* vb4 = vbal + (b * CW + warp) * 4;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, (vbits >> j) & 1u);
+                    if (lane == 0) vb4[j] = m;
+                }
+                __syncwarp();
+            }
             float* cx = cxb + (b * CW + warp) * 384;
             uint32_t rank = incl - cnt;
             // triangulation of the surviving pixels (7/triangulation.cpp:1230-1247); the camera table entry of the
