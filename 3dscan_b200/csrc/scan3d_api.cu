@@ -148,7 +148,7 @@ int scan3d_create(const scan3d_config* cfg, int device, scan3d_ctx** out)
         }
         CK(dalloc(&ctx->d_count, 4));
         CK(cudaMemsetAsync(ctx->d_count, 0, 16, ctx->stream));
-        const int ntiles = fused_num_tiles(ctx->cfg);
+        const int ntiles = std::max(fused_num_tiles(ctx->cfg), fused8_num_chunks(ctx->cfg) + 1);
         CK(dalloc(&ctx->tile_state, (size_t)ntiles + 1));
         CK(cudaMemsetAsync(ctx->tile_state, 0, ((size_t)ntiles + 1) * 8, ctx->stream));
         if (getenv("SCAN3D_TRACE")) {
@@ -206,7 +206,7 @@ void scan3d_destroy(scan3d_ctx* ctx)
     void* ptrs[] = {ctx->cam_lut, ctx->proj_lut, ctx->atan_tab, ctx->nstep_w, ctx->wrapped[0], ctx->wrapped[1],
                     ctx->unwrapped[0], ctx->unwrapped[1], ctx->code[0], ctx->code[1], ctx->mask[0],
                     ctx->mask[1], ctx->valid, ctx->cpmap, ctx->xyz, ctx->pts, ctx->pix, ctx->rgb,
-                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->sched_ctr, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff, ctx->pattern_profiles,
+                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->sched_ctr, ctx->stage_pts, ctx->stage_vb, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff, ctx->pattern_profiles,
                     ctx->undist_xy[0], ctx->undist_xy[1], ctx->undist_frac[0], ctx->undist_frac[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -502,15 +502,21 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     if (ctx->trace) CK(cudaMemsetAsync(ctx->trace, 0, (size_t)1024 * 64 * 8 * 8, ctx->stream));   // diagnostics only
     a.epoch = ++ctx->epoch;
     if ((ctx->epoch & 0x3fffffffu) == 0) {   // epoch wrapped: clear the look-back words once
-        CK(cudaMemsetAsync(ctx->tile_state, 0, ((size_t)fused_num_tiles(c) + 1) * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->tile_state, 0, ((size_t)std::max(fused_num_tiles(c), fused8_num_chunks(c) + 1) + 1) * 8, ctx->stream));
         a.epoch = ++ctx->epoch;
     }
     a.W = c.W; a.H = c.H; a.row0 = c.row0; a.H_total = c.H_total; a.PW = c.PW; a.PH = c.PH;
     a.N = c.N; a.M_v = c.M_v; a.M_h = c.M_h; a.fw_v = c.fw_v; a.fw_h = c.fw_h;
-    static const int impl = getenv("SCAN3D_FUSED_IMPL") ? atoi(getenv("SCAN3D_FUSED_IMPL")) : 8;
+    static const int impl = getenv("SCAN3D_FUSED_IMPL") ? atoi(getenv("SCAN3D_FUSED_IMPL")) : 7;
     if (impl >= 8 && fused8_supported(c)) {
         a.sched_ctr = ctx->sched_ctr;
         a.pos_base = ctx->sched_base;
+        if (c.dirs == 2 && !ctx->stage_pts) {
+            CK(dalloc(&ctx->stage_pts, fused8_stage_floats(ctx->sm_count)));
+            CK(dalloc(&ctx->stage_vb, fused8_stage_vb_words(ctx->sm_count)));
+        }
+        a.stage_pts = ctx->stage_pts;
+        a.stage_vb = ctx->stage_vb;
         uint32_t advance = 0;
         CK(launch_fused8(c, a, ctx->dcal, ctx->sm_count, &ctx->tmaps, &advance, ctx->stream));
         ctx->sched_base += advance;

@@ -99,6 +99,9 @@ constexpr int regs7(int cw, int minb)
 #ifndef S3D_VAR_PASS_UNROLL
 #define S3D_VAR_PASS_UNROLL 0
 #endif
+#ifndef S3D_VAR_WARP_SKIP
+#define S3D_VAR_WARP_SKIP 1
+#endif
 #ifndef S3D_VAR_IO_SLEEP_NS
 #define S3D_VAR_IO_SLEEP_NS 250
 #endif
@@ -455,7 +458,26 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
         // ---------------- FP64 phase (registers only) ----------------
         uint32_t vbits = 0;
         int4 cp01 = make_int4(0, 0, 0, 0), cp23 = cp01;   // the 4 pixels' correspondences, for the triangulation below
+#if S3D_VAR_WARP_SKIP
+        // a warp whose 128 pixels hold no pixel of the mask writes the constant outputs and leaves its issue slots
+        // to the other warps of the SM (about one warp in ten inside a tile that does hold ROI pixels)
+        const bool warp_has_px = __any_sync(0xffffffffu, mbits != 0);
+        if (active && !warp_has_px) {
+            const size_t g = (size_t)p0 + lp0;
+            *reinterpret_cast<float4*>(a.unw_v + g) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<uint2*>(a.code_v + g) = make_uint2(~0u, ~0u);
+            *reinterpret_cast<uint32_t*>(a.valid + g) = 0u;
+            if (DIRS == 2) {
+                *reinterpret_cast<float4*>(a.unw_h + g) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<uint2*>(a.code_h + g) = make_uint2(~0u, ~0u);
+                reinterpret_cast<int4*>(a.cpmap + g)[0] = make_int4(0, 0, 0, 0);
+                reinterpret_cast<int4*>(a.cpmap + g)[1] = make_int4(0, 0, 0, 0);
+            }
+        }
+        if (active && warp_has_px) {
+#else
         if (active) {
+#endif
             // Two passes of 2 pixels: inside a pass everything is straight-line (2 pixels x 2
             // directions interleave in the FP64 pipe); the pass loop is rolled to keep the
             // consumer loop inside the instruction cache.

@@ -1,25 +1,27 @@
-// scan3d_fused_kernel8.cu -- third cut of the single-pass kernel ("v8").  Same work and the same bit-for-bit
-// results as k_fused7 (scan3d_fused_kernel7.cu); what changed is who waits for whom (round-2 ncu per-line
-// profile of v7, profiles/r2_optimisation_log.md: 17 % of the consumer warps' time at the CTA-wide count
-// barrier, 12 % on global loads, 2 extra launches per scan for the work list):
+// scan3d_fused_kernel8.cu -- third cut of the single-pass kernel ("v8"): WARP-AUTONOMOUS pipelines.  Same work and
+// the same bit-for-bit results as k_fused7 (scan3d_fused_kernel7.cu); what changed is who waits for whom.  The
+// round-2 per-line profile of v7 (profiles/r2_v7_ncu_by_line.txt) shows the consumer warps 17 % of their time at
+// the CTA-wide count barrier, 12 % on global loads and ~5 % waiting for the CTA's single input slot, at 62 % issue
+// utilisation; two intermediate cuts that kept an IO warp per CTA (one slot per CTA, then one sub-slot per warp)
+// only moved that waiting to the next shared resource (profiles/r2_optimisation_log.md).  So here NOTHING is shared
+// between the warps of a CTA:
 //
-//   * ONE launch per scan.  There is no work-list pre-pass: work positions are tile indices drawn from a
-//     global counter that is never reset (the host passes the counter's value at launch: every CTA overdraws
-//     exactly once, so a launch advances it by n_tiles + grid); the IO warp looks at the tile's own ROI bytes
-//     and, when no pixel is selected, writes the tile's constant outputs itself, publishes a zero count and
-//     draws again -- the 56 frame segments of such a tile are never read;
-//   * of a tile that does hold ROI pixels only the 128-pixel sub-tiles (one per consumer warp) with ROI
-//     pixels are loaded: one 2-D tensor-map copy [frames] x [128 B] each;
-//   * no barrier among the consumer warps.  Every warp owns a private point buffer (2 x 128 points): it
-//     counts its own survivors, reports the count through an mbarrier, triangulates straight into its buffer
-//     and -- two tiles later, when the IO warp has resolved the tile's place in the raster order
-//     (decoupled look-back) and published one base offset per warp -- streams its own points out.  The
-//     IO warp never touches a point;
-//   * a warp whose 128 pixels hold no ROI pixel skips the FP64 phase altogether;
-//   * the undistortion-table entry of the next surviving pixel is fetched while the current one is solved.
-//
-//   CTA = CW consumer warps + 1 IO warp; shared memory and register budget as in v7 (3 CTAs = 21 consumer
-//   warps per SM at 80 registers for the 56-frame 12 MP configuration).
+//   * the work unit is a CHUNK of 128 consecutive pixels of the row-major frame = one warp x 4 pixels per thread;
+//     a warp draws chunk indices from a global counter that is never reset (the host passes the counter's value
+//     at launch; every warp overdraws exactly once, so a launch advances it by n_chunks + warps) -- ONE launch per
+//     scan, no work-list pre-pass;
+//   * the drawing warp looks at the chunk's own ROI bytes: no selected pixel -> it writes the chunk's constant
+//     outputs, publishes a zero count and draws again; the 56 frame segments of such a chunk are never read;
+//   * every warp owns a sub-slot [frames] x [128 B] + a 4-row ROI window in shared memory and ONE mbarrier.  As
+//     soon as its integer phase has consumed the sub-slot it issues the tensor-map copy of its NEXT chunk itself
+//     (the draw for it was made a whole chunk earlier), which lands while the FP64 phase of the current one runs;
+//   * raster-order compaction without anybody waiting: the warp publishes the chunk's survivor count right after
+//     the decode, triangulates straight into a small ring of staging slots in global memory (L2 resident: the ring
+//     is rewritten every few chunks) and only D chunks LATER resolves the chunk's place in the raster order --
+//     decoupled look-back over the chunk counts, which by then are all there and mostly already prefixes -- and
+//     moves the points to their final place.  Zero-count chunks go through the same deferred resolution, so runs of
+//     empty chunks never lengthen anybody's look-back;
+//   * no IO warp: 8 consumer warps per CTA, 3 CTAs = 24 warps per SM at 80 registers (v7: 21 + 3 IO warps).
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -29,22 +31,29 @@
 
 namespace s3d {
 
-constexpr int ROI8_ROW = 128 + 2 * ROI_HALO;     // one warp's ROI window row: its 128 pixels + halo
-constexpr int FIXED8 = 24 * 8 /*mbarriers: full[8] free[8] counted[2] prefix[2] (+4 spare)*/ + 64 /*cnts[2][8]*/ + 64 /*base[2][8]*/ +
-                       32 /*pos ring[8]*/ + 32 /*sub-tile mask ring[8]*/;
+#ifndef S3D_K8_WARPS
+#define S3D_K8_WARPS 8
+#endif
+#ifndef S3D_K8_MINB
+#define S3D_K8_MINB 3
+#endif
+constexpr int K8_WARPS = S3D_K8_WARPS;           // warps per CTA, all of them workers
+constexpr int K8_ROI_ROW = 128 + 2 * ROI_HALO;   // one row of a warp's ROI window: its 128 pixels + halo
+constexpr int K8_RING = 32;                      // pending (published, not yet resolved) chunks per warp
+constexpr int K8_D = 3;                          // a chunk's place in the raster order is resolved D chunks later
+constexpr int K8_DS = K8_D + 1;                  // staging slots per warp
 
 static int num_frames8(const scan3d_config& c)
 {
     return c.dirs == 2 ? 2 * c.N + 2 * (c.M_v + c.M_h) : c.N + 2 * c.M_v;
 }
-static size_t smem8(const scan3d_config& c, int cw)
+static size_t smem8(const scan3d_config& c)
 {
-    const int T = 128 * cw;
-    return (size_t)num_frames8(c) * T + (size_t)cw * 4 * ROI8_ROW + (c.dirs == 2 ? 2 * 12 * T + 2 * cw * 16 : 0) + FIXED8;
+    return (size_t)K8_WARPS * ((size_t)num_frames8(c) * 128 + 4 * K8_ROI_ROW + K8_RING * 8 + 16) + ATAN_TAB_DOUBLES * 8;
 }
 
 struct Plan8 {
-    int cw, minb;
+    int minb;
     size_t smem;
 };
 
@@ -52,18 +61,17 @@ static bool plan8(const scan3d_config& c, Plan8* out)
 {
     if (c.W % 16 != 0) return false;
     if (!(c.N == 3 || c.N == 4 || c.N == 5 || c.N == 8)) return false;
-    int minb0 = 3;
+    int minb0 = S3D_K8_MINB;
     if (const char* e = getenv("SCAN3D_FUSED_CFG")) {
-        int a = 0, b = 0;
-        if (sscanf(e, "%d,%d", &a, &b) == 2 && a == 7 && (b == 2 || b == 3)) minb0 = b;
+        const int b = atoi(e);
+        if (b == 2 || b == S3D_K8_MINB) minb0 = b;
     }
-    for (int b = minb0; b >= 2; b--) {
-        const size_t sm = smem8(c, 7);
+    const size_t sm = smem8(c);
+    for (int b = minb0; b >= 2; b -= (b == S3D_K8_MINB ? S3D_K8_MINB - 2 : 1))
         if ((sm + 1024) * b <= (size_t)SMEM_MAX + 1024) {
-            out->cw = 7; out->minb = b; out->smem = sm;
+            out->minb = b; out->smem = sm;
             return true;
         }
-    }
     return false;
 }
 
@@ -73,311 +81,268 @@ bool fused8_supported(const scan3d_config& c)
     return plan8(c, &p);
 }
 
-constexpr int regs8(int cw, int minb)
+int fused8_num_chunks(const scan3d_config& c) { return (int)(((size_t)c.W * c.H + 127) / 128); }
+
+constexpr int regs8(int minb)
 {
-    // per SM sub-partition: ceil(resident warps / 4) warps share 16384 registers
-    const int warps = minb * (cw + 1);
-    const int r = 16384 / (((warps + 3) / 4) * 32);
+    // per SM sub-partition: resident warps / 4 share 16384 registers
+    const int r = 16384 / (((minb * K8_WARPS + 3) / 4) * 32);
     return r > 255 ? 255 : (r / 8) * 8;
 }
 
-template <int N, int DIRS, int CW, int MINB, bool EXACT>
-__global__ void __launch_bounds__((CW + 1) * 32) __maxnreg__(regs8(CW, MINB))
+// mask recurrence for the 4 pixels of a thread next to a ROI edge or the frame border (rare): out of line
+static __device__ __noinline__ uint32_t mask_slow8(const uint8_t* sroi, int lpw, int xt, int y, int W, int H_total)
+{
+    uint32_t mbits = 0;
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+        const int x = xt + j;
+        auto inv = [&](int gx, int gy) { return sroi[(gy - y + 2) * K8_ROI_ROW + (lpw + j + (gx - x) + ROI_HALO)] == 0; };
+        bool v = !inv(x, y);
+        const bool border = x == 0 || y == 0 || x == W - 1 || y == H_total - 1;
+        if (v && !border) v = !mask_trigger(x, y, W, H_total, inv);
+        mbits |= (v ? 1u : 0u) << j;
+    }
+    return mbits;
+}
+
+// ---- a pending chunk (ring entry e = {chunk, survivors | staging slot << 16 | age stamp << 24}) gets its place in
+//      the raster order: decoupled look-back over the chunk states (all lower chunks' counts are normally long out,
+//      most of them already as prefixes), the inclusive prefix is published, the chunk's points move from the warp's
+//      staging slot to their final place.  Out of line: the hot loop stays small, and this runs once per chunk.
+static __device__ __noinline__ void resolve8(const FusedArgs& a, int2 e, unsigned long long tag, const float* stage,
+                                             const uint32_t* stage_vb, int n_chunks, int lane)
+{
+    const int c = e.x;
+    const uint32_t n = (uint32_t)e.y & 0xffffu;
+    const int slot = (e.y >> 16) & 0xff;
+    uint32_t excl = 0;
+    int look = c - 1;
+    for (;;) {
+        const int idx = look - lane;
+        unsigned long long ws = tag | (2ull << 32);   // virtual chunk < 0: prefix 0
+        if (idx >= 0) ws = ld_state(a.tile_state + idx);
+        const bool okw = (ws >> 34) == (tag >> 34) && ((ws >> 32) & 3ull) != 0;
+        const bool is_prefix = okw && ((ws >> 32) & 3ull) == 2;
+        const unsigned rm = __ballot_sync(0xffffffffu, okw);
+        const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+        // needed lanes: from the nearest chunk up to the first known prefix
+        const int stop = pm ? __ffs(pm) - 1 : 31;
+        const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
+        if ((rm & need) != need) { __nanosleep(200); continue; }   // a lower chunk is still being decoded somewhere
+        uint32_t v = lane <= stop ? (uint32_t)ws : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (pm) break;
+        look -= 32;
+    }
+    if (lane == 0) {
+        st_state(a.tile_state + c, tag | (2ull << 32) | (excl + n));
+        if (c == n_chunks - 1) *a.d_count = excl + n;
+    }
+    if (n == 0) return;
+    const float* src = stage + slot * 384;
+    float* dst = a.pts + 3 * (size_t)excl;
+    const int nf = 3 * (int)n;
+    float v[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+        const int i = lane + 32 * q;
+        v[q] = i < nf ? __ldcg(src + i) : 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+        const int i = lane + 32 * q;
+        if (i < nf) dst[i] = v[q];
+    }
+    if (stage_vb) {
+        const uint32_t* vb4 = stage_vb + slot * 4;
+        const uint32_t vb = ((__ldcg(vb4 + 0) >> lane) & 1u) | (((__ldcg(vb4 + 1) >> lane) & 1u) << 1) |
+                            (((__ldcg(vb4 + 2) >> lane) & 1u) << 2) | (((__ldcg(vb4 + 3) >> lane) & 1u) << 3);
+        const uint32_t cn = __popc(vb);
+        uint32_t incl = cn;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t dp = excl + incl - cn;
+        for (int j = 0; j < 4; j++)
+            if ((vb >> j) & 1u) {
+                const size_t gp = (size_t)c * 128 + 4 * lane + j;
+                if (a.pix) a.pix[dp] = (uint32_t)((size_t)a.row0 * a.W + gp);
+                if (a.rgb) {
+                    a.rgb[3 * (size_t)dp + 0] = a.texture[3 * gp + 2];
+                    a.rgb[3 * (size_t)dp + 1] = a.texture[3 * gp + 1];
+                    a.rgb[3 * (size_t)dp + 2] = a.texture[3 * gp + 0];
+                }
+                dp++;
+            }
+    }
+}
+
+template <int N, int DIRS, int MINB, bool EXACT>
+__global__ void __launch_bounds__(K8_WARPS * 32) __maxnreg__(regs8(MINB))
 k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal, const __grid_constant__ CUtensorMap stack_map)
 {
-    constexpr int T = 128 * CW;
     constexpr bool fastdiv = true;   // host verified (else this kernel is not used)
-    static_assert(CW <= 8, "per-warp state is kept in 8-entry rows");
 
     extern __shared__ __align__(128) uint8_t smem[];
     const int NF = DIRS == 2 ? 2 * N + 2 * (a.M_v + a.M_h) : N + 2 * a.M_v;
-    uint8_t* slot = smem;                                                          // [CW][NF][128]: one sub-slot per warp
-    uint8_t* sroi = smem + (size_t)NF * T;                                         // [CW][4][ROI8_ROW]
-    float* cxb = reinterpret_cast<float*>(sroi + CW * 4 * ROI8_ROW);                // [2][CW][3*128] points
-    uint32_t* vbal = reinterpret_cast<uint32_t*>(cxb + (DIRS == 2 ? 2 * 3 * T : 0));   // [2][CW][4] ballots of the valid bits
-    uint64_t* bars = reinterpret_cast<uint64_t*>(vbal + (DIRS == 2 ? 2 * CW * 4 : 0));
-    volatile uint32_t* cnts = reinterpret_cast<volatile uint32_t*>(bars + 24);     // [2][8] survivors per warp
-    volatile uint32_t* base = cnts + 16;                                           // [2][8] global point offset per warp
-    volatile int* posr = reinterpret_cast<volatile int*>(const_cast<uint32_t*>(base) + 16);   // [8] work positions of the CTA's tiles (-1: end)
-    volatile int* subr = posr + 8;                                                 // [8] their sub-tile masks
-    const uint32_t bar_full = smem_u32(bars), bar_free = smem_u32(bars + 8), bar_counted = smem_u32(bars + 16),
-                   bar_prefix = smem_u32(bars + 18);
-    const double* __restrict__ tab = a.atan_tab;    // 72 doubles, read through L1 (the shared memory is full)
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int W = a.W;
     const int plane = W * a.H;
-    const int n_tiles = a.n_tiles;
+    const int n_chunks = a.n_tiles;
 
-    if (tid == 0) {
-        for (int w = 0; w < CW; w++) {
-            mbar_init(bar_full + 8 * w, 1);
-            mbar_init(bar_free + 8 * w, 1);
-        }
-        mbar_init(bar_counted, CW);
-        mbar_init(bar_counted + 8, CW);
-        mbar_init(bar_prefix, 1);
-        mbar_init(bar_prefix + 8, 1);
+    // shared memory: [warp] sub-slots | [warp] ROI windows | [warp] pending rings | [warp] mbarrier | atan table
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(smem + (size_t)warp * NF * 128);
+    uint8_t* p_roi = smem + (size_t)K8_WARPS * NF * 128;
+    const uint8_t* sroi = p_roi + warp * 4 * K8_ROI_ROW;
+    int2* ring = reinterpret_cast<int2*>(p_roi + K8_WARPS * 4 * K8_ROI_ROW) + warp * K8_RING;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_roi + K8_WARPS * (4 * K8_ROI_ROW + K8_RING * 8));
+    double* tab = reinterpret_cast<double*>(bars + 2 * K8_WARPS);
+    const uint32_t my_full = smem_u32(bars + warp);
+
+    if (lane == 0) {
+        mbar_init(my_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
+    for (int i = tid; i < ATAN_TAB_DOUBLES; i += K8_WARPS * 32) tab[i] = a.atan_tab[i];
     __syncthreads();
+    // ---- from here on the warps of the CTA never meet again ----
 
-    if (warp == CW) {
-        // ================================ IO WARP ================================
-        const unsigned long long tag = (unsigned long long)(a.epoch & 0x3fffffffu) << 34;
-        const long long roi_total = (long long)W * a.H_total;
-        int kw = 0;                              // lane w: sub-tiles handed to consumer warp w so far
-        bool done_w = lane >= CW;                // lane w: warp w got its end marker
-        int drawn = 0;                           // tiles (and the end marker) drawn by this CTA
-        int n_real = 0;                          // ... of which real tiles
-        bool end_drawn = false;
-        int agg_it = 0;                          // next tile whose count gets published
-        int epi_it = 0;                          // next tile whose place in the raster order gets resolved
-        bool resolving = false;
-        int look = 0;
-        uint32_t excl = 0;
-        uint32_t tot[2] = {0, 0}, woff[2] = {0, 0};
-        int epos[2] = {0, 0};
+    const unsigned long long tag = (unsigned long long)(a.epoch & 0x3fffffffu) << 34;
+    const long long roi_total = (long long)W * a.H_total;
+    const int gwarp = (int)blockIdx.x * K8_WARPS + warp;
+    const int total_warps = (int)gridDim.x * K8_WARPS;
+    float* const stage = DIRS == 2 ? a.stage_pts + (size_t)gwarp * (K8_DS * 384) : nullptr;
+    uint32_t* const stage_vb = (DIRS == 2 && (a.pix || a.rgb)) ? a.stage_vb + (size_t)gwarp * (K8_DS * 4) : nullptr;
+
+    int it = 0;                      // chunks decoded by this warp
+    int rh = 0, rt = 0;              // pending ring: head (oldest), tail
+    bool end_seen = false;           // this warp has drawn its one position past the end
+
+    auto resolve_one = [&]() {
+        const int2 e = ring[rh & (K8_RING - 1)];
+        rh++;
+        resolve8(a, e, tag, stage, stage_vb, n_chunks, lane);
+    };
+    // a chunk whose count is out joins the pending ring (resolved K8_D decoded chunks later)
+    auto push = [&](int c, uint32_t n, int slot) {       // (callers make room first)
+        if (lane == 0) ring[rt & (K8_RING - 1)] = make_int2(c, (int)(n | ((uint32_t)slot << 16) | ((uint32_t)(it & 0xff) << 24)));
+        rt++;
+        __syncwarp();
+    };
+
+    // ---- work: the next chunk with ROI pixels, or -1 = no more work, or -2 = the pending ring is full and cannot be
+    //      emptied yet (the undecided position is kept in `carry`).  first = a position drawn earlier, or -1 to draw
+    //      now; low = the lowest chunk this warp holds whose count is not out yet.  A pending entry above `low` must
+    //      not be resolved here: its look-back would wait for this very warp. ----
+    int carry = -1;
+    auto next_chunk = [&](int first, int low) -> int {
+        int c = first;
         for (;;) {
-            const bool all_done = __all_sync(0xffffffffu, done_w);
-            if (all_done && !(DIRS == 2 && epi_it < n_real)) break;
-            bool progressed = false;
-            // ---- (1) consumer warps whose sub-slot is free: hand each the next tile's sub-tile ----
-            unsigned ready = __ballot_sync(0xffffffffu, !done_w && mbar_test(bar_free + 8 * lane, (kw & 1) ^ 1));
-            while (ready) {
-                progressed = true;
-                const int w = __ffs(ready) - 1;
-                ready &= ready - 1;
-                const int k = __shfl_sync(0xffffffffu, kw, w);
-                if (k == drawn) {
-                    // the first warp to get here draws the CTA's next tile: work positions until one with ROI pixels turns up
-                    int pos = -1;
-                    uint32_t sub = 0;
-                    while (!end_drawn) {
-                        pos = 0;
-                        if (lane == 0) pos = (int)(atomicAdd(a.sched_ctr, 1u) - a.pos_base);
-                        pos = __shfl_sync(0xffffffffu, pos, 0);
-                        if (pos >= n_tiles) { pos = -1; end_drawn = true; break; }
-                        const int p0 = pos * T, wt = min(T, plane - p0);
-                        const uint8_t* r = a.roi + (size_t)a.row0 * W + p0;
-                        // whoever draws position p pulls the ROI bytes of position p + grid into L2: that is about where
-                        // the draws will be one tile period from now
-                        if (lane < CW && pos + (int)gridDim.x < n_tiles && 128 * lane < plane - p0 - (int)gridDim.x * T)
-                            prefetch_l2(r + (size_t)gridDim.x * T + 128 * lane);
-                        sub = 0;
-                        for (int o = 0; o < T; o += 512) {
-                            const int off = o + 16 * lane;
-                            uint4 v = make_uint4(0, 0, 0, 0);
-                            if (off < wt) v = __ldg(reinterpret_cast<const uint4*>(r + off));
-                            const unsigned m = __ballot_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0);
-                            // 8 lanes = 128 bytes = one sub-tile
-#pragma unroll
-                            for (int q = 0; q < 4; q++)
-                                if ((m >> (8 * q)) & 0xffu) sub |= 1u << (o / 128 + q);
-                        }
-                        // the first and the last tile always take the regular route (prefix seed / final count)
-                        if (sub != 0 || pos == 0 || pos == n_tiles - 1) break;
-                        // no selected pixel: constant outputs, zero count, next draw
-                        const uint4 z = make_uint4(0, 0, 0, 0), m1 = make_uint4(~0u, ~0u, ~0u, ~0u);
-                        for (int i = lane; i < wt / 4; i += 32) {
-                            reinterpret_cast<uint4*>(a.unw_v + p0)[i] = z;
-                            if (DIRS == 2) reinterpret_cast<uint4*>(a.unw_h + p0)[i] = z;
-                        }
-                        for (int i = lane; i < wt / 8; i += 32) {
-                            reinterpret_cast<uint4*>(a.code_v + p0)[i] = m1;
-                            if (DIRS == 2) reinterpret_cast<uint4*>(a.code_h + p0)[i] = m1;
-                        }
-                        for (int i = lane; i < wt / 16; i += 32) reinterpret_cast<uint4*>(a.valid + p0)[i] = z;
-                        if (DIRS == 2) {
-                            for (int i = lane; i < wt / 2; i += 32) reinterpret_cast<uint4*>(a.cpmap + p0)[i] = z;
-                            if (lane == 0) {
-                                // count 0 goes out at once; it is a prefix already when the predecessor's is known
-                                const unsigned long long ws = ld_state(a.tile_state + pos - 1);
-                                const bool pre = (ws >> 34) == (tag >> 34) && ((ws >> 32) & 3ull) == 2;
-                                st_state(a.tile_state + pos, pre ? ws : (tag | (1ull << 32)));
-                            }
-                        }
-                    }
-                    if (lane == 0) {
-                        posr[drawn & 7] = pos;
-                        subr[drawn & 7] = (int)sub;
-                    }
-                    __syncwarp();
-                    drawn++;
-                    if (pos >= 0) n_real++;
+            if (DIRS == 2)
+                while (rt - rh >= K8_RING - 1) {
+                    if (ring[rh & (K8_RING - 1)].x > low) { carry = c; return -2; }
+                    resolve_one();
                 }
-                const int pos = posr[k & 7];
-                const bool has = pos >= 0 && ((subr[k & 7] >> w) & 1);
-                const uint32_t bfull = bar_full + 8 * w;
-                if (!has) {
-                    // end marker, or a sub-tile without ROI pixels: nothing to load
-                    if (lane == 0) mbar_arrive(bfull);
-                } else {
-                    const int p0w = pos * T + 128 * w, wtw = min(128, plane - p0w);
-                    const long long gbase = (long long)a.row0 * W + p0w - ROI_HALO;
-                    long long seg0 = 0, seg1 = 0;
-                    uint32_t roi_tx = 0;
-                    if (lane < 4) {
-                        seg0 = max(gbase + (long long)(lane - 2) * W, 0LL);
-                        seg1 = min(gbase + (long long)(lane - 2) * W + wtw + 2 * ROI_HALO, roi_total);
-                        if (seg1 > seg0) roi_tx = (uint32_t)(seg1 - seg0);
-                    }
-                    uint32_t roi_sum = roi_tx;
-                    roi_sum += __shfl_xor_sync(0xffffffffu, roi_sum, 1);
-                    roi_sum += __shfl_xor_sync(0xffffffffu, roi_sum, 2);
-                    roi_sum = __shfl_sync(0xffffffffu, roi_sum, 0);
-                    if (lane == 0) mbar_expect_tx(bfull, (uint32_t)NF * (a.use_tmap ? 128u : (uint32_t)wtw) + roi_sum);
-                    __syncwarp();
-                    const uint32_t dst = smem_u32(slot) + w * NF * 128;
-                    if (a.use_tmap) {
-                        // [NF frames] x [128 B] as one 2-D tensor copy (64-bit elements; bytes past the end of a frame
-                        // are zero-filled): lands as a dense [NF][128] block
-                        if (lane == 0) tensor_g2s_2d(dst, &stack_map, p0w >> 3, 0, bfull);
-                    } else {
-                        const uint8_t* src = a.stack + p0w;
-                        for (int f = lane; f < NF; f += 32) bulk_g2s(dst + f * 128, src + (size_t)f * plane, (uint32_t)wtw, bfull);
-                    }
-                    if (roi_tx)
-                        bulk_g2s(smem_u32(sroi) + (w * 4 + lane) * ROI8_ROW + (uint32_t)(seg0 - (gbase + (long long)(lane - 2) * W)),
-                                 a.roi + seg0, roi_tx, bfull);
-                }
-                if (lane == w) {
-                    kw++;
-                    done_w = pos < 0;
+            if (c < 0) {
+                if (end_seen) return -1;
+                c = 0;
+                if (lane == 0) c = (int)(atomicAdd(a.sched_ctr, 1u) - a.pos_base);
+                c = __shfl_sync(0xffffffffu, c, 0);
+            }
+            if (c >= n_chunks) { end_seen = true; return -1; }
+            const int p0 = c * 128, wc = min(128, plane - p0);
+            const uint8_t* r = a.roi + (size_t)a.row0 * W + p0;
+            // whoever draws chunk c pulls the ROI bytes of chunk c + (number of warps) into L2: about where the
+            // draws will be one chunk period from now
+            if (lane == 0 && c + total_warps < n_chunks) prefetch_l2(r + (size_t)total_warps * 128);
+            uint32_t v = 0;
+            if (4 * lane < wc) v = __ldg(reinterpret_cast<const uint32_t*>(r) + lane);
+            if (__any_sync(0xffffffffu, v != 0)) return c;
+            // no selected pixel: constant outputs (phase 0, fringe order -1, invalid, c_p_map 0), zero count
+            if (4 * lane < wc) {
+                const size_t g = (size_t)p0 + 4 * lane;
+                *reinterpret_cast<float4*>(a.unw_v + g) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<uint2*>(a.code_v + g) = make_uint2(~0u, ~0u);
+                *reinterpret_cast<uint32_t*>(a.valid + g) = 0u;
+                if (DIRS == 2) {
+                    *reinterpret_cast<float4*>(a.unw_h + g) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<uint2*>(a.code_h + g) = make_uint2(~0u, ~0u);
+                    reinterpret_cast<int4*>(a.cpmap + g)[0] = make_int4(0, 0, 0, 0);
+                    reinterpret_cast<int4*>(a.cpmap + g)[1] = make_int4(0, 0, 0, 0);
                 }
             }
             if (DIRS == 2) {
-                // ---- (2) every warp of a tile has reported its survivors: the tile's count goes out at once
-                //      (its triangulation is still running; every later tile's look-back needs it) ----
-                if (agg_it < n_real && agg_it < epi_it + 2 &&
-                    __any_sync(0xffffffffu, mbar_try(bar_counted + 8 * (agg_it & 1), (agg_it >> 1) & 1))) {
-                    progressed = true;
-                    const int b = agg_it & 1;
-                    const int pos = posr[agg_it & 7];
-                    const uint32_t c = lane < CW ? cnts[b * 8 + lane] : 0u;
-                    uint32_t incl = c;
-#pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 7);
-                    if (lane == 0) st_state(a.tile_state + pos, tag | ((pos ? 1ull : 2ull) << 32) | total);
-                    tot[b] = total;
-                    woff[b] = incl - c;
-                    epos[b] = pos;
-                    agg_it++;
-                }
-                // ---- (3) resumable decoupled look-back of the oldest counted tile; once its exclusive prefix is
-                //      known every warp of the tile gets its base offset and streams its points out itself ----
-                if (epi_it < agg_it) {
-                    const int b = epi_it & 1;
-                    if (!resolving) { resolving = true; excl = 0; look = epos[b] - 1; }
-                    bool resolved = epos[b] == 0;
-                    if (!resolved) {
-#pragma unroll 1
-                        for (int hop = 0; hop < 24; hop++) {
-                            const int idx = look - lane;
-                            unsigned long long ws = tag | (2ull << 32);   // virtual tile < 0: prefix 0
-                            if (idx >= 0) ws = ld_state(a.tile_state + idx);
-                            const bool okw = (ws >> 34) == (tag >> 34) && ((ws >> 32) & 3ull) != 0;
-                            const bool is_prefix = okw && ((ws >> 32) & 3ull) == 2;
-                            const unsigned rm = __ballot_sync(0xffffffffu, okw);
-                            const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
-                            // needed lanes: from the nearest tile up to the first known prefix
-                            const int stop = pm ? __ffs(pm) - 1 : 31;
-                            const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
-                            if ((rm & need) != need) break;            // a needed count is not out yet
-                            progressed = true;
-                            uint32_t v = lane <= stop ? (uint32_t)ws : 0;
-#pragma unroll
-                            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                            excl += v;
-                            if (pm) { resolved = true; break; }
-                            look -= 32;
-                        }
-                    }
-                    if (resolved) {
-                        progressed = true;
-                        if (lane == 0) {
-                            if (epos[b] != 0) st_state(a.tile_state + epos[b], tag | (2ull << 32) | (excl + tot[b]));
-                            if (epos[b] == n_tiles - 1) *a.d_count = excl + tot[b];
-                        }
-                        if (lane < CW) base[b * 8 + lane] = excl + woff[b];
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_prefix + 8 * b);
-                        epi_it++;
-                        resolving = false;
-                    }
-                }
+                if (lane == 0) st_state(a.tile_state + c, tag | ((c ? 1ull : 2ull) << 32));
+                push(c, 0, 0);
             }
-            if (!progressed) __nanosleep(200);
-        }
-        return;
-    }
-
-    // ================================ CONSUMERS ================================
-    // Every warp runs its own pipeline over the CTA's tile sequence: sub-slot, ROI window, point buffers and the
-    // full / free barriers are the warp's own; the warps of a CTA only meet in the tile's count (bar_counted).
-    const uint32_t my_full = bar_full + 8 * warp, my_free = bar_free + 8 * warp;
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(slot + (size_t)warp * NF * 128);
-    const uint8_t* sroi_w = sroi + warp * 4 * ROI8_ROW;
-
-    // streams the warp's n_pts points of tile number k of this CTA (they sit in buffer k & 1) to their place
-    // in the raster order: gb = global index of the warp's first point
-    auto drain = [&](int k, uint32_t gb, uint32_t n_pts) {
-        const int b = k & 1;
-        const float* src = cxb + (b * CW + warp) * 384;
-        float* dst = a.pts + 3 * (size_t)gb;
-        const int n = 3 * (int)n_pts;
-        for (int i = lane; i < n; i += 32) dst[i] = src[i];
-        if (a.pix || a.rgb) {
-            const uint32_t* vb4 = vbal + (b * CW + warp) * 4;
-            const uint32_t vb = ((vb4[0] >> lane) & 1u) | (((vb4[1] >> lane) & 1u) << 1) | (((vb4[2] >> lane) & 1u) << 2) |
-                                (((vb4[3] >> lane) & 1u) << 3);
-            const int pix0 = posr[k & 7] * T + 4 * tid;
-            const uint32_t c = __popc(vb);
-            uint32_t incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            uint32_t dp = gb + incl - c;
-            for (int j = 0; j < 4; j++)
-                if ((vb >> j) & 1u) {
-                    const size_t gp = (size_t)pix0 + j;
-                    if (a.pix) a.pix[dp] = (uint32_t)((size_t)a.row0 * W + gp);
-                    if (a.rgb) {
-                        a.rgb[3 * (size_t)dp + 0] = a.texture[3 * gp + 2];
-                        a.rgb[3 * (size_t)dp + 1] = a.texture[3 * gp + 1];
-                        a.rgb[3 * (size_t)dp + 2] = a.texture[3 * gp + 0];
-                    }
-                    dp++;
-                }
+            c = -1;
         }
     };
 
-    int it = 0;
-    for (;; it++) {
+    // ---- the warp's own loads: [NF frames] x [128 B] sub-tile + 4 ROI rows, all completing on the warp's mbarrier ----
+    auto issue_load = [&](int c) {
+        const int p0 = c * 128, wc = min(128, plane - p0);
+        const long long gbase = (long long)a.row0 * W + p0 - ROI_HALO;
+        long long seg0 = 0, seg1 = 0;
+        uint32_t roi_tx = 0;
+        if (lane < 4) {
+            seg0 = max(gbase + (long long)(lane - 2) * W, 0LL);
+            seg1 = min(gbase + (long long)(lane - 2) * W + wc + 2 * ROI_HALO, roi_total);
+            if (seg1 > seg0) roi_tx = (uint32_t)(seg1 - seg0);
+        }
+        uint32_t roi_sum = roi_tx;
+        roi_sum += __shfl_xor_sync(0xffffffffu, roi_sum, 1);
+        roi_sum += __shfl_xor_sync(0xffffffffu, roi_sum, 2);
+        roi_sum = __shfl_sync(0xffffffffu, roi_sum, 0);
+        if (lane == 0) {
+            fence_async_smem();      // the warp's reads of the sub-slot are done; the copy below rewrites it
+            mbar_expect_tx(my_full, (uint32_t)NF * (a.use_tmap ? 128u : (uint32_t)wc) + roi_sum);
+        }
+        __syncwarp();
+        const uint32_t dst = smem_u32(sw);
+        if (a.use_tmap) {
+            // one 2-D tensor copy (64-bit elements; bytes past the end of a frame are zero-filled): a dense [NF][128] block
+            if (lane == 0) tensor_g2s_2d(dst, &stack_map, p0 >> 3, 0, my_full);
+        } else {
+            const uint8_t* src = a.stack + p0;
+            for (int f = lane; f < NF; f += 32) bulk_g2s(dst + f * 128, src + (size_t)f * plane, (uint32_t)wc, my_full);
+        }
+        if (roi_tx)
+            bulk_g2s(smem_u32(sroi) + lane * K8_ROI_ROW + (uint32_t)(seg0 - (gbase + (long long)(lane - 2) * W)),
+                     a.roi + seg0, roi_tx, my_full);
+    };
+
+    constexpr int NONE_LOW = 0x7fffffff;
+    int cur = next_chunk(-1, NONE_LOW);
+    if (cur >= 0) issue_load(cur);
+    int nxt = cur >= 0 ? next_chunk(-1, cur) : -1;
+
+    while (cur >= 0) {
+        // the draw for the chunk after next goes out now and is looked at after the FP64 phase
+        int fut = -1;
+        const bool fut_drawn = !end_seen && nxt != -2;      // (nxt == -2: an undecided position is carried, see below)
+        if (fut_drawn && lane == 0) fut = (int)(atomicAdd(a.sched_ctr, 1u) - a.pos_base);
+
         if (!mbar_try(my_full, it & 1))
             while (!mbar_try(my_full, it & 1)) __nanosleep(64);
-        const int pos = posr[it & 7];
-        if (pos < 0) break;
-        const bool loaded = (subr[it & 7] >> warp) & 1;       // this warp's 128 pixels hold ROI pixels and were loaded
-        const int p0 = pos * T, wt = min(T, plane - p0);
-        const int lp0 = 4 * tid, lpw = 4 * lane;
-        const bool active = lp0 < wt;
-        const int row = (p0 + lp0) / W;
-        const int xt = (p0 + lp0) - row * W;
+        const int p0 = cur * 128, wc = min(128, plane - p0);
+        const int lpw = 4 * lane;
+        const bool active = lpw < wc;
+        const int row = (p0 + lpw) / W;
+        const int xt = (p0 + lpw) - row * W;
         const int y = a.row0 + row;
 
         // ---------------- integer phase: mask, fringe terms, Gray bits ----------------
         uint32_t mbits = 0;
         Terms Tv, Th;
         uint32_t gvA = 0, gvB = 0, ghA = 0, ghB = 0;
-        if (active && loaded) {
+        if (active) {
             const bool window_ok = y >= 2 && y + 1 < a.H_total && xt >= 4 && xt + 7 < W;
             bool fast = false;
             if (window_ok) {
@@ -386,26 +351,14 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 for (int r = 0; r < 4; r++)
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
-                        const uint32_t v = *reinterpret_cast<const uint32_t*>(sroi_w + r * ROI8_ROW + (lpw + ROI_HALO - 4) + 4 * c);
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(sroi + r * K8_ROI_ROW + (lpw + ROI_HALO - 4) + 4 * c);
                         any_zero |= (v - 0x01010101u) & ~v & 0x80808080u;
                     }
                 if (any_zero == 0) { mbits = 0xf; fast = true; }
             }
             if (!fast) {
-                const uint32_t centre = *reinterpret_cast<const uint32_t*>(sroi_w + 2 * ROI8_ROW + lpw + ROI_HALO);
-                if (centre != 0) {
-#pragma unroll 1
-                    for (int j = 0; j < 4; j++) {
-                        const int x = xt + j;
-                        auto inv = [&](int gx, int gy) {
-                            return sroi_w[(gy - y + 2) * ROI8_ROW + (lpw + j + (gx - x) + ROI_HALO)] == 0;
-                        };
-                        bool v = !inv(x, y);
-                        const bool border = x == 0 || y == 0 || x == W - 1 || y == a.H_total - 1;
-                        if (v && !border) v = !mask_trigger(x, y, W, a.H_total, inv);
-                        mbits |= (v ? 1u : 0u) << j;
-                    }
-                }
+                const uint32_t centre = *reinterpret_cast<const uint32_t*>(sroi + 2 * K8_ROI_ROW + lpw + ROI_HALO);
+                if (centre != 0) mbits = mask_slow8(sroi, lpw, xt, y, W, a.H_total);
             }
             if (mbits) {
                 fringe_terms<N>(sw, 0, 32, lane, Tv);
@@ -417,18 +370,19 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 }
             }
         }
-        // the warp is done with its sub-slot: the next tile's sub-tile can come in
+        // the sub-slot is consumed: the next chunk's frames come in while the FP64 phase runs
         __syncwarp();
-        if (lane == 0) mbar_arrive(my_free);
+        if (nxt >= 0) issue_load(nxt);
+
         // ---------------- FP64 phase (registers only) ----------------
         uint32_t vbits = 0;
         int4 cp01 = make_int4(0, 0, 0, 0), cp23 = cp01;   // the 4 pixels' correspondences, for the triangulation below
-        const size_t g = (size_t)p0 + lp0;
+        const size_t g = (size_t)p0 + lpw;
         if (__any_sync(0xffffffffu, mbits != 0)) {
             if (active) {
                 // Two passes of 2 pixels: inside a pass everything is straight-line (2 pixels x 2
                 // directions interleave in the FP64 pipe); the pass loop is rolled to keep the
-                // consumer loop inside the instruction cache.
+                // loop inside the instruction cache.
 #pragma unroll 1
                 for (int h = 0; h < 2; h++) {
                     float r_unwv[2], r_unwh[2];
@@ -490,7 +444,7 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 }
             }
         } else if (active) {
-            // no ROI pixel among the warp's 128: constant outputs (phase 0, fringe order -1, invalid, c_p_map 0)
+            // the mask recurrence left no pixel of the chunk: constant outputs
             *reinterpret_cast<float4*>(a.unw_v + g) = make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<uint2*>(a.code_v + g) = make_uint2(~0u, ~0u);
             *reinterpret_cast<uint32_t*>(a.valid + g) = 0u;
@@ -502,8 +456,9 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
             }
         }
         if (DIRS == 2) {
-            // ---- the warp's survivors: count, report, then triangulate straight into the warp's buffer ----
-            const int b = it & 1;
+            // ---- the chunk's survivors: the count goes out at once (every higher chunk's look-back needs it), the
+            //      points are solved straight into a staging slot, their final place is found K8_D chunks from now ----
+            const int slot = it % K8_DS;
             const uint32_t cnt = __popc(vbits);
             uint32_t incl = cnt;
 #pragma unroll
@@ -512,37 +467,16 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 if (lane >= o) incl += t;
             }
             const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
-            // buffer b still holds the warp's points of tile it-2: their base offset must be known by now
-            uint32_t gb_prev = 0, n_prev = 0;
-            if (it >= 2) {
-                const uint32_t par = ((it - 2) >> 1) & 1;
-                if (!mbar_try(bar_prefix + 8 * b, par))
-                    while (!mbar_try(bar_prefix + 8 * b, par)) __nanosleep(64);
-                gb_prev = base[b * 8 + warp];
-                n_prev = cnts[b * 8 + warp];
-            }
-            __syncwarp();
-            // (base[b] and cnts[b] are rewritten for this tile only after every warp has arrived here)
-            if (lane == 0) {
-                cnts[b * 8 + warp] = wtotal;
-                mbar_arrive(bar_counted + 8 * b);
-            }
-
-            if (it >= 2) {
-                drain(it - 2, gb_prev, n_prev);
-                __syncwarp();
-            }
-            if (a.pix || a.rgb) {
+            if (lane == 0) st_state(a.tile_state + cur, tag | ((cur ? 1ull : 2ull) << 32) | wtotal);
+            if (stage_vb) {
                 // the threads' valid bits as 4 ballots, for the pixel indices / colours that go with the points
-                uint32_t* vb4 = vbal + (b * CW + warp) * 4;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const uint32_t m = __ballot_sync(0xffffffffu, (vbits >> j) & 1u);
-                    if (lane == 0) vb4[j] = m;
+                    if (lane == 0) stage_vb[slot * 4 + j] = m;
                 }
-                __syncwarp();
             }
-            float* cx = cxb + (b * CW + warp) * 384;
+            float* cx = stage + slot * 384;
             uint32_t rank = incl - cnt;
             // triangulation of the surviving pixels (7/triangulation.cpp:1230-1247); the camera table entry of the
             // next pixel is in flight while this one is solved
@@ -576,18 +510,30 @@ k_fused8(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 rank++;
             }
             __syncwarp();
+            while (rt - rh >= K8_RING) resolve_one();       // (every pending entry is below cur, whose count is out)
+            push(cur, wtotal, slot);
         }
-    }
-    if (DIRS == 2) {
-        // the last two tiles of this CTA are still in the buffers
-        for (int k = max(it - 2, 0); k < it; k++) {
-            const int b = k & 1;
-            const uint32_t par = (k >> 1) & 1;
-            if (!mbar_try(bar_prefix + 8 * b, par))
-                while (!mbar_try(bar_prefix + 8 * b, par)) __nanosleep(64);
-            drain(k, base[b * 8 + warp], cnts[b * 8 + warp]);
+        it++;
+
+        if (nxt == -2) {
+            // the pending ring was full of chunks above the one just decoded: it can be emptied now; the load of
+            // the next chunk goes out late (a bubble, only after very long runs of chunks without ROI pixels)
+            nxt = next_chunk(carry, NONE_LOW);
+            if (nxt >= 0) issue_load(nxt);
         }
+        // ---- the chunk after next: the draw made at the top (zero-count chunks on the way are dealt with there) ----
+        int nxt2 = -1;
+        if (nxt >= 0) nxt2 = next_chunk(fut_drawn ? __shfl_sync(0xffffffffu, fut, 0) : -1, nxt);
+
+        // ---- pending chunks that are K8_D chunks old: find their place, move their points ----
+        if (DIRS == 2)
+            while (rh < rt && ((it - ((unsigned)ring[rh & (K8_RING - 1)].y >> 24)) & 0xff) >= K8_D) resolve_one();
+
+        cur = nxt;
+        nxt = nxt2;
     }
+    if (DIRS == 2)
+        while (rh < rt) resolve_one();
 }
 
 // 2-D view of the capture stack for the tile loads: inner dimension = one frame as 64-bit words,
@@ -617,33 +563,36 @@ static bool stack_tensor_map8(CUtensorMap* map, const uint8_t* stack, size_t pla
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int N, int DIRS, int CW, int MINB, bool EXACT>
+// words of staging a launch on sm_count SMs needs (points: floats; valid-bit ballots: uint32)
+size_t fused8_stage_floats(int sm_count) { return (size_t)sm_count * S3D_K8_MINB * K8_WARPS * K8_DS * 384; }
+size_t fused8_stage_vb_words(int sm_count) { return (size_t)sm_count * S3D_K8_MINB * K8_WARPS * K8_DS * 4; }
+
+template <int N, int DIRS, int MINB, bool EXACT>
 static cudaError_t launch8_t(const FusedArgs& a, const DeviceCalib& cal, int sm_count, const Plan8& p, Fused8Cache* cache,
                              uint32_t* advance, cudaStream_t st)
 {
-    auto kern = k_fused8<N, DIRS, CW, MINB, EXACT>;
-    static bool configured = false;     // per instantiation: attributes and occupancy are set once per process
+    auto kern = k_fused8<N, DIRS, MINB, EXACT>;
+    static size_t smem_cached = 0;      // per instantiation: attributes and occupancy are set once per process and size
     static int per_sm_cached = 0;
-    static size_t smem_cached = 0;
-    if (!configured || smem_cached != p.smem) {
+    if (smem_cached != p.smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
         if (e != cudaSuccess) return e;
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (CW + 1) * 32, p.smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K8_WARPS * 32, p.smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         if (getenv("SCAN3D_DEBUG")) {
             cudaFuncAttributes fa;
             cudaFuncGetAttributes(&fa, kern);
-            fprintf(stderr, "k_fused8<%d,%d,%d,%d,%d>: occupancy %d CTAs/SM, %d regs, %zu B dyn smem, local %zu B\n", N, DIRS, CW, MINB,
+            fprintf(stderr, "k_fused8<%d,%d,%d,%d>: occupancy %d CTAs/SM, %d regs, %zu B dyn smem, local %zu B\n", N, DIRS, MINB,
                     (int)EXACT, per_sm, fa.numRegs, p.smem, fa.localSizeBytes);
         }
         per_sm_cached = per_sm > MINB ? MINB : per_sm;
         smem_cached = p.smem;
-        configured = true;
     }
-    const int grid = a.n_tiles < sm_count * per_sm_cached ? a.n_tiles : sm_count * per_sm_cached;   // all CTAs resident
+    const int want = (a.n_tiles + K8_WARPS - 1) / K8_WARPS;
+    const int grid = want < sm_count * per_sm_cached ? want : sm_count * per_sm_cached;   // all CTAs resident
     FusedArgs a2 = a;
     const int NF = DIRS == 2 ? 2 * N + 2 * (a.M_v + a.M_h) : N + 2 * a.M_v;
     // the tensor map depends on the stack's address only: keep the last few (a ring of resident stacks is the common case)
@@ -664,8 +613,8 @@ static cudaError_t launch8_t(const FusedArgs& a, const DeviceCalib& cal, int sm_
     alignas(64) CUtensorMap dummy;
     if (!map) { memset(&dummy, 0, sizeof(dummy)); map = &dummy; }
     a2.use_tmap = map != &dummy;
-    kern<<<grid, (CW + 1) * 32, p.smem, st>>>(a2, cal, *map);
-    *advance = (uint32_t)a.n_tiles + (uint32_t)grid;     // every CTA draws one position past the end
+    kern<<<grid, K8_WARPS * 32, p.smem, st>>>(a2, cal, *map);
+    *advance = (uint32_t)a.n_tiles + (uint32_t)grid * K8_WARPS;     // every warp draws one position past the end
     return cudaGetLastError();
 }
 
@@ -673,12 +622,12 @@ template <int N, int DIRS>
 static cudaError_t launch8_nd(const FusedArgs& a, const DeviceCalib& cal, int sm_count, const Plan8& p, bool exact,
                               Fused8Cache* cache, uint32_t* advance, cudaStream_t st)
 {
-#define S3D_CASE8(MB)                                                                                          \
-    if (p.minb == MB) {                                                                                        \
-        if (exact || DIRS == 1) return launch8_t<N, DIRS, 7, MB, true>(a, cal, sm_count, p, cache, advance, st); \
-        return launch8_t<N, DIRS, 7, MB, (DIRS == 1)>(a, cal, sm_count, p, cache, advance, st);                  \
+#define S3D_CASE8(MB)                                                                                      \
+    if (p.minb == MB) {                                                                                    \
+        if (exact || DIRS == 1) return launch8_t<N, DIRS, MB, true>(a, cal, sm_count, p, cache, advance, st); \
+        return launch8_t<N, DIRS, MB, (DIRS == 1)>(a, cal, sm_count, p, cache, advance, st);                  \
     }
-    S3D_CASE8(3) S3D_CASE8(2)
+    S3D_CASE8(S3D_K8_MINB) S3D_CASE8(2)
 #undef S3D_CASE8
     return cudaErrorInvalidValue;
 }
@@ -689,10 +638,10 @@ cudaError_t launch_fused8(const scan3d_config& c, const FusedArgs& a_in, const D
     Plan8 p;
     if (!plan8(c, &p)) return cudaErrorInvalidValue;
     if (((uintptr_t)a_in.stack & 15) || ((uintptr_t)a_in.roi & 15)) return cudaErrorMisalignedAddress;
+    if (c.dirs == 2 && !a_in.stage_pts) return cudaErrorInvalidValue;
     FusedArgs a = a_in;
-    const int T = 128 * p.cw;
     a.tiles_per_row = 0;
-    a.n_tiles = (int)(((size_t)c.W * c.H + T - 1) / T);
+    a.n_tiles = fused8_num_chunks(c);
     a.dynamic = 1;
     const bool exact = !(c.flags & SCAN3D_FLAG_FAST_TRIANGULATION);
 #define S3D_F8(NN) (c.dirs == 2 ? launch8_nd<NN, 2>(a, cal, sm_count, p, exact, cache, advance, st) : launch8_nd<NN, 1>(a, cal, sm_count, p, exact, cache, advance, st))

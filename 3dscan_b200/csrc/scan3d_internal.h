@@ -70,6 +70,8 @@ struct scan3d_ctx {
     uint32_t* sched_ctr = nullptr;             // k_fused8: work-position counter, never reset ...
     uint32_t sched_base = 0;                   // ... its value at the next launch (advances by n_tiles + grid per launch)
     s3d::Fused8Cache tmaps;
+    float* stage_pts = nullptr;                // k_fused8: staging rings (allocated on first use)
+    uint32_t* stage_vb = nullptr;
 
     // staging for the host-buffer entries
     uint8_t* d_stack = nullptr;
@@ -139,6 +141,8 @@ struct FusedArgs {
     int dynamic;                  // v7: draw work-list positions from that counter instead of b, b+G, ...
     uint32_t* sched_ctr;          // v8: work-position counter (monotonic across launches)
     uint32_t pos_base;            // v8: the counter's value when this launch starts
+    float* stage_pts;             // v8: per-warp rings of staging slots for triangulated points (L2 resident)
+    uint32_t* stage_vb;           // v8: ... and for the ballots of their valid bits (pixel indices / colours)
     int use_tmap;                 // v7: tile loads are one 2-D tensor copy (set by the launcher)
     unsigned long long* trace;    // optional timeline buffer (SCAN3D_TRACE), else null
     const double2* cam_lut; const double2* proj_lut;
@@ -161,6 +165,9 @@ cudaError_t launch_fused7(const scan3d_config& c, const FusedArgs& a, const Devi
 // third cut (scan3d_fused_kernel8.cu, the default): one launch per scan, no consumer barrier.  *advance = how far
 // the launch moves the context's work-position counter
 bool fused8_supported(const scan3d_config& c);
+int fused8_num_chunks(const scan3d_config& c);
+size_t fused8_stage_floats(int sm_count);
+size_t fused8_stage_vb_words(int sm_count);
 cudaError_t launch_fused8(const scan3d_config& c, const FusedArgs& a, const DeviceCalib& cal, int sm_count,
                           Fused8Cache* cache, uint32_t* advance, cudaStream_t st);
 

@@ -272,6 +272,7 @@ def main():
                     help="reference operation order in the normal-equation solve (bit-identical points)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--contexts", type=int, default=1, help="contexts (each on its own stream) the batch alternates over")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="row-shard workload, N>1: how the points reach rank 0")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -295,7 +296,7 @@ def main():
     cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs, flags=flags)
     config = {"workload": args.workload, "frame": [W, H], "projector": [PW, PH], "phase_steps": N,
               "gray_bits": [Mv, Mh][:dirs], "directions": dirs, "frames_per_scan": s3.stack_planes(cfg),
-              "scans_per_gpu_per_step": args.batch, "resident_ring": args.ring,
+              "scans_per_gpu_per_step": args.batch, "resident_ring": args.ring, "contexts_per_gpu": args.contexts,
               "sharding": "frame-parallel scans, no collective" if world > 1 else "single GPU",
               "l2_policy": "inputs larger than L2 (ring of distinct stacks, %.2f GB per GPU)"
                            % (args.ring * s3.stack_planes(cfg) * npix / 1e9),
@@ -374,10 +375,15 @@ def main():
         rois.append(torch.roll(base_roi, shifts=shift, dims=1) if shift else base_roi)
     torch.cuda.synchronize()
 
+    # --contexts 2: the scans of a batch alternate over two contexts on two streams (still one GPU, still
+    # frame-parallel): the tail of one scan's persistent kernel overlaps the start of the next one's
+    side_streams = [torch.cuda.Stream() for _ in range(args.contexts - 1)]
+    ctxs = [ctx] + [s3.Scan3D(cfg, local_rank, cal, stream=st.cuda_stream) for st in side_streams]
+
     def step():
         for b in range(args.batch):
             k = b % args.ring
-            ctx.reconstruct_dev(ring[k].data_ptr(), rois[k].data_ptr())
+            ctxs[b % len(ctxs)].reconstruct_dev(ring[k].data_ptr(), rois[k].data_ptr())
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -385,18 +391,22 @@ def main():
         step()
     sampler.wait_first_row()
     barrier()
-    l0 = ctx.launch_count()
+    l0 = sum(c.launch_count() for c in ctxs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
     ev0.record(stream)
+    for st in side_streams:
+        st.wait_stream(stream)         # every stream starts behind ev0 ...
     for _ in range(args.steps):
         step()
+    for st in side_streams:
+        stream.wait_stream(st)         # ... and ev1 is behind every stream
     ev1.record(stream)
     barrier()
     t_wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count() - l0
+    launches = sum(c.launch_count() for c in ctxs) - l0
     clocks = sampler.stop(t_wall0, t_wall1)
     count = ctx.point_count() if dirs == 2 else 0
     tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -486,6 +496,8 @@ def main():
             except Exception as e:   # the all-core figure above is the contract; this one is extra
                 cpu["single_thread"] = {"error": str(e)}
 
+    for c in ctxs[1:]:
+        c.close()
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,

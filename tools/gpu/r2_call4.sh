@@ -1,5 +1,5 @@
-# round-2 GPU call 3: v8b (per-warp sub-slots) -- parity suite, bench vs v7, ncu
-D=gpurun_out/c3; mkdir -p $D
+# round-2 GPU call 4: warp-autonomous v8 -- parity suite, bench vs v7, ncu
+D=gpurun_out/c4; mkdir -p $D
 timeout 900 python -m pytest tests -x -q -m gpu > $D/pytest.log 2>&1; tail -5 $D/pytest.log
 B="python bench.py --no-e2e --no-cpu-baseline --steps 20"
 timeout 300 $B > $D/v8.json 2> $D/v8.err
@@ -10,7 +10,7 @@ timeout 300 $B --workload c2_1080p_3step_8bit_v > $D/v8_c2.json 2>/dev/null
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fused8 -s 8 -c 1 -o $D/fused8 python bench.py --no-e2e --no-cpu-baseline --steps 1 --batch 4 > $D/ncu.log 2>&1
 python - <<'PY'
 import glob, json
-for f in sorted(glob.glob("gpurun_out/c3/*.json")):
+for f in sorted(glob.glob("gpurun_out/c4/*.json")):
     try:
         d = json.load(open(f))
         print(f"{f:45s} {d['roofline']['avg_launch_us']:8.1f} us/scan  frac {d['roofline']['frac']:.3f}  sm {d['clocks']['sm_mhz']} launches/scan {d['roofline']['launches_per_scan']}")
