@@ -24,6 +24,7 @@ PLANE_MASK_H = 10
 FLAG_POINT_PIXELS = 1
 FLAG_FAST_TRIANGULATION = 2
 FLAG_MODULATION_MASK = 4
+FLAG_STRICT_REFERENCE = 8
 
 _PLANE_DTYPE = {
     PLANE_WRAPPED_V: (np.float32, ()), PLANE_WRAPPED_H: (np.float32, ()),
@@ -165,6 +166,7 @@ def host_lib():
     L = _load("libscan3d_host.so")
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
     L.scan3d_read_bmp8.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), vp, i64]
+    L.scan3d_read_bmp_bgr.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), vp, i64]
     L.scan3d_write_bmp8.argtypes = [C.c_char_p, i32, i32, vp]
     L.scan3d_read_cv_matrix.argtypes = [C.c_char_p, C.c_char_p, i32, i32, vp]
     L.scan3d_load_calibration.argtypes = [C.c_char_p, C.POINTER(Calib)]
@@ -273,6 +275,18 @@ def read_bmp8(path):
         raise Scan3DError(L.scan3d_host_last_error().decode())
     buf = np.empty((h.value, w.value), np.uint8)
     if L.scan3d_read_bmp8(path.encode(), C.byref(w), C.byref(h), _ptr(buf), buf.size):
+        raise Scan3DError(L.scan3d_host_last_error().decode())
+    return buf
+
+
+def read_bmp_bgr(path):
+    """cvLoadImage(path) in colour: [H][W][3] B,G,R (8/save_point_cloud.cpp:59 loads the texture this way)."""
+    w, h = C.c_int(), C.c_int()
+    L = host_lib()
+    if L.scan3d_read_bmp_bgr(path.encode(), C.byref(w), C.byref(h), None, 0):
+        raise Scan3DError(L.scan3d_host_last_error().decode())
+    buf = np.empty((h.value, w.value, 3), np.uint8)
+    if L.scan3d_read_bmp_bgr(path.encode(), C.byref(w), C.byref(h), _ptr(buf), buf.size):
         raise Scan3DError(L.scan3d_host_last_error().decode())
     return buf
 

@@ -29,8 +29,14 @@ if os.environ.get("SCAN3D_BUILD_TRACE") == "1":
 # SCAN3D_BUILD_DEFS="-DS3D_VAR_X=1 ...": experimental kernel variants (tools/build_variants.py builds them into
 # their own SCAN3D_LIBDIR; the default build defines none of them)
 NVCC_FLAGS += [d for d in os.environ.get("SCAN3D_BUILD_DEFS", "").split() if d.startswith("-D")]
-CU_SOURCES = ["scan3d_api.cu", "scan3d_stage_kernels.cu", "scan3d_fused_kernel.cu", "scan3d_fused_kernel7.cu", "scan3d_fused_kernel8.cu",
-              "scan3d_aux_kernels.cu", "scan3d_aux_api.cu"]
+CU_SOURCES = ["scan3d_api.cu", "scan3d_stage_kernels.cu", "scan3d_worklist.cu", "scan3d_fused_kernel7.cu",
+              "scan3d_aux_kernels.cu", "scan3d_aux_api.cu", "scan3d_shard.cu"]
+# SCAN3D_BUILD_V8=1 also compiles the warp-autonomous cut of the single-pass kernel (scan3d_fused_kernel8.cu: parity
+# green, one launch per scan, but slower than k_fused7 on the 12 MP workload -- profiles/r2_optimisation_log.md);
+# it is then selected with SCAN3D_FUSED_IMPL=8
+if os.environ.get("SCAN3D_BUILD_V8") == "1":
+    CU_SOURCES.append("scan3d_fused_kernel8.cu")
+    NVCC_FLAGS.append("-DS3D_BUILD_V8=1")
 HOST_SOURCES = ["scan3d_io.cpp", "scan3d_synth.cpp"]
 COMPAT_SOURCES = ["scan3d_stages.cpp"]
 
@@ -54,7 +60,7 @@ def build_cuda(force=False, verbose=False):
     os.makedirs(LIB, exist_ok=True)
     so = os.path.join(LIB, "libscan3d.so")
     hdr = os.path.join(HERE, "..", "include", "scan3d.h")
-    if not (force or _stale(so, _deps(CSRC, [hdr]))):
+    if not (force or _stale(so, _deps(CSRC, [hdr, os.path.join(HERE, "..", "include", "scan3d_shard.h")]))):
         return so
     from concurrent.futures import ThreadPoolExecutor
 
@@ -74,7 +80,7 @@ def build_cuda(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(len(CU_SOURCES), os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, CU_SOURCES))
     cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-           "-ccbin", "/usr/bin/g++", "-o", so] + objs
+           "-ccbin", "/usr/bin/g++", "-o", so] + objs + ["-lrt"]
     subprocess.check_call(cmd)
     return so
 

@@ -135,65 +135,7 @@ S3A_HD uint8_t bilinear_u8(int v0, int v1, int v2, int v3, int frac)
     return (uint8_t)(s >> 15);  // <= 255 because the weights sum to 2^15
 }
 
-// ---- windowed gather (experimental remap variant, S3D_VAR_REMAP_WINDOW) -----------------------------------
-// The undistortion map is close to the identity, so the 4 consecutive output pixels of a thread usually read
-// the same two source rows and columns that lie within a few bytes of each other.  Then two aligned 8-byte
-// loads per source row (a 16-byte window starting at an 8-byte aligned column) replace the 8 one-byte
-// gathers of that row; the taps come out of the window with a funnel shift.
-struct RemapGroup {        // frame-independent part of a thread's 4 pixels, prepared once per map
-    int fast;              // 1: window path usable; 0: per-tap gathers (borders, strong distortion)
-    int base;              // byte offset of the window in the frame: sy * W + (min sx & ~7)
-    int off[4];            // sx[k] - (min sx & ~7), 0..14
-};
-
-S3A_HD RemapGroup remap_group_prepare(const int16_t* xy /* [4][2] */, int W, int H, bool aligned8)
-{
-    RemapGroup g;
-    g.fast = 0; g.base = 0;
-    for (int k = 0; k < 4; k++) g.off[k] = 0;
-    const int sy = xy[1];
-    int lo = xy[0], hi = xy[0];
-    bool same_row = true;
-    for (int k = 1; k < 4; k++) {
-        same_row = same_row && xy[2 * k + 1] == sy;
-        lo = xy[2 * k] < lo ? xy[2 * k] : lo;
-        hi = xy[2 * k] > hi ? xy[2 * k] : hi;
-    }
-    const int b8 = lo & ~7;
-    // every tap (x, x+1) x (y, y+1) inside the image, the window inside the row, offsets within 0..14
-    if (aligned8 && same_row && sy >= 0 && sy + 1 < H && lo >= 0 && hi + 1 < W && hi - b8 <= 14 && b8 + 16 <= W) {
-        g.fast = 1;
-        g.base = sy * W + b8;
-        for (int k = 0; k < 4; k++) g.off[k] = xy[2 * k] - b8;
-    }
-    return g;
-}
-
-// taps (x, x+1) of one source row out of its 16-byte window w[0..3] (little-endian words): v0 | v1 << 8
-S3A_HD uint32_t window_taps(const uint32_t* w, int o)
-{
-    const int i = o >> 2, s = 8 * (o & 3);
-    const uint32_t lo = i == 0 ? w[0] : i == 1 ? w[1] : i == 2 ? w[2] : w[3];
-    const uint32_t hi = i == 0 ? w[1] : i == 1 ? w[2] : i == 2 ? w[3] : 0u;
-#if defined(__CUDA_ARCH__)
-    return __funnelshift_r(lo, hi, s) & 0xffffu;
-#else
-    return (s ? (lo >> s) | (hi << (32 - s)) : lo) & 0xffffu;
-#endif
-}
-
-// the 4 output pixels of a prepared group for one frame whose two windows have been loaded: packed bytes
-S3A_HD uint32_t remap_group_blend(const RemapGroup& g, const uint32_t* row0, const uint32_t* row1, const int* frac)
-{
-    uint32_t packed = 0;
-    for (int k = 0; k < 4; k++) {
-        const uint32_t a = window_taps(row0, g.off[k]), b = window_taps(row1, g.off[k]);
-        packed |= (uint32_t)bilinear_u8((int)(a & 0xff), (int)(a >> 8), (int)(b & 0xff), (int)(b >> 8), frac[k]) << (8 * k);
-    }
-    return packed;
-}
-
-// ---- tiled staging (experimental remap variant, S3D_VAR_REMAP_TILED) ---------------------------------------
+// ---- tiled staging (k_remap_tiled) ------------------------------------------------------------------------
 // A CTA owns an output tile of TILE_H x TILE_W pixels.  The source pixels its taps touch form a bounding box that
 // is barely larger than the tile (the map is close to the identity); per frame that box is staged in shared
 // memory with aligned 16-byte copies and the taps are gathered from there.  The box is frame-independent.
@@ -230,6 +172,41 @@ S3A_HD bool remap_box_vector_inside(const RemapBox& b, int r, int c, int W, int 
 
 // offset of source pixel (sx, sy) inside the staging buffer (row pitch REMAP_BOX_W)
 S3A_HD int remap_box_offset(const RemapBox& b, int sx, int sy) { return (sy - b.y0) * REMAP_BOX_W + (sx - b.x0); }
+
+// The blend of one output pixel from the staged box in ~10 instructions: the frame-independent weights are kept
+// as two packed pairs of 16-bit integers (wA = row y: w00 | w01 << 16, wB = row y + 1), the taps (x, x + 1) of a
+// row come out of two aligned 32-bit words of the box with one funnel shift, and two 16-bit x 8-bit two-way dot
+// products (IDP.2A) accumulate bilinear_u8()'s sum exactly (integers: the order of the products does not matter).
+S3A_HD void bilinear_weight_pairs(int frac, uint32_t* wA, uint32_t* wB)
+{
+    const uint32_t ax = frac & 31, ay = (frac >> 5) & 31;
+    *wA = (32 * (32 - ay) * (32 - ax)) | ((32 * (32 - ay) * ax) << 16);      // each <= 32768: fits 16 unsigned bits
+    *wB = (32 * ay * (32 - ax)) | ((32 * ay * ax) << 16);
+}
+// bytes box[off], box[off + 1] in bits 0..15 (the box is 4-byte aligned and padded by one word)
+S3A_HD uint32_t box_taps(const uint8_t* box, int off)
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(box + (off & ~3));
+    const uint32_t lo = w[0], hi = w[1];
+    const int sh = 8 * (off & 3);
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+S3A_HD uint32_t dot2_u16_u8(uint32_t w, uint32_t taps, uint32_t acc)
+{
+#if defined(__CUDA_ARCH__)
+    return __dp2a_lo(w, taps, acc);
+#else
+    return acc + (w & 0xffffu) * (taps & 0xffu) + (w >> 16) * ((taps >> 8) & 0xffu);
+#endif
+}
+S3A_HD uint32_t bilinear_u8_pairs(uint32_t wA, uint32_t wB, uint32_t taps_row0, uint32_t taps_row1)
+{
+    return dot2_u16_u8(wB, taps_row1, dot2_u16_u8(wA, taps_row0, 1u << 14)) >> 15;
+}
 
 // register_point_clouds' rotation about Y for a cloud captured at turntable angle theta (degrees,
 // float): R(0,0) = R(2,2) = (float)cos(theta*Pi/180.0), R(0,2) = (float)(-1.0f*sin(...)),

@@ -148,7 +148,7 @@ int scan3d_create(const scan3d_config* cfg, int device, scan3d_ctx** out)
         }
         CK(dalloc(&ctx->d_count, 4));
         CK(cudaMemsetAsync(ctx->d_count, 0, 16, ctx->stream));
-        const int ntiles = std::max(fused_num_tiles(ctx->cfg), fused8_num_chunks(ctx->cfg) + 1);
+        const int ntiles = fused_num_tiles(ctx->cfg);
         CK(dalloc(&ctx->tile_state, (size_t)ntiles + 1));
         CK(cudaMemsetAsync(ctx->tile_state, 0, ((size_t)ntiles + 1) * 8, ctx->stream));
         if (getenv("SCAN3D_TRACE")) {
@@ -206,7 +206,7 @@ void scan3d_destroy(scan3d_ctx* ctx)
     void* ptrs[] = {ctx->cam_lut, ctx->proj_lut, ctx->atan_tab, ctx->nstep_w, ctx->wrapped[0], ctx->wrapped[1],
                     ctx->unwrapped[0], ctx->unwrapped[1], ctx->code[0], ctx->code[1], ctx->mask[0],
                     ctx->mask[1], ctx->valid, ctx->cpmap, ctx->xyz, ctx->pts, ctx->pix, ctx->rgb,
-                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->sched_ctr, ctx->stage_pts, ctx->stage_vb, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff, ctx->pattern_profiles,
+                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->sched_ctr, ctx->stage_pts, ctx->stage_vb, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff, ctx->roi_strict, ctx->pattern_profiles,
                     ctx->undist_xy[0], ctx->undist_xy[1], ctx->undist_frac[0], ctx->undist_frac[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -316,6 +316,18 @@ static int ensure_stage_planes(scan3d_ctx* ctx, int dir)
 
 static inline float* points_of(const scan3d_ctx* ctx) { return ctx->pts_ext ? ctx->pts_ext : ctx->pts; }
 
+// SCAN3D_FLAG_STRICT_REFERENCE: replace the caller's ROI by the plane check_I_mod_criteria derives from it as committed
+static int strict_roi(scan3d_ctx* ctx, const uint8_t** roi_dev)
+{
+    if (!(ctx->cfg.flags & SCAN3D_FLAG_STRICT_REFERENCE)) return SCAN3D_OK;
+    const size_t n = (size_t)ctx->cfg.W * ctx->cfg.H_total;
+    if (!ctx->roi_strict) CK(dalloc(&ctx->roi_strict, n));
+    CK(launch_strict_roi(*roi_dev, ctx->roi_strict, n, ctx->cfg.N, ctx->stream));
+    ctx->launches++;
+    *roi_dev = ctx->roi_strict;
+    return SCAN3D_OK;
+}
+
 static int roi_bytes(const scan3d_ctx* ctx, size_t* out)
 {
     *out = (size_t)ctx->cfg.W * ctx->cfg.H_total;
@@ -330,6 +342,10 @@ int scan3d_compute_wrapped_phase_dev(scan3d_ctx* ctx, int dir, const uint8_t* fr
     int rc = ensure_stage_planes(ctx, dir);
     if (rc) return rc;
     const Shape s = shape_of(ctx->cfg);
+    if (!ctx->in_reconstruct) {       // (scan3d_reconstruct_dev has already done it)
+        rc = strict_roi(ctx, &roi_dev);
+        if (rc) return rc;
+    }
     if (ctx->cfg.flags & SCAN3D_FLAG_MODULATION_MASK) {
         if (!ctx->roi_eff) CK(dalloc(&ctx->roi_eff, npix(ctx)));
         CK(launch_modulation_roi(s, fringe_dev, roi_dev, ctx->roi_eff, ctx->stream));
@@ -341,7 +357,7 @@ int scan3d_compute_wrapped_phase_dev(scan3d_ctx* ctx, int dir, const uint8_t* fr
     ctx->launches += 2;
     ctx->have_wrapped[dir] = true;
     ctx->have_unwrapped[dir] = false;
-    ctx->have_cpmap = ctx->have_xyz = ctx->have_points = false;
+    ctx->have_cpmap = ctx->have_valid = ctx->have_xyz = ctx->have_points = false;
     return SCAN3D_OK;
 }
 
@@ -378,7 +394,7 @@ int scan3d_unwrap_phase_dev(scan3d_ctx* ctx, int dir, const uint8_t* gray_dev, c
                      ctx->unwrapped[dir], ctx->stream));
     ctx->launches++;
     ctx->have_unwrapped[dir] = true;
-    ctx->have_cpmap = ctx->have_xyz = ctx->have_points = false;
+    ctx->have_cpmap = ctx->have_valid = ctx->have_xyz = ctx->have_points = false;
     return SCAN3D_OK;
 }
 
@@ -411,7 +427,7 @@ int scan3d_compute_c_p_map(scan3d_ctx* ctx)
     CK(launch_cpmap(s, ctx->cfg.fw_v, ctx->cfg.fw_h, ctx->unwrapped[0], ctx->unwrapped[1], ctx->mask[0],
                     ctx->mask[1], ctx->cpmap, ctx->valid, ctx->stream));
     ctx->launches++;
-    ctx->have_cpmap = true;
+    ctx->have_cpmap = ctx->have_valid = true;
     ctx->have_xyz = ctx->have_points = false;
     return SCAN3D_OK;
 }
@@ -471,6 +487,7 @@ static int reconstruct_stagewise(scan3d_ctx* ctx, const uint8_t* stack, const ui
     }
     if (c.dirs == 1) {
         CK(cudaMemcpyAsync(ctx->valid, ctx->mask[0], n, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->have_valid = true;
         return SCAN3D_OK;
     }
     int rc = scan3d_compute_c_p_map(ctx);
@@ -485,10 +502,16 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     if (!ctx || !stack_dev || !roi_dev) return fail(ctx, SCAN3D_ERR_ARG, "null argument");
     if (ctx->cfg.dirs == 2 && !ctx->has_calib) return fail(ctx, SCAN3D_ERR_STATE, "reconstruct before set_calibration");
     CK(cudaSetDevice(ctx->device));
-    int stages = 0;
-    size_t smem = 0;
-    if (!ctx->fast_div_ok || (ctx->cfg.flags & SCAN3D_FLAG_MODULATION_MASK) || !fused_supported(ctx->cfg, &stages, &smem))
-        return reconstruct_stagewise(ctx, stack_dev, roi_dev);
+    {
+        const int rc = strict_roi(ctx, &roi_dev);
+        if (rc) return rc;
+    }
+    if (!ctx->fast_div_ok || (ctx->cfg.flags & SCAN3D_FLAG_MODULATION_MASK) || !fused7_supported(ctx->cfg)) {
+        ctx->in_reconstruct = true;
+        const int rc = reconstruct_stagewise(ctx, stack_dev, roi_dev);
+        ctx->in_reconstruct = false;
+        return rc;
+    }
     const scan3d_config& c = ctx->cfg;
     FusedArgs a{};
     a.stack = stack_dev; a.roi = roi_dev;
@@ -502,11 +525,12 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     if (ctx->trace) CK(cudaMemsetAsync(ctx->trace, 0, (size_t)1024 * 64 * 8 * 8, ctx->stream));   // diagnostics only
     a.epoch = ++ctx->epoch;
     if ((ctx->epoch & 0x3fffffffu) == 0) {   // epoch wrapped: clear the look-back words once
-        CK(cudaMemsetAsync(ctx->tile_state, 0, ((size_t)std::max(fused_num_tiles(c), fused8_num_chunks(c) + 1) + 1) * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->tile_state, 0, ((size_t)fused_num_tiles(c) + 1) * 8, ctx->stream));
         a.epoch = ++ctx->epoch;
     }
     a.W = c.W; a.H = c.H; a.row0 = c.row0; a.H_total = c.H_total; a.PW = c.PW; a.PH = c.PH;
     a.N = c.N; a.M_v = c.M_v; a.M_h = c.M_h; a.fw_v = c.fw_v; a.fw_h = c.fw_h;
+#if S3D_BUILD_V8
     static const int impl = getenv("SCAN3D_FUSED_IMPL") ? atoi(getenv("SCAN3D_FUSED_IMPL")) : 7;
     if (impl >= 8 && fused8_supported(c)) {
         a.sched_ctr = ctx->sched_ctr;
@@ -521,16 +545,17 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
         CK(launch_fused8(c, a, ctx->dcal, ctx->sm_count, &ctx->tmaps, &advance, ctx->stream));
         ctx->sched_base += advance;
         ctx->launches += 1;   // the one persistent kernel
-    } else {
-        const bool use7 = impl != 6 && fused7_supported(c);
-        if (use7) CK(launch_fused7(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
-        else CK(launch_fused(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
+    } else
+#endif
+    {
+        CK(launch_fused7(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
         ctx->launches += 3;   // work-list flags, work-list scan, persistent fused kernel
     }
     ctx->have_wrapped[0] = ctx->have_wrapped[1] = false;
     ctx->have_unwrapped[0] = true;
     ctx->have_unwrapped[1] = c.dirs == 2;
     ctx->have_cpmap = c.dirs == 2;
+    ctx->have_valid = true;
     ctx->have_xyz = false;
     ctx->have_points = c.dirs == 2;
     return SCAN3D_OK;
@@ -577,6 +602,21 @@ static void* plane_ptr(scan3d_ctx* ctx, int plane, size_t* elt)
     }
 }
 
+// has the plane been produced by a compute entry since the context was created / the inputs last changed?
+static bool plane_ready(const scan3d_ctx* ctx, int plane)
+{
+    switch (plane) {
+        case SCAN3D_PLANE_WRAPPED_V: case SCAN3D_PLANE_MASK: return ctx->have_wrapped[0];
+        case SCAN3D_PLANE_WRAPPED_H: case S3D_PLANE_MASK_H: return ctx->have_wrapped[1];
+        case SCAN3D_PLANE_UNWRAPPED_V: case SCAN3D_PLANE_CODE_V: return ctx->have_unwrapped[0];
+        case SCAN3D_PLANE_UNWRAPPED_H: case SCAN3D_PLANE_CODE_H: return ctx->have_unwrapped[1];
+        case SCAN3D_PLANE_VALID: return ctx->have_valid;
+        case SCAN3D_PLANE_CPMAP: return ctx->have_cpmap;
+        case SCAN3D_PLANE_XYZ: return ctx->have_xyz;
+        default: return false;
+    }
+}
+
 int64_t scan3d_plane_bytes(const scan3d_ctx* ctx, int plane)
 {
     if (!ctx) return 0;
@@ -587,7 +627,7 @@ int64_t scan3d_plane_bytes(const scan3d_ctx* ctx, int plane)
 
 void* scan3d_device_plane(scan3d_ctx* ctx, int plane)
 {
-    if (!ctx) return nullptr;
+    if (!ctx || !plane_ready(ctx, plane)) return nullptr;     // (a plane nothing has written is not handed out)
     size_t elt;
     return plane_ptr(ctx, plane, &elt);
 }
@@ -597,7 +637,9 @@ int scan3d_get_plane(scan3d_ctx* ctx, int plane, void* dst_host)
     if (!ctx || !dst_host) return fail(ctx, SCAN3D_ERR_ARG, "null argument");
     size_t elt;
     void* src = plane_ptr(ctx, plane, &elt);
-    if (!src) return fail(ctx, SCAN3D_ERR_STATE, "plane not available");
+    if (!src || !plane_ready(ctx, plane))
+        return fail(ctx, SCAN3D_ERR_STATE, "plane not available: no compute entry has produced it (the single-pass entry "
+                                           "keeps wrapped phases and per-direction masks in registers)");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(dst_host, src, elt * npix(ctx), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -846,16 +888,19 @@ int scan3d_debug_atan2(scan3d_ctx* ctx, const double* y_host, const double* x_ho
     CK(cudaSetDevice(ctx->device));
     double *dy = nullptr, *dx = nullptr;
     float* dout = nullptr;
-    CK(cudaMalloc((void**)&dy, (size_t)n * 8));
-    CK(cudaMalloc((void**)&dx, (size_t)n * 8));
-    CK(cudaMalloc((void**)&dout, (size_t)n * 4));
-    CK(cudaMemcpyAsync(dy, y_host, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(dx, x_host, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(launch_debug_atan2(dy, dx, dout, n, mode, ctx->atan_tab, ctx->stream));
-    ctx->launches++;
-    CK(cudaMemcpyAsync(out_host, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaMalloc((void**)&dy, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dx, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dout, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dy, y_host, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x_host, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_debug_atan2(dy, dx, dout, n, mode, ctx->atan_tab, ctx->stream);
+    if (e == cudaSuccess) {
+        ctx->launches++;
+        e = cudaMemcpyAsync(out_host, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    const cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     cudaFree(dy); cudaFree(dx); cudaFree(dout);
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, SCAN3D_ERR_CUDA, cudaGetErrorString(e != cudaSuccess ? e : e2));
     return SCAN3D_OK;
 }
 

@@ -46,11 +46,22 @@ static int ensure_map(scan3d_ctx* ctx, int kind, int W, int H)
 {
     if (ctx->undist_xy[kind]) return SCAN3D_OK;
     const size_t n = (size_t)W * H;
-    CK(cudaMalloc((void**)&ctx->undist_xy[kind], n * sizeof(short2)));
-    CK(cudaMalloc((void**)&ctx->undist_frac[kind], n * sizeof(uint16_t)));
+    short2* xy = nullptr;
+    uint16_t* frac = nullptr;
     const double* K = kind == 0 ? ctx->hcal.Kc : ctx->hcal.Kp;
     const double* d = kind == 0 ? ctx->hcal.dc : ctx->hcal.dp;
-    CK(launch_undistort_map(K, d, W, H, ctx->undist_xy[kind], ctx->undist_frac[kind], ctx->stream));
+    cudaError_t e = cudaMalloc((void**)&xy, n * sizeof(short2));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&frac, n * sizeof(uint16_t));
+    if (e == cudaSuccess) e = launch_undistort_map(K, d, W, H, xy, frac, ctx->stream);
+    if (e != cudaSuccess) {      // both maps or none: a half-built pair must never look usable
+        cudaFree(xy);
+        cudaFree(frac);
+        cudaGetLastError();
+        ctx->err = std::string("undistortion map: ") + cudaGetErrorString(e);
+        return SCAN3D_ERR_CUDA;
+    }
+    ctx->undist_xy[kind] = xy;
+    ctx->undist_frac[kind] = frac;
     ctx->launches++;
     return SCAN3D_OK;
 }

@@ -3,38 +3,16 @@
 //
 //   k_undistort_map   cv::undistort's fixed-point map, once per calibration and device
 //                     (2/project_pattern.cpp:220: the reference rebuilds it for every captured frame)
-//   k_remap_frames    cv::remap of a whole captured stack through that map: the map entry of a pixel is
-//                     read once and applied to every frame (F bytes in + F bytes out + 6 B map per pixel)
+//   k_remap_tiled     cv::remap of a whole captured stack through that map: the map entry of a pixel is read once
+//                     and applied to every frame (F bytes in + F bytes out + 6 B map per pixel).  One CTA per
+//                     8 x 256 output tile; per frame the tile's source box (the map is close to the identity) is
+//                     staged in shared memory with 16-byte cp.async copies, double-buffered over the frame loop,
+//                     and blended from there: ~10 instructions per output byte (scan3d_aux_math.h)
+//   k_remap_frames    the same through per-tap global gathers: any width, any distortion (fallback)
 //   k_roi_fill        image_scissor's scan-line fill (m_tech_project_console.cpp:186-229)
 //   k_register_points register_point_clouds' rigid transform (9/register_point_clouds.cpp:117-137)
 #include "scan3d_internal.h"
 #include "../common/scan3d_aux_math.h"
-
-// Experimental variants of k_remap_frames (tools/build_variants.py; off in the default build):
-//   S3D_VAR_REMAP_UNROLL=n  frame loop unrolled n times (loads of n frames in flight per thread)
-//   S3D_VAR_REMAP_WINDOW    two aligned 8-byte loads per source row instead of 8 one-byte gathers when a thread's
-//                           4 pixels allow it (scan3d_aux_math.h, "windowed gather"; 96 % of the groups at 12 MP)
-#ifndef S3D_VAR_REMAP_UNROLL
-#define S3D_VAR_REMAP_UNROLL 1
-#endif
-#ifndef S3D_VAR_REMAP_WINDOW
-#define S3D_VAR_REMAP_WINDOW 0
-#endif
-//   S3D_VAR_REMAP_TILED     2-D output tiles, the tile's source box staged in shared memory per frame with 16-byte
-//                           cp.async copies (double-buffered over the frame loop), taps gathered from shared memory
-#ifndef S3D_VAR_REMAP_TILED
-#define S3D_VAR_REMAP_TILED 0
-#endif
-#ifndef S3D_VAR_REMAP_TILED_MINB
-#define S3D_VAR_REMAP_TILED_MINB 3      // CTAs per SM the tiled kernel is compiled for (3: 80 registers, 76 B of spill; 2: 128, none)
-#endif
-#define S3D_PRAGMA_(x) _Pragma(#x)
-#if S3D_VAR_REMAP_UNROLL > 1
-#define S3D_UNROLL_N_(n) S3D_PRAGMA_(unroll n)
-#define S3D_FRAME_UNROLL S3D_UNROLL_N_(S3D_VAR_REMAP_UNROLL)
-#else
-#define S3D_FRAME_UNROLL
-#endif
 
 namespace s3d {
 
@@ -88,26 +66,6 @@ __global__ void __launch_bounds__(256) k_remap_frames(const uint8_t* __restrict_
                 fr[k] = map_frac[p + k];
             }
         }
-#if S3D_VAR_REMAP_WINDOW
-        if (VEC == 4) {
-            int16_t xy16[8];
-#pragma unroll
-            for (int k = 0; k < 4; k++) { xy16[2 * k] = xy[k].x; xy16[2 * k + 1] = xy[k].y; }
-            const s3a::RemapGroup grp = s3a::remap_group_prepare(xy16, W, H, (W & 7) == 0 && ((uintptr_t)src & 7) == 0);
-            if (grp.fast) {
-                S3D_FRAME_UNROLL
-                for (int f = 0; f < n_frames; f++) {
-                    const uint8_t* s = src + (size_t)f * plane + grp.base;
-                    const uint2 a0 = __ldg(reinterpret_cast<const uint2*>(s)), a1 = __ldg(reinterpret_cast<const uint2*>(s + 8));
-                    const uint2 b0 = __ldg(reinterpret_cast<const uint2*>(s + W)), b1 = __ldg(reinterpret_cast<const uint2*>(s + W + 8));
-                    const uint32_t r0[4] = {a0.x, a0.y, a1.x, a1.y}, r1[4] = {b0.x, b0.y, b1.x, b1.y};
-                    *reinterpret_cast<uint32_t*>(dst + (size_t)f * plane + p) = s3a::remap_group_blend(grp, r0, r1, fr);
-                }
-                continue;
-            }
-        }
-#endif
-        S3D_FRAME_UNROLL
         for (int f = 0; f < n_frames; f++) {
             const uint8_t* s = src + (size_t)f * plane;
             uint32_t packed = 0;
@@ -126,7 +84,6 @@ __global__ void __launch_bounds__(256) k_remap_frames(const uint8_t* __restrict_
     }
 }
 
-#if S3D_VAR_REMAP_TILED
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -135,13 +92,21 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+#ifndef S3D_REMAP_STAGES
+#define S3D_REMAP_STAGES 6
+#endif
+constexpr int REMAP_STAGES = S3D_REMAP_STAGES;
 // One CTA (256 threads) per output tile of REMAP_TILE_H x REMAP_TILE_W pixels; thread t owns the 4-pixel groups
 // (row t/64, columns 4*(t%64)..+3) and (row t/64 + 4, same columns).  W % 16 == 0.
-__global__ void __launch_bounds__(256, S3D_VAR_REMAP_TILED_MINB) k_remap_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+__global__ void __launch_bounds__(256, 3) k_remap_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                       const short2* __restrict__ map_xy, const uint16_t* __restrict__ map_frac,
                                                       int W, int H, int n_frames)
 {
-    __shared__ __align__(16) uint8_t box[2][s3a::REMAP_BOX_H * s3a::REMAP_BOX_W];
+    // ring of staged source boxes: REMAP_STAGES - 1 frames are in flight per CTA while one is blended (the kernel is
+    // bound by the bytes it keeps in flight: 2 buffers gave 0.31 of the HBM roofline) (+ one vector per buffer: the
+    // taps are cut out of word pairs)
+    constexpr int NS = REMAP_STAGES;
+    __shared__ __align__(16) uint8_t box[NS][s3a::REMAP_BOX_H * s3a::REMAP_BOX_W + 16];
     __shared__ int ext[4];   // min sx, max sx, min sy, max sy over the tile
     const size_t plane = (size_t)W * H;
     const int tiles_x = (W + s3a::REMAP_TILE_W - 1) / s3a::REMAP_TILE_W;
@@ -201,52 +166,67 @@ __global__ void __launch_bounds__(256, S3D_VAR_REMAP_TILED_MINB) k_remap_tiled(c
         return;
     }
 
+    // the box's 16-byte vectors, at most 2 per thread (16 rows x 18 vectors = 288): where each lands in the buffer and
+    // where it comes from in a frame -- the same for every frame
     const int vec_per_row = b.w >> 4, n_vec = b.rows * vec_per_row;
+    int v_dst[2], v_kind[2];          // kind: 0 = none, 1 = copy, 2 = outside the image (constant border: zeros)
+    long long v_src[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int v = t + 256 * q;
+        v_kind[q] = 0; v_dst[q] = 0; v_src[q] = 0;
+        if (v < n_vec) {
+            const int r = v / vec_per_row, c = v - r * vec_per_row;
+            v_dst[q] = r * s3a::REMAP_BOX_W + 16 * c;
+            v_src[q] = (long long)(b.y0 + r) * W + (b.x0 + 16 * c);
+            v_kind[q] = s3a::remap_box_vector_inside(b, r, c, W, H) ? 1 : 2;
+        }
+    }
     auto stage = [&](int f, int buf) {
         const uint8_t* s = src + (size_t)f * plane;
-        for (int v = t; v < n_vec; v += 256) {
-            const int r = v / vec_per_row, c = v - r * vec_per_row;
-            uint8_t* d = &box[buf][r * s3a::REMAP_BOX_W + 16 * c];
-            if (s3a::remap_box_vector_inside(b, r, c, W, H))
-                cp_async16(d, s + (long long)(b.y0 + r) * W + (b.x0 + 16 * c));
-            else
-                *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);     // constant border
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            if (v_kind[q] == 1) cp_async16(&box[buf][v_dst[q]], s + v_src[q]);
+            else if (v_kind[q] == 2) *reinterpret_cast<uint4*>(&box[buf][v_dst[q]]) = make_uint4(0, 0, 0, 0);
         }
         cp_async_commit();
     };
+    // frame-independent per pixel: offset of its first tap in the box, the 4 weights as two packed pairs
     int off[2][4];
+    uint32_t wA[2][4], wB[2][4];
 #pragma unroll
     for (int g = 0; g < 2; g++)
 #pragma unroll
-        for (int k = 0; k < 4; k++) off[g][k] = have[g] ? s3a::remap_box_offset(b, xy[g][k].x, xy[g][k].y) : 0;
+        for (int k = 0; k < 4; k++) {
+            off[g][k] = have[g] ? s3a::remap_box_offset(b, xy[g][k].x, xy[g][k].y) : 0;
+            s3a::bilinear_weight_pairs(fr[g][k], &wA[g][k], &wB[g][k]);
+        }
 
     if (n_frames <= 0) return;
-    stage(0, 0);
+    // every iteration commits exactly one copy group (an empty one past the last frame), so "at most NS - 2 groups
+    // pending" always means "frame f has landed"
+    for (int f = 0; f < NS - 1; f++) {
+        if (f < n_frames) stage(f, f);
+        else cp_async_commit();
+    }
     for (int f = 0; f < n_frames; f++) {
-        const int buf = f & 1;
-        if (f + 1 < n_frames) {
-            stage(f + 1, buf ^ 1);     // the other buffer was released by the barrier that closed frame f - 1
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        const uint8_t* sb = box[buf];
+        cp_async_wait<NS - 2>();
+        __syncthreads();               // frame f is visible to everybody, and everybody is done with frame f - 1 ...
+        if (f + NS - 1 < n_frames) stage(f + NS - 1, (f + NS - 1) % NS);      // ... whose buffer this refills
+        else cp_async_commit();
+        const uint8_t* sb = box[f % NS];
 #pragma unroll
         for (int g = 0; g < 2; g++) {
             if (!have[g]) continue;
             uint32_t packed = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint8_t* p = sb + off[g][k];
-                packed |= (uint32_t)s3a::bilinear_u8(p[0], p[1], p[s3a::REMAP_BOX_W], p[s3a::REMAP_BOX_W + 1], fr[g][k]) << (8 * k);
-            }
+            for (int k = 0; k < 4; k++)
+                packed |= s3a::bilinear_u8_pairs(wA[g][k], wB[g][k], s3a::box_taps(sb, off[g][k]),
+                                                 s3a::box_taps(sb, off[g][k] + s3a::REMAP_BOX_W)) << (8 * k);
             *reinterpret_cast<uint32_t*>(dst + (size_t)f * plane + pix[g]) = packed;
         }
-        __syncthreads();
     }
 }
-#endif
 
 // One CTA per row.  The reference's nested search (start pixel, next non-zero pixel, fill between,
 // restart AT the end pixel) fills every zero pixel that lies strictly between the first and the last
@@ -317,13 +297,11 @@ cudaError_t launch_remap_frames(const uint8_t* src, uint8_t* dst, const short2* 
                                 int H, int n_frames, int sm_count, cudaStream_t st)
 {
     const size_t plane = (size_t)W * H;
-#if S3D_VAR_REMAP_TILED
     if (W % 16 == 0 && (((uintptr_t)src | (uintptr_t)dst) % 16 == 0)) {
         const int tiles = ((W + s3a::REMAP_TILE_W - 1) / s3a::REMAP_TILE_W) * ((H + s3a::REMAP_TILE_H - 1) / s3a::REMAP_TILE_H);
         k_remap_tiled<<<tiles, 256, 0, st>>>(src, dst, map_xy, map_frac, W, H, n_frames);
         return cudaGetLastError();
     }
-#endif
     const bool vec = (plane % 4 == 0) && (((uintptr_t)src | (uintptr_t)dst) % 4 == 0);
     const size_t groups = vec ? plane / 4 : plane;
     size_t blocks = (groups + 255) / 256;

@@ -93,39 +93,7 @@ constexpr int regs7(int cw, int minb)
     return r > 255 ? 255 : (r / 8) * 8;
 }
 
-// back-off of the IO warp's event loop between empty polls (experimental knob, tools/build_variants.py: the three
-// IO warps of an SM issue ~10 % of the kernel's instructions, most of them polling)
-// S3D_VAR_PASS_UNROLL=1: both 2-pixel decode passes unrolled (8 independent FP64 chains per thread, ~600 more instructions)
-#ifndef S3D_VAR_PASS_UNROLL
-#define S3D_VAR_PASS_UNROLL 0
-#endif
-#ifndef S3D_VAR_WARP_SKIP
-#define S3D_VAR_WARP_SKIP 1
-#endif
-#ifndef S3D_VAR_IO_SLEEP_NS
-#define S3D_VAR_IO_SLEEP_NS 250
-#endif
 
-#if S3D_VAR_COLD_OUTLINE
-// mask recurrence for the 4 pixels of a thread next to a ROI edge or the frame border (rare): out of line
-static __device__ __noinline__ uint32_t mask_slow7(const uint8_t* sroi, int roi_row, int lp0, int xt, int y, int W, int H_total)
-{
-    uint32_t mbits = 0;
-    const uint32_t centre = *reinterpret_cast<const uint32_t*>(sroi + 2 * roi_row + lp0 + ROI_HALO);
-    if (centre != 0) {
-#pragma unroll 1
-        for (int j = 0; j < 4; j++) {
-            const int x = xt + j;
-            auto inv = [&](int gx, int gy) { return sroi[(gy - y + 2) * roi_row + (lp0 + j + (gx - x) + ROI_HALO)] == 0; };
-            bool v = !inv(x, y);
-            const bool border = x == 0 || y == 0 || x == W - 1 || y == H_total - 1;
-            if (v && !border) v = !mask_trigger(x, y, W, H_total, inv);
-            mbits |= (v ? 1u : 0u) << j;
-        }
-    }
-    return mbits;
-}
-#endif
 
 template <int N, int DIRS, int CW, int MINB, bool EXACT>
 __global__ void __launch_bounds__((CW + 1) * 32) __maxnreg__(regs7(CW, MINB))
@@ -382,7 +350,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     }
                 }
             }
-            if (!progressed) __nanosleep(S3D_VAR_IO_SLEEP_NS);
+            if (!progressed) __nanosleep(250);
         }
         return;
     }
@@ -420,9 +388,6 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     }
                 if (any_zero == 0) { mbits = 0xf; fast = true; }
             }
-#if S3D_VAR_COLD_OUTLINE
-            if (!fast) mbits = mask_slow7(sroi, G.roi_row, lp0, xt, y, W, a.H_total);
-#else
             if (!fast) {
                 const uint32_t centre = *reinterpret_cast<const uint32_t*>(sroi + 2 * G.roi_row + lp0 + ROI_HALO);
                 if (centre != 0) {
@@ -439,7 +404,6 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     }
                 }
             }
-#endif
             if (mbits) {
                 fringe_terms<N>(sw, 0, WPF, tid, Tv);
                 gray_bits(sw, N, N + a.M_v, a.M_v, WPF, tid, gvA, gvB);
@@ -458,7 +422,6 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
         // ---------------- FP64 phase (registers only) ----------------
         uint32_t vbits = 0;
         int4 cp01 = make_int4(0, 0, 0, 0), cp23 = cp01;   // the 4 pixels' correspondences, for the triangulation below
-#if S3D_VAR_WARP_SKIP
         // a warp whose 128 pixels hold no pixel of the mask writes the constant outputs and leaves its issue slots
         // to the other warps of the SM (about one warp in ten inside a tile that does hold ROI pixels)
         const bool warp_has_px = __any_sync(0xffffffffu, mbits != 0);
@@ -475,45 +438,20 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
             }
         }
         if (active && warp_has_px) {
-#else
-        if (active) {
-#endif
             // Two passes of 2 pixels: inside a pass everything is straight-line (2 pixels x 2
             // directions interleave in the FP64 pipe); the pass loop is rolled to keep the
             // consumer loop inside the instruction cache.
             const size_t g = (size_t)p0 + lp0;
-#if S3D_VAR_PASS_UNROLL
-#pragma unroll
-#else
 #pragma unroll 1
-#endif
             for (int h = 0; h < 2; h++) {
                 float r_unwv[2], r_unwh[2];
                 int r_cv[2], r_ch[2];
                 int2 r_cp[2];
                 uint32_t vb = 0;
-#if S3D_VAR_TERM_ROTATE
-                // second pass: pixels 2,3 move into the lanes of pixels 0,1, so that every lane selection below
-                // is a compile-time one (the per-term run-time selects were ~100 of the pass's 589 instructions)
-                if (h) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        Tv.t[k][0] = Tv.t[k][1];
-                        if (DIRS == 2) Th.t[k][0] = Th.t[k][1];
-                    }
-                    gvA >>= 16; gvB >>= 16; ghA >>= 16; ghB >>= 16;
-                    mbits >>= 2;
-                }
-#endif
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
-#if S3D_VAR_TERM_ROTATE
-                    const int j = u;
-                    const int x = xt + 2 * h + u;
-#else
                     const int j = 2 * h + u;
                     const int x = xt + j;
-#endif
                     const bool m = (mbits >> j) & 1u;
                     const int cv = code_of(gvA, gvB, j, a.M_v);
                     const float wv = add_pi(phase_of<N>(Tv, j, tab));                    // 4/phase_unwrap.cpp:290

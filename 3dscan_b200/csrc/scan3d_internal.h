@@ -42,6 +42,7 @@ struct scan3d_ctx {
     uint8_t* pattern_profiles = nullptr;   // scan3d_generate_patterns: 1-D profiles of both directions' patterns
     bool have_profiles[2] = {false, false};
     uint8_t* roi_eff = nullptr;    // SCAN3D_FLAG_MODULATION_MASK: ROI && modulation criterion of the current direction
+    uint8_t* roi_strict = nullptr; // SCAN3D_FLAG_STRICT_REFERENCE: (ROI == 1) && N in {3, 4}, whole frame
     double* nstep_w = nullptr;     // sin[64] then cos[64] (generic-N extension)
     short2* undist_xy[2] = {nullptr, nullptr};     // cv::undistort's fixed-point map of the camera [0] / projector [1]
     uint16_t* undist_frac[2] = {nullptr, nullptr}; // (scan3d_undistort_frames; built on first use per calibration)
@@ -80,7 +81,8 @@ struct scan3d_ctx {
     // stage bookkeeping
     bool have_wrapped[2] = {false, false};
     bool have_unwrapped[2] = {false, false};
-    bool have_cpmap = false, have_xyz = false, have_points = false;
+    bool have_cpmap = false, have_valid = false, have_xyz = false, have_points = false;
+    bool in_reconstruct = false;   // stage entries called from scan3d_reconstruct_dev's stage chain
 };
 
 namespace s3d {
@@ -104,6 +106,7 @@ inline Shape shape_of(const scan3d_config& c)
 cudaError_t launch_mask(const Shape& s, const uint8_t* roi_full, uint8_t* mask, cudaStream_t st);
 cudaError_t launch_expand_patterns(const uint8_t* profiles, int profile_len, int n_patterns, uint8_t* out, int PW, int PH,
                                    int dir, cudaStream_t st);
+cudaError_t launch_strict_roi(const uint8_t* roi, uint8_t* roi_eff, size_t n, int N, cudaStream_t st);
 cudaError_t launch_modulation_roi(const Shape& s, const uint8_t* fringe, const uint8_t* roi, uint8_t* roi_eff, cudaStream_t st);
 cudaError_t launch_wrapped(const Shape& s, int N, const uint8_t* fringe, const uint8_t* roi_full,
                            float* wrapped, const double* atan_tab, const double* nstep_w,
@@ -152,12 +155,9 @@ struct FusedArgs {
     int N, M_v, M_h, fw_v, fw_h;
     int n_tiles, tiles_per_row;
 };
-bool fused_supported(const scan3d_config& c, int* stages_out, size_t* smem_out);
 int fused_num_tiles(const scan3d_config& c);
-cudaError_t launch_fused(const scan3d_config& c, const FusedArgs& a, const DeviceCalib& cal,
-                         int sm_count, cudaStream_t st);
 
-// second-generation fused kernel (scan3d_fused_kernel7.cu); SCAN3D_FUSED_IMPL=6|7 selects
+// the single-pass kernel (scan3d_fused_kernel7.cu)
 bool fused7_supported(const scan3d_config& c);
 cudaError_t launch_fused7(const scan3d_config& c, const FusedArgs& a, const DeviceCalib& cal,
                           int sm_count, cudaStream_t st);

@@ -22,21 +22,6 @@
 double s3d_host_rcp_seed(double x);
 #endif
 
-// Experimental variants (tools/build_variants.py; all off in the default build, see
-// profiles/r1_optimisation_log.md "Candidates for round 2"):
-//   S3D_VAR_COLD_OUTLINE  rarely taken branches of the fused kernel's hot loop become out-of-line calls
-//   S3D_VAR_ROWSEL_RCP    atan2 table row from rcp.approx.f32 + multiply instead of __fdividef + clamp
-//   S3D_VAR_TERM_ROTATE   the fused kernel's second 2-pixel pass shifts its lanes down instead of selecting per term
-#ifndef S3D_VAR_COLD_OUTLINE
-#define S3D_VAR_COLD_OUTLINE 0
-#endif
-#ifndef S3D_VAR_ROWSEL_RCP
-#define S3D_VAR_ROWSEL_RCP 0
-#endif
-#ifndef S3D_VAR_TERM_ROTATE
-#define S3D_VAR_TERM_ROTATE 0
-#endif
-
 namespace s3d {
 
 // "Pi" as the reference's macro expands inside each expression.
@@ -129,13 +114,8 @@ __device__ __forceinline__ float atan2_to_float(double y, double x, float yf, fl
     const double mx = swap ? ay : ax, mn = swap ? ax : ay;
     const float axf = fabsf(xf), ayf = fabsf(yf);
     // 0/0 -> NaN -> cvt.rni gives 0: row 0, and the result is forced to 0 below
-#if S3D_VAR_ROWSEL_RCP
-    // min/max is in [0, 1] (or NaN for 0/0 -> row 0), the operands are bounded: no range handling, no clamp
-    const int i = __float2int_rn(fminf(axf, ayf) * rcp_seed_f32(fmaxf(axf, ayf)) * 32.0f);
-#else
     int i = __float2int_rn(__fdividef(fminf(axf, ayf), fmaxf(axf, ayf)) * 32.0f);
     i = min(max(i, 0), 32);
-#endif
     // c = i/32 exactly: (2^47 + i/32) - 2^47 with the integer dropped into the mantissa
     const double c = __hiloint2double(0x42e00000, i) - 140737488355328.0;
     const double num = fma(-c, mx, mn);
@@ -369,21 +349,6 @@ __device__ __forceinline__ double undist_coord_std(double u, double c, double in
 {
     return dadd(dmul(f, dmul(dsub(u, c), inv_f)), c);
 }
-#if S3D_VAR_COLD_OUTLINE
-// general K (skew, or a third row that is not 0 0 1): out of line, so that its two IEEE divisions (~100
-// instructions with their slow paths) stay out of the fused kernel's triangulation loop
-static __device__ __noinline__ void reproject_general(const double* __restrict__ K, double ifx, double ify, double u, double v,
-                                               double* ou, double* ov)
-{
-    const double x = dmul(dsub(u, K[2]), ifx);
-    const double y = dmul(dsub(v, K[5]), ify);
-    const double m0 = dadd(dadd(dadd(0.0, dmul(K[0], x)), dmul(K[1], y)), dmul(K[2], 1.0));
-    const double m1 = dadd(dadd(dadd(0.0, dmul(K[3], x)), dmul(K[4], y)), dmul(K[5], 1.0));
-    const double m2 = dadd(dadd(dadd(0.0, dmul(K[6], x)), dmul(K[7], y)), dmul(K[8], 1.0));
-    *ou = ddiv(m0, m2);
-    *ov = ddiv(m1, m2);
-}
-#endif
 __device__ __forceinline__ void undistorted_pixel_nodist(const double* __restrict__ K, double ifx,
                                                          double ify, bool std_form, double u,
                                                          double v, double* ou, double* ov)
@@ -393,10 +358,6 @@ __device__ __forceinline__ void undistorted_pixel_nodist(const double* __restric
         *ov = undist_coord_std(v, K[5], ify, K[4]);
         return;
     }
-#if S3D_VAR_COLD_OUTLINE
-    reproject_general(K, ifx, ify, u, v, ou, ov);
-    return;
-#endif
     const double x = dmul(dsub(u, K[2]), ifx);
     const double y = dmul(dsub(v, K[5]), ify);
     const double m0 = dadd(dadd(dadd(0.0, dmul(K[0], x)), dmul(K[1], y)), dmul(K[2], 1.0));

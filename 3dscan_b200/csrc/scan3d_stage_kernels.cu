@@ -43,6 +43,19 @@ __global__ void k_modulation_roi(const uint8_t* __restrict__ fringe, const uint8
     roi_eff[i] = ((double)t3 > 0.01 && roi[i] != 0) ? 1 : 0;
 }
 
+// SCAN3D_FLAG_STRICT_REFERENCE: the ROI as check_I_mod_criteria reads it as committed (3/wrapped_phase.cpp:106-115)
+__global__ void k_strict_roi(const uint8_t* __restrict__ roi, uint8_t* __restrict__ roi_eff, size_t n, int n_is_3_or_4)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) roi_eff[i] = (n_is_3_or_4 && roi[i] == 1) ? 1 : 0;
+}
+
+cudaError_t launch_strict_roi(const uint8_t* roi, uint8_t* roi_eff, size_t n, int N, cudaStream_t st)
+{
+    k_strict_roi<<<(unsigned)cdiv((long long)n, 256), 256, 0, st>>>(roi, roi_eff, n, N == 3 || N == 4);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_modulation_roi(const Shape& s, const uint8_t* fringe, const uint8_t* roi, uint8_t* roi_eff, cudaStream_t st)
 {
     const size_t n = (size_t)s.W * s.H;

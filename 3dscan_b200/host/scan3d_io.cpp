@@ -45,32 +45,54 @@ extern "C" {
 
 const char* scan3d_host_last_error(void) { return g_err.c_str(); }
 
+// shared by the grey and the colour reader: header checks of an uncompressed 8- or 24-bit BMP
+static int bmp_open(const char* path, std::vector<uint8_t>& b, int* w, int* h, int* hs, int* bpp, uint32_t* off, size_t* stride,
+                    uint32_t* ncol, const uint8_t** pal)
+{
+    if (!slurp(path, b) || b.size() < 54 || b[0] != 'B' || b[1] != 'M')
+        return fail(SCAN3D_ERR_IO, std::string("cannot read BMP ") + path);
+    *off = rd32(&b[10]);
+    const uint32_t hdr = rd32(&b[14]);
+    *w = (int)rd32(&b[18]);
+    *hs = (int)rd32(&b[22]);
+    *bpp = rd16(&b[28]);
+    const uint32_t comp = rd32(&b[30]);
+    *h = *hs < 0 ? -*hs : *hs;
+    if (comp != 0 || (*bpp != 8 && *bpp != 24) || *w <= 0 || *h <= 0 || *w > 65536 || *h > 65536)
+        return fail(SCAN3D_ERR_IO, std::string("unsupported BMP flavour: ") + path);
+    *stride = (((size_t)*w * *bpp + 31) / 32) * 4;
+    if (hdr < 40 || hdr > 1024 || *off < 14 + hdr || *off > b.size() || b.size() - *off < *stride * (size_t)*h)
+        return fail(SCAN3D_ERR_IO, std::string("truncated or malformed BMP ") + path);
+    *ncol = 0;
+    *pal = nullptr;
+    if (*bpp == 8) {
+        uint32_t n = rd32(&b[46]);
+        if (n == 0 || n > 256) n = 256;
+        // the palette lies between the info header and the pixel data: never read past either
+        const size_t room = (*off - (14 + (size_t)hdr)) / 4;
+        *ncol = n < room ? n : (uint32_t)room;
+        *pal = &b[14 + hdr];
+    }
+    return SCAN3D_OK;
+}
+
 int scan3d_read_bmp8(const char* path, int* W, int* H, uint8_t* buf, int64_t buf_bytes)
 {
     if (!path || !W || !H) return fail(SCAN3D_ERR_ARG, "null argument");
     std::vector<uint8_t> b;
-    if (!slurp(path, b) || b.size() < 54 || b[0] != 'B' || b[1] != 'M')
-        return fail(SCAN3D_ERR_IO, std::string("cannot read BMP ") + path);
-    const uint32_t off = rd32(&b[10]), hdr = rd32(&b[14]);
-    const int w = (int)rd32(&b[18]), hs = (int)rd32(&b[22]);
-    const int bpp = rd16(&b[28]);
-    const uint32_t comp = rd32(&b[30]);
-    const int h = hs < 0 ? -hs : hs;
-    if (comp != 0 || (bpp != 8 && bpp != 24) || w <= 0 || h <= 0)
-        return fail(SCAN3D_ERR_IO, std::string("unsupported BMP flavour: ") + path);
+    int w, h, hs, bpp;
+    uint32_t off, ncol;
+    size_t stride;
+    const uint8_t* pal;
+    const int rc = bmp_open(path, b, &w, &h, &hs, &bpp, &off, &stride, &ncol, &pal);
+    if (rc) return rc;
     *W = w;
     *H = h;
     if (!buf) return SCAN3D_OK;
     if (buf_bytes < (int64_t)w * h) return fail(SCAN3D_ERR_ARG, "buffer too small");
-    const size_t stride = (((size_t)w * bpp + 31) / 32) * 4;
-    if (b.size() < off + stride * h) return fail(SCAN3D_ERR_IO, std::string("truncated BMP ") + path);
     uint8_t lut[256];
-    if (bpp == 8) {
-        uint32_t ncol = rd32(&b[46]);
-        if (ncol == 0 || ncol > 256) ncol = 256;
-        const uint8_t* pal = &b[14 + hdr];
+    if (bpp == 8)
         for (uint32_t i = 0; i < 256; i++) lut[i] = i < ncol ? grey_of(pal[4 * i], pal[4 * i + 1], pal[4 * i + 2]) : 0;
-    }
     for (int y = 0; y < h; y++) {
         const uint8_t* src = &b[off + stride * (size_t)(hs > 0 ? h - 1 - y : y)];
         uint8_t* dst = buf + (size_t)y * w;
@@ -78,6 +100,35 @@ int scan3d_read_bmp8(const char* path, int* W, int* H, uint8_t* buf, int64_t buf
             for (int x = 0; x < w; x++) dst[x] = lut[src[x]];
         else
             for (int x = 0; x < w; x++) dst[x] = grey_of(src[3 * x], src[3 * x + 1], src[3 * x + 2]);
+    }
+    return SCAN3D_OK;
+}
+
+// cvLoadImage(path) with its default flag (colour): [H][W][3] B,G,R bytes, top row first
+// (8/save_point_cloud.cpp:59-66 loads Point_cloud/texture.bmp this way and cvSplits it into blue, green, red)
+int scan3d_read_bmp_bgr(const char* path, int* W, int* H, uint8_t* buf, int64_t buf_bytes)
+{
+    if (!path || !W || !H) return fail(SCAN3D_ERR_ARG, "null argument");
+    std::vector<uint8_t> b;
+    int w, h, hs, bpp;
+    uint32_t off, ncol;
+    size_t stride;
+    const uint8_t* pal;
+    const int rc = bmp_open(path, b, &w, &h, &hs, &bpp, &off, &stride, &ncol, &pal);
+    if (rc) return rc;
+    *W = w;
+    *H = h;
+    if (!buf) return SCAN3D_OK;
+    if (buf_bytes < (int64_t)3 * w * h) return fail(SCAN3D_ERR_ARG, "buffer too small");
+    for (int y = 0; y < h; y++) {
+        const uint8_t* src = &b[off + stride * (size_t)(hs > 0 ? h - 1 - y : y)];
+        uint8_t* dst = buf + (size_t)3 * y * w;
+        if (bpp == 24) {
+            memcpy(dst, src, (size_t)3 * w);
+        } else {
+            for (int x = 0; x < w; x++)
+                for (int k = 0; k < 3; k++) dst[3 * x + k] = src[x] < ncol ? pal[4 * src[x] + k] : 0;
+        }
     }
     return SCAN3D_OK;
 }

@@ -54,7 +54,13 @@ void ensure_ctx()
     c.fw_v = fringe_width_pixels_vertical; c.fw_h = fringe_width_pixels_horizontal;
     c.dirs = 2; c.row0 = 0; c.H_total = c.H; c.flags = 0;
     if (g_ctx && memcmp(&c, &g_cfg, sizeof(c)) == 0) return;
-    if (g_ctx) scan3d_destroy(g_ctx);
+    if (g_ctx) {
+        // a configuration global changed between two stages: the planes of the old shape cannot be carried over
+        // (the reference would go on with stale arrays of the old size here); say so instead of doing it silently
+        fprintf(stderr, "scan3d compat: pattern / frame globals changed between stages -- the context is recreated, "
+                        "the results of earlier stages are dropped (call the stages again from compute_wrapped_phase)\n");
+        scan3d_destroy(g_ctx);
+    }
     g_ctx = nullptr;
     ck(scan3d_create(&c, g_device, &g_ctx), "scan3d_create");
     g_cfg = c;
@@ -210,13 +216,14 @@ void triangulate()
 void save_point_cloud(unsigned cloud_index)
 {
     ensure_ctx();
-    // texture.bmp (8/save_point_cloud.cpp:59-66) is optional here: grey replicated to BGR if present
+    // texture.bmp, loaded in colour and split into blue / green / red as the reference does
+    // (8/save_point_cloud.cpp:59-66,88-90); optional here: without it the points stay black
     int w = 0, h = 0;
     const std::string tex = g_root + "/Point_cloud/texture.bmp";
-    if (scan3d_read_bmp8(tex.c_str(), &w, &h, nullptr, 0) == SCAN3D_OK && w == Camera_imagewidth && h == Camera_imageheight) {
-        std::vector<uint8_t> g(npix()), bgr(3 * npix());
-        scan3d_read_bmp8(tex.c_str(), &w, &h, g.data(), (int64_t)npix());
-        for (size_t i = 0; i < npix(); i++) bgr[3 * i] = bgr[3 * i + 1] = bgr[3 * i + 2] = g[i];
+    if (scan3d_read_bmp_bgr(tex.c_str(), &w, &h, nullptr, 0) == SCAN3D_OK && w == Camera_imagewidth && h == Camera_imageheight) {
+        std::vector<uint8_t> bgr(3 * npix());
+        if (scan3d_read_bmp_bgr(tex.c_str(), &w, &h, bgr.data(), (int64_t)bgr.size()) != SCAN3D_OK)
+            die("save_point_cloud", scan3d_host_last_error());
         ck(scan3d_set_texture(g_ctx, bgr.data()), "scan3d_set_texture");
     }
     int64_t n = 0;

@@ -11,9 +11,11 @@ Two schemes, both named by BASELINE.json's north star:
     ROI plane (1 B/pixel) is simply replicated and each ctx is created with (row0, H_total), so no
     halo exchange is needed.  Each rank's compacted point list is in raster order of its rows, so
     concatenating the lists in rank order gives the raster order of the full frame.  The one real
-    exchange step is `gather_points`: an all-gather of the per-rank counts followed by
-    point-to-point sends of the compacted points into rank `dst`'s buffer at the right offset
-    (NCCL over NVLink on GPUs; the same code runs over gloo on CPU tensors in the tests).
+    exchange step has two implementations: `RowShardGroup` (the default on GPUs: binding of the C++ host
+    module include/scan3d_shard.h -- counts on a shared-memory board, one copy-engine push per rank over
+    NVLink straight to the final raster offset, no kernel) and `gather_points` (an all-gather of the
+    per-rank counts followed by point-to-point sends into rank `dst`'s buffer: NCCL over NVLink on GPUs,
+    the same code over gloo on CPU tensors in the tests).
 """
 import torch
 import torch.distributed as dist
@@ -32,7 +34,7 @@ def row_block(H_total, rank, world):
     return row0, rows
 
 
-def gather_points(points, count, dst=0, group=None, out=None, aligned_staging=None):
+def gather_points(points, count, dst=0, group=None, out=None, aligned_staging=None, slot=0):
     """Concatenate the ranks' compacted point lists, in rank order, on rank `dst`.
 
     points: [capacity, C] tensor on this rank (only the first `count` rows are valid)
@@ -40,6 +42,8 @@ def gather_points(points, count, dst=0, group=None, out=None, aligned_staging=No
     Returns (all_points, counts) on rank `dst` ([sum(counts), C] tensor, list of ints) and
     (None, counts) elsewhere.  `out` may preallocate the destination on rank `dst`.
     aligned_staging: receive misaligned blocks through a staging block (default: on CUDA tensors).
+    slot: callers that overlap two gathers on two streams pass different slots: the staging blocks are kept per
+    (peer, slot), so the receive of one gather never lands in a block the other is still copying out of.
     """
     if not dist.is_initialized():
         return points[:int(count)], [int(count)]
@@ -76,7 +80,7 @@ def gather_points(points, count, dst=0, group=None, out=None, aligned_staging=No
                     # NCCL moves 16 bytes per thread; a receive address that is only 4-byte aligned
                     # (12 B points at an arbitrary offset) halves the transfer rate (measured 207 vs
                     # 440 GB/s).  Receive into an aligned staging block, then one device copy.
-                    stage = _staging(r, counts[r], tuple(points.shape[1:]), points.dtype, dev)[:counts[r]]
+                    stage = _staging((r, slot), counts[r], tuple(points.shape[1:]), points.dtype, dev)[:counts[r]]
                     staged.append((target, stage))
                     target = stage
                 ops.append(dist.P2POp(dist.irecv, target, r, group))
@@ -120,109 +124,80 @@ def allgather_points(points, count, group=None):
     return torch.cat([p[:n] for p, n in zip(parts, counts)]), counts
 
 
-class PeerPointSink:
-    """Row-sharded mode with the exchange folded into the reconstruction kernel.
+class RowShardGroup:
+    """Binding of include/scan3d_shard.h: the row-sharded mode's gather of every rank's compacted points on rank 0.
 
-    Rank `dst` owns `slots` staging blocks per other rank (`scan3d_peer_alloc`) and shares their
-    CUDA IPC handles; every other rank maps its blocks (`scan3d_peer_open`) and hands the mapped
-    pointer to its context
-    (`scan3d_set_points_buffer`), so the fused kernel's IO warps stream the compacted points
-    straight into `dst`'s memory over NVLink while the decode is still running -- no NCCL transfer
-    afterwards, nothing that needs SMs beside the persistent kernel.  What is left per scan is
-    `finish()`: an all-gather of the counts (the one host sync) and, on `dst`, one device copy per
-    other rank that moves its block to its raster offset behind the lower ranks' points.
+    The protocol lives in the C++ host module (3dscan_b200/csrc/scan3d_shard.cu): per-scan control words on a POSIX
+    shared-memory board, root's output blocks shared through CUDA IPC, ONE copy-engine push per rank and scan over
+    NVLink straight to the points' final raster offset -- no kernel, so the persistent reconstruction kernel of the
+    next scan runs undisturbed.  A block is reused every `slots` scans; the ranks push into it only after root has
+    released the previous cloud (`release`), so overlapped schedules are race-free by construction.
 
-    Ordering: `finish(slot)` is stream-ordered after the rank's reconstruction; the all-gather
-    completes on `dst` only after every rank's kernel has, and a kernel's peer writes are performed
-    by the time it completes.  A block is written again `slots` scans later; `finish` makes the
-    stream that runs the next all-gather wait for the copy-out of the block that scan will reuse.
-    """
+    name: identical on every rank, unique per job (e.g. derived from MASTER_PORT).  device < 0 selects the GPU-less
+    mode (blocks in shared memory, points from host arrays): the CPU tests of the ordering logic use it."""
 
-    def __init__(self, ctx, capacity_points, dst=0, group=None, slots=2):
+    def __init__(self, name, rank, world, device, capacity_points, slots=2):
+        import ctypes as C
         import importlib
         s3 = importlib.import_module("3dscan_b200")
-        self._s3 = s3
-        self.group, self.dst, self.slots = group, dst, slots
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.ctx = list(ctx) if isinstance(ctx, (list, tuple)) else [ctx] * slots
-        self.device = torch.cuda.current_device()
-        caps = [None] * self.world
-        dist.all_gather_object(caps, int(capacity_points), group=group)
-        self.caps = caps
-        self.copied = [None] * slots          # events: block of slot s copied out on dst
-        self.owned, self.opened, self.stage = [], [], {}
-        payload = [None]
-        if self.rank == dst:
-            handles = {}
-            for r in range(self.world):
-                if r == dst:
-                    continue
-                blocks, hs = [], []
-                for _ in range(slots):
-                    ptr, h = s3.peer_alloc(self.device, caps[r] * 12)
-                    self.owned.append(ptr)
-                    blocks.append(s3.wrap_device(ptr, (caps[r], 3), "<f4"))
-                    hs.append(h)
-                self.stage[r], handles[r] = blocks, hs
-            payload[0] = handles
-        dist.broadcast_object_list(payload, src=dst, group=group)
-        if self.rank != dst:
-            for s, h in enumerate(payload[0][self.rank]):
-                ptr = s3.peer_open(self.device, h)        # opened FROM this rank's device: lazy peer access
-                self.opened.append(ptr)
-                self.ctx[s].set_points_buffer(ptr, caps[self.rank])
-        dist.barrier(group=group)
+        self._C, self._s3 = C, s3
+        self.L = s3.cuda_lib()
+        L = self.L
+        L.scan3d_shard_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
+        L.scan3d_shard_destroy.argtypes = [C.c_void_p]
+        L.scan3d_shard_last_error.argtypes = [C.c_void_p]
+        L.scan3d_shard_last_error.restype = C.c_char_p
+        L.scan3d_shard_bind.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.scan3d_shard_gather.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.scan3d_shard_gather_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.scan3d_shard_output.argtypes = [C.c_void_p, C.c_int]
+        L.scan3d_shard_output.restype = C.c_void_p
+        L.scan3d_shard_release.argtypes = [C.c_void_p, C.c_int]
+        self.rank, self.world, self.slots, self.capacity, self.device = rank, world, slots, int(capacity_points), device
+        h = C.c_void_p()
+        rc = L.scan3d_shard_create(str(name).encode(), rank, world, device, int(capacity_points), slots, C.byref(h))
+        if rc:
+            raise RuntimeError("scan3d_shard_create: " + (L.scan3d_shard_last_error(None) or b"").decode())
+        self.h = h
 
-    def begin(self, slot):
-        """Before enqueuing the reconstruction of a scan that uses block `slot` (needed when one
-        context serves several slots; with one context per slot it changes nothing)."""
-        if self.rank != self.dst:
-            self.ctx[slot].set_points_buffer(self.opened[slot], self.caps[self.rank])
+    def _ck(self, rc, what):
+        if rc:
+            raise RuntimeError(what + ": " + (self.L.scan3d_shard_last_error(self.h) or b"").decode())
 
-    def bind_output(self, slot, out):
-        """dst == lowest rank only: its own points start at offset 0, so its context can write `out` directly."""
-        if self.rank == self.dst and self.dst == 0:
-            self.ctx[slot].set_points_buffer(out.data_ptr(), out.shape[0])
+    def bind(self, slot, ctx):
+        self._ck(self.L.scan3d_shard_bind(self.h, slot, ctx.h), "scan3d_shard_bind")
 
-    def finish(self, slot, count, own_points, out):
-        """All ranks, after their reconstruction of this scan was enqueued on the current stream.
-        count: device-resident count tensor of this rank.  Returns (points, counts) on dst."""
-        dev = count.device
-        cur = torch.cuda.current_stream()
-        nxt = (slot + 1) % self.slots
-        if self.rank == self.dst and self.copied[nxt] is not None:
-            cur.wait_event(self.copied[nxt])      # the scan that reuses block `nxt` starts after this all-gather
-        counts_all = torch.zeros(self.world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(counts_all, count.reshape(1).to(torch.int64), group=self.group)
-        counts = [int(v) for v in counts_all.tolist()]
-        if self.rank != self.dst:
-            return None, counts
-        offsets = [0]
-        for n in counts:
-            offsets.append(offsets[-1] + n)
-        result = out[:offsets[-1]]
-        own = result[offsets[self.dst]:offsets[self.dst + 1]]
-        if counts[self.dst] and own.data_ptr() != own_points.data_ptr():
-            own.copy_(own_points[:counts[self.dst]])
-        for r, blocks in self.stage.items():
-            if counts[r]:
-                result[offsets[r]:offsets[r + 1]].copy_(blocks[slot][:counts[r]])
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        self.copied[slot] = ev
-        return result, counts
+    def gather(self, slot, ctx):
+        """After ctx.reconstruct_dev(...) of this rank's rows was enqueued.  Returns (total, counts)."""
+        C = self._C
+        total, counts = C.c_int64(), (C.c_int64 * self.world)()
+        self._ck(self.L.scan3d_shard_gather(self.h, slot, ctx.h, C.byref(total), counts), "scan3d_shard_gather")
+        return total.value, list(counts)
+
+    def gather_host(self, slot, points):
+        """GPU-less mode: points = this rank's float32 [n][3] array."""
+        import numpy as np
+        C = self._C
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        total, counts = C.c_int64(), (C.c_int64 * self.world)()
+        self._ck(self.L.scan3d_shard_gather_host(self.h, slot, pts.ctypes.data_as(C.c_void_p), pts.shape[0], C.byref(total), counts),
+                 "scan3d_shard_gather_host")
+        return total.value, list(counts)
+
+    def output_ptr(self, slot):
+        return self.L.scan3d_shard_output(self.h, slot)
+
+    def output_host(self, slot, n):
+        """GPU-less mode, root: the first n gathered points of the slot as a numpy view."""
+        import numpy as np
+        C = self._C
+        p = self.output_ptr(slot)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(int(n), 3))
+
+    def release(self, slot):
+        self._ck(self.L.scan3d_shard_release(self.h, slot), "scan3d_shard_release")
 
     def close(self):
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)
-        for c in set(self.ctx):
-            try:
-                c.set_points_buffer(None, 0)
-            except Exception:
-                pass
-        for p in self.opened:
-            self._s3.peer_close(self.device, p)
-        dist.barrier(group=self.group)
-        for p in self.owned:
-            self._s3.peer_free(self.device, p)
-        self.opened, self.owned, self.stage = [], [], {}
+        if self.h:
+            self.L.scan3d_shard_destroy(self.h)
+            self.h = None

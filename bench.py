@@ -140,59 +140,59 @@ def oracle_scan_seconds(cfg, ocal, stack, roi, threads, min_seconds, max_runs):
     return float(np.median(times)), len(times)
 
 
-def bench_rowshard(args, s3, cal, cfg_full, config, rank, world, local_rank, stream, barrier, bpp):
-    """configs[4]: one very large frame; rank r decodes + triangulates its block of rows, then the
-    compacted point lists are gathered (rank order == raster order) on rank 0 over NCCL."""
+def bench_rowshard(args, s3, cal, cfg_full, config, rank, world, local_rank, stream, barrier, bpp, steps=None, tag="c5"):
+    """configs[4]: one very large frame; rank r decodes + triangulates its block of rows, then the compacted point
+    lists are gathered (rank order == raster order) on rank 0.  Returns the result line (rank 0) or None."""
     import importlib
     import torch
     import torch.distributed as dist
     sh = importlib.import_module("3dscan_b200.sharding")
+    steps = steps or args.steps
     W, Ht = cfg_full.W, cfg_full.H
     row0, rows = sh.row_block(Ht, rank, world)
     cfg = s3.make_config(W, rows, cfg_full.PW, cfg_full.PH, cfg_full.N, cfg_full.M_v, cfg_full.M_h,
                          cfg_full.fw_v, cfg_full.fw_h, 2, row0=row0, H_total=Ht, flags=cfg_full.flags)
     nf = s3.stack_planes(cfg)
-    # two contexts on two streams: the NCCL exchange of scan k overlaps the decode of scan k+1
+    # two contexts on two streams: the exchange of scan k overlaps the decode of scan k+1
     streams = [stream, torch.cuda.Stream()]
     ctxs = [s3.Scan3D(cfg, local_rank, cal, stream=st.cuda_stream) for st in streams]
-    ctx = ctxs[0]
     stack_h = torch.empty((nf, rows, W), dtype=torch.uint8, pin_memory=True)
     roi_h = torch.empty((Ht, W), dtype=torch.uint8, pin_memory=True)
     s3.synth_stack(cfg, cal, s3.default_synth_params(seed=0x3D5CA9), out=stack_h.numpy(), roi_out=roi_h.numpy(),
                    threads=max(1, (os.cpu_count() or 8) // max(1, world)))
     stack_d, roi_d = stack_h.to("cuda"), roi_h.to("cuda")
     del stack_h
-    outs = [torch.empty((Ht * W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None for _ in ctxs]
     total = [0]
-    srcs = [_wrap_device(torch, c.device_points(), (rows * W, 3), "<f4") for c in ctxs]
-    cnts = [_wrap_device(torch, c.device_point_count(), (1,), "<i4") for c in ctxs]
     seq = [0]
 
     def decode(k):
         ctxs[k & 1].reconstruct_dev(stack_d.data_ptr(), roi_d.data_ptr())      # runs on streams[k & 1]
 
-    # --exchange peer (default, N > 1): the other ranks' kernels stream their points into rank 0's
-    # memory over NVLink (sharding.PeerPointSink); what is left per scan is the all-gather of the
-    # counts and one device copy per rank on rank 0.  --exchange nccl: send/recv after the kernel.
-    sink = None
-    if world > 1 and args.exchange == "peer":
-        sink = sh.PeerPointSink(ctxs, rows * W, dst=0, slots=2)
+    # --exchange peer (default): the C++ row-shard group (include/scan3d_shard.h): counts over a shared-memory board,
+    # one copy-engine push per rank over NVLink to the final raster offset in rank 0's block.
+    # --exchange nccl: all-gather of the counts + NCCL send/recv of the points after the kernel.
+    group, outs = None, None
+    if args.exchange == "peer" or world == 1:
+        name = "b%s_%s_%d" % (os.environ.get("MASTER_PORT", "0"), tag, os.getppid() if world > 1 else os.getpid())
+        group = sh.RowShardGroup(name, rank, world, local_rank, Ht * W, slots=2)
         for i in range(2):
-            sink.bind_output(i, outs[i]) if rank == 0 else None
-        if rank == 0:
-            srcs = [outs[0], outs[1]]          # rank 0's contexts write their points straight into the outputs
+            group.bind(i, ctxs[i])
+    else:
+        outs = [torch.empty((Ht * W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None for _ in ctxs]
+        srcs = [_wrap_device(torch, c.device_points(), (rows * W, 3), "<f4") for c in ctxs]
+        cnts = [_wrap_device(torch, c.device_point_count(), (1,), "<i4") for c in ctxs]
 
     def step():
-        # one scan per step: enqueue the decode of scan k+1, then exchange scan k (the host wait for
-        # the counts only depends on scan k's stream)
+        # one scan per step: enqueue the decode of scan k+1, then gather scan k (the host only waits for scan k)
         k = seq[0]
         decode(k + 1)
-        with torch.cuda.stream(streams[k & 1]):
-            if sink is not None:
-                res, counts = sink.finish(k & 1, cnts[k & 1], srcs[k & 1], outs[k & 1])
-            else:
-                res, counts = sh.gather_points(srcs[k & 1], cnts[k & 1], dst=0, out=outs[k & 1])
-        total[0] = sum(counts)
+        if group is not None:
+            total[0], _ = group.gather(k & 1, ctxs[k & 1])
+            group.release(k & 1)               # (rank 0: nobody consumes the cloud here)
+        else:
+            with torch.cuda.stream(streams[k & 1]):
+                _, counts = sh.gather_points(srcs[k & 1], cnts[k & 1], dst=0, out=outs[k & 1], slot=k & 1)
+            total[0] = sum(counts)
         seq[0] = k + 1
 
     sampler = ClockSampler(local_rank)
@@ -210,7 +210,7 @@ def bench_rowshard(args, s3, cal, cfg_full, config, rank, world, local_rank, str
     t0 = time.time()
     ev0.record(stream)
     streams[1].wait_stream(stream)     # both streams start behind ev0
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     stream.wait_stream(streams[1])
     ev1.record(stream)
@@ -223,30 +223,45 @@ def bench_rowshard(args, s3, cal, cfg_full, config, rank, world, local_rank, str
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms.item())
     npix = W * Ht
-    value = args.steps * npix / (ms_max * 1e-3) / 1e6
+    value = steps * npix / (ms_max * 1e-3) / 1e6
     peak, peak_kind = measured_peak_gbs()
-    achieved = bpp * npix / (ms_max * 1e-3 / args.steps) / 1e9
+    ms_scan = ms_max / steps
+    achieved = bpp * npix / (ms_scan * 1e-3) / 1e9
+    # what bounds the mode: every rank's HBM share of the decode, or rank 0's NVLink ingest of the other ranks' points
+    nvlink_gbs = 770.0                                   # measured peer-copy rate per direction (B200_PROFILING.md)
+    ingest_bytes = 12.0 * total[0] * (world - 1) / max(1, world)
+    floor_hbm_ms = bpp * npix / world / (peak * 1e9) * 1e3
+    floor_link_ms = ingest_bytes / (nvlink_gbs * 1e9) * 1e3
+    line = None
     if rank == 0:
-        config.update({"sharding": ("one frame row-sharded over %d rank(s); " % world) + ("points streamed by the kernel into rank 0's memory over NVLink (peer memory), all-gather of counts + one device copy per rank" if sink is not None else "all-gather of counts + NCCL send/recv of compacted points to rank 0") + "; 2 contexts on 2 streams",
-                       "rows_per_rank": rows, "scans_per_gpu_per_step": 1, "resident_ring": 1,
-                       "l2_policy": "inputs larger than L2 (%.2f GB per GPU)" % (nf * rows * W / 1e9)})
-        line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "scans_per_s": args.steps / (ms_max * 1e-3), "points_last_scan": total[0],
+        cfgd = dict(config)
+        cfgd.update({"workload": "c5_50mp_rowshard_8step_10bit_vh", "frame": [W, Ht],
+                     "sharding": ("one frame row-sharded over %d rank(s); " % world) +
+                     ("counts over a shared-memory board, one copy-engine push per rank over NVLink to the final raster offset in rank 0's block (include/scan3d_shard.h)"
+                      if group is not None else "all-gather of counts + NCCL send/recv of compacted points to rank 0") + "; 2 contexts on 2 streams",
+                     "rows_per_rank": rows, "scans_per_gpu_per_step": 1, "resident_ring": 1,
+                     "l2_policy": "inputs larger than L2 (%.2f GB per GPU)" % (nf * rows * W / 1e9)})
+        line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": steps,
+                "warmup": args.warmup, "ms_per_step": ms_scan, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfgd,
+                "scans_per_s": steps / (ms_max * 1e-3), "points_last_scan": total[0],
                 "gpu_launches": sum(c.launch_count() for c in ctxs) - l0, "clocks": clocks,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
+                "roofline": {"bound": "hbm" if floor_hbm_ms >= floor_link_ms else "nvlink ingest of rank 0",
+                             "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                              "frac": achieved / (peak * world), "traffic": None,
-                             "peak_kind": "%d x MEASURED_PEAKS.json hbm_gbs; time includes the point gather" % world},
+                             "floor_ms_hbm": floor_hbm_ms, "floor_ms_nvlink_ingest": floor_link_ms,
+                             "frac_of_binding_floor": max(floor_hbm_ms, floor_link_ms) / ms_scan,
+                             "nvlink_ingest_gbs": ingest_bytes / (ms_scan * 1e-3) / 1e9,
+                             "peak_kind": "%d x MEASURED_PEAKS.json hbm_gbs; time includes the point gather; NVLink floor = (world-1)/world of the points at the measured 770 GB/s peer-copy rate into rank 0" % world},
                 "e2e": None, "cpu_baseline": None}
-        print(json.dumps(line))
     torch.cuda.synchronize()
-    if sink is not None:
-        sink.close()
+    if group is not None:
+        group.close()
     for c in ctxs:
         c.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del stack_d, roi_d
+    torch.cuda.empty_cache()
+    return line
 
 
 def _wrap_device(torch, ptr, shape, typestr):
@@ -261,18 +276,19 @@ def _wrap_device(torch, ptr, shape, typestr):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_12mp_8step_10bit_vh", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=16, help="scans per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="scans per GPU per step (configs[3]: a batch of 256 scans)")
     ap.add_argument("--ring", type=int, default=4, help="distinct resident stacks per GPU")
-    ap.add_argument("--e2e-scans", type=int, default=2, help="scans per e2e step")
+    ap.add_argument("--e2e-scans", type=int, default=3, help="scans per e2e step (one lane = one context + host thread per scan)")
     ap.add_argument("--exact-triangulation", action="store_true",
                     help="reference operation order in the normal-equation solve (bit-identical points)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--contexts", type=int, default=1, help="contexts (each on its own stream) the batch alternates over")
+    ap.add_argument("--no-rowshard", action="store_true", help="N > 1: skip the row-sharded 50 MP frame that rides along")
+    ap.add_argument("--contexts", type=int, default=2, help="contexts (each on its own stream) the batch alternates over")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="row-shard workload, N>1: how the points reach rank 0")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -350,7 +366,12 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     if args.workload.startswith("c5_"):
-        return bench_rowshard(args, s3, cal, cfg, config, rank, world, local_rank, stream, barrier, bpp)
+        line = bench_rowshard(args, s3, cal, cfg, config, rank, world, local_rank, stream, barrier, bpp)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     ctx = s3.Scan3D(cfg, local_rank, cal, stream=stream.cuda_stream)
     nf = s3.stack_planes(cfg)
     # Resident ring of distinct scans.  One synthetic capture is rendered on the host (rank 0, all
@@ -434,7 +455,7 @@ def main():
         # one scan's points and its kernel overlap the H2D of the other scan's stack (PCIe is full
         # duplex); the H2D stream itself is the bound (57 B/pixel in).
         h2d = (nf + 1) * npix
-        lanes = 2 if args.e2e_scans % 2 == 0 else 1
+        lanes = args.e2e_scans if args.e2e_scans <= 4 else 2
         e_ctxs = [ctx] + [s3.Scan3D(cfg, local_rank, cal, stream=torch.cuda.Stream().cuda_stream) for _ in range(lanes - 1)]
         pts_hosts = [torch.empty((npix, 3), dtype=torch.float32, pin_memory=True) if dirs == 2 else None for _ in e_ctxs]
         out_hosts = [torch.empty((H, W), dtype=torch.float32, pin_memory=True) for _ in e_ctxs]
@@ -473,8 +494,21 @@ def main():
         te = torch.tensor([dt], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        # what the host->device path of this box can do at best: one large pinned copy, best of 3 (this rank alone)
+        probe = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        h2d_peak = 0.0
+        for _ in range(3):
+            torch.cuda.synchronize()
+            tp = time.time()
+            probe.copy_(host_stack.view(-1)[:probe.numel()], non_blocking=True)
+            torch.cuda.synchronize()
+            h2d_peak = max(h2d_peak, probe.numel() / (time.time() - tp) / 1e9)
+        del probe
         e2e = {"value": world * e_steps * args.e2e_scans * npix / float(te.item()) / 1e6, "unit": "Mpix/s",
                "h2d_bytes_per_step": h2d * args.e2e_scans, "d2h_bytes_per_step": d2h * args.e2e_scans,
+               "h2d_gbs_achieved_per_gpu": e_steps * args.e2e_scans * h2d / float(te.item()) / 1e9,
+               "h2d_gbs_pinned_copy_peak": h2d_peak,
+               "bound": "host->device copies (PCIe): the kernel side is %.0fx faster than the input arrives" % (value / world / max(1e-9, e_steps * args.e2e_scans * npix / float(te.item()) / 1e6)),
                "scans_per_step": args.e2e_scans, "steps": e_steps,
                "api": "scan3d_reconstruct(host stack, host roi) + scan3d_get_points, %d context(s) on %d host thread(s)" % (lanes, lanes)}
 
@@ -493,11 +527,34 @@ def main():
             try:
                 sec1, _ = oracle_scan_seconds(cfg, ocal, host_stack.numpy(), host_roi.numpy(), 1, 0.0, 1)
                 cpu["single_thread"] = {"value": npix / sec1 / 1e6, "unit": "Mpix/s", "cores": 1, "seconds_per_scan": sec1}
+                cpu["single_thread_value"] = npix / sec1 / 1e6      # (flat copies: nested objects get dropped by some parsers)
+                cpu["single_thread_seconds_per_scan"] = sec1
             except Exception as e:   # the all-core figure above is the contract; this one is extra
                 cpu["single_thread"] = {"error": str(e)}
 
     for c in ctxs[1:]:
         c.close()
+    # ---- N > 1: configs[4] rides along (one 50 MP frame row-sharded over the ranks), so that the scaling record
+    #      carries it at every GPU count
+    rowshard = None
+    if world > 1 and not args.no_rowshard and args.workload.startswith("c3_"):
+        barrier()
+        ctx.close()
+        del ring, rois, base_stack, base_roi
+        torch.cuda.empty_cache()
+        W5, H5, PW5, PH5, N5, Mv5, Mh5, fwv5, fwh5, _ = WORKLOADS["c5_50mp_rowshard_8step_10bit_vh"]
+        cal5d = scaled_calib(load_calib_c1(), W5 / 1600.0, PW5 / 1280.0)
+        cal5 = s3.make_calib(*[cal5d[k] for k in ("Kc", "dc", "Kp", "dp", "rc", "tc", "rp", "tp")])
+        cfg5 = s3.make_config(W5, H5, PW5, PH5, N5, Mv5, Mh5, fwv5, fwh5, 2, flags=flags)
+        l5 = bench_rowshard(args, s3, cal5, cfg5, {}, rank, world, local_rank, stream, barrier,
+                            algorithmic_bytes_per_pixel(N5, Mv5, Mh5, 2), steps=max(8, min(args.steps, 24)), tag="ride")
+        if rank == 0:
+            rowshard = {"workload": "c5_50mp_rowshard_8step_10bit_vh", "ms_per_scan": l5["ms_per_step"], "mpix_per_s": l5["value"],
+                        "points": l5["points_last_scan"], "frac_of_n_x_hbm": l5["roofline"]["frac"],
+                        "floor_ms_hbm": l5["roofline"]["floor_ms_hbm"], "floor_ms_nvlink_ingest": l5["roofline"]["floor_ms_nvlink_ingest"],
+                        "frac_of_binding_floor": l5["roofline"]["frac_of_binding_floor"], "bound": l5["roofline"]["bound"],
+                        "nvlink_ingest_gbs": l5["roofline"]["nvlink_ingest_gbs"], "exchange": l5["config"]["sharding"], "steps": l5["steps"]}
+        ctx = None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -505,8 +562,11 @@ def main():
                 "scans_per_s": world * args.steps * args.batch / (ms_max * 1e-3),
                 "points_last_scan": count, "gpu_launches": launches, "clocks": clocks,
                 "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+        if rowshard is not None:
+            line["rowshard"] = rowshard
         print(json.dumps(line))
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

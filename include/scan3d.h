@@ -98,6 +98,11 @@ typedef struct {
  * stage kernels in sequence instead of the single-pass kernel (the mask recurrence then needs
  * the modulation of pixels two rows up, which a linear tile does not hold). */
 #define SCAN3D_FLAG_MODULATION_MASK 4u
+/* check_I_mod_criteria exactly as committed (3/wrapped_phase.cpp:78-127): a pixel is selected only where the ROI
+ * byte == 1, and only when N is 3 or 4 -- the reference's 5-step block (:117-127) is commented out, so its own
+ * 5-step run ends with an all-zero valid map and an empty cloud.  OFF by default: by default every non-zero ROI
+ * byte selects its pixel for every N (documented extension; image_scissor only writes 0 and 1). */
+#define SCAN3D_FLAG_STRICT_REFERENCE 8u
 
 /* The 8 matrices load_matrices() reads (6/system_calibration.cpp:1526-1554): intrinsics (3x3
  * row-major), distortion (k1,k2,p1,p2,k3), world->device rotation vectors and translations. */

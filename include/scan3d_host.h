@@ -27,6 +27,9 @@ extern "C" {
 /* ---- files ---- */
 /* 8-bit palettised or 24-bit BMP -> grey u8 [H][W] (top-down).  Pass buf = NULL to query the size. */
 int scan3d_read_bmp8(const char *path, int *W, int *H, uint8_t *buf, int64_t buf_bytes);
+/* cvLoadImage(path) with its default (colour) flag: buf = [H][W][3] B,G,R bytes, top row first.  8- and 24-bit
+ * uncompressed BMP (8/save_point_cloud.cpp:59-66 loads Point_cloud/texture.bmp this way). */
+int scan3d_read_bmp_bgr(const char *path, int *W, int *H, uint8_t *buf, int64_t buf_bytes);
 int scan3d_write_bmp8(const char *path, int W, int H, const uint8_t *buf);
 /* OpenCV XML <name type_id="opencv-matrix"> with <dt>d</dt>: reads rows*cols doubles. */
 int scan3d_read_cv_matrix(const char *path, const char *name, int rows, int cols, double *out);

@@ -233,7 +233,7 @@ class Result:
 
 
 def reconstruct(cfg, cal, fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi, threads=1,
-                want_xyz=True, modulation=False):
+                want_xyz=True, modulation=False, strict=False):
     """cfg: dict with W,H,PW,PH,N,M_v,M_h,fw_v,fw_h,dirs.  Returns a Result of numpy planes."""
     c = Config(**{k: int(cfg[k]) for k in
                   ("W", "H", "PW", "PH", "N", "M_v", "M_h", "fw_v", "fw_h", "dirs")})
@@ -258,7 +258,7 @@ def reconstruct(cfg, cal, fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi,
                 _p(r.cpmap), _p(r.xyz), _p(r.pts), _p(r.pix), 0)
     u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
     keep = [u8(x) for x in (fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi)]
-    lib().o3d_reconstruct_ex(C.byref(c), C.byref(cal), *[_p(k) for k in keep], int(bool(modulation)),
+    lib().o3d_reconstruct_ex(C.byref(c), C.byref(cal), *[_p(k) for k in keep], int(bool(modulation)) | (2 if strict else 0),
                              C.byref(o), int(threads))
     r.count = int(o.count)
     if two:

@@ -54,6 +54,19 @@ void o3d_check_roi(const uint8_t *roi, int W, int H, int32_t *valid)
     for (long i = 0; i < (long)W * H; i++) valid[i] = roi[i] != 0 ? 1 : 0;
 }
 
+/* The same function exactly as committed (3/wrapped_phase.cpp:78-127): the map is cleared, then filled from
+ * `selected_region[j][i] == 1` ONLY when number_of_patterns_fringe is 3 or 4 (:106); the 5-step block (:117-127)
+ * is commented out, so a 5-step run of the reference ends with an all-zero valid map and an empty cloud.
+ * o3d_check_roi above (any N, roi != 0) is the deliberate extension the product's default follows; this literal
+ * form backs SCAN3D_FLAG_STRICT_REFERENCE. */
+void o3d_check_roi_strict(const uint8_t *roi, int N, int W, int H, int32_t *valid)
+{
+    for (long i = 0; i < (long)W * H; i++) valid[i] = 0;
+    if (N == 4 || N == 3)
+        for (long i = 0; i < (long)W * H; i++)
+            if (roi[i] == 1) valid[i] = 1;
+}
+
 /* Extension weights for N not in {3,4,5,8}: shifts delta_k = 2*pi*k/N (true pi), libm. */
 /* check_I_mod_criteria, the branch the reference keeps commented out (3/wrapped_phase.cpp:84-104,
  * 3-step only): gamma = sqrtf(3 (I0-I2)^2 + (2 I1 - I0 - I2)^2) / (float)(I0+I1+I2), the pixel is
@@ -601,7 +614,9 @@ void o3d_reconstruct_ex(const o3d_config *cfg, const o3d_calib *cal, const uint8
         const int M = dir == 0 ? cfg->M_v : cfg->M_h;
         memset(wr, 0, n * sizeof(float));
         memset(un, 0, n * sizeof(float));
-        if (modulation && cfg->N == 3) o3d_check_I_mod_criteria(dir == 0 ? fringe_v : fringe_h, roi, W, H, valid);
+        /* `modulation` is a bit set: 1 = the commented-out modulation criterion, 2 = check_I_mod_criteria as committed */
+        if ((modulation & 1) && cfg->N == 3) o3d_check_I_mod_criteria(dir == 0 ? fringe_v : fringe_h, roi, W, H, valid);
+        else if (modulation & 2) o3d_check_roi_strict(roi, cfg->N, W, H, valid);
         else o3d_check_roi(roi, W, H, valid);
         o3d_wrapped_phase(dir == 0 ? fringe_v : fringe_h, cfg->N, W, H, valid, wr, NULL, threads);
         o3d_mask_recurrence(valid, W, H, NULL);

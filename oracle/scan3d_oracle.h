@@ -42,6 +42,13 @@
  *   frame; raster-order compaction with (float) casts.
  * Policies where the reference reads uninitialised memory: all output planes are
  * zero-filled before a stage writes them.
+ * Deliberate deviations from the reference AS COMMITTED (both have a literal counterpart, o3d_check_roi_strict /
+ * flag bit 2 of o3d_reconstruct_ex, that the product follows under SCAN3D_FLAG_STRICT_REFERENCE):
+ *   - check_I_mod_criteria fills the valid map only for N == 3 or 4 (3/wrapped_phase.cpp:106; the 5-step block
+ *     :117-127 is commented out), so the reference's own 5-step run yields an all-zero map and an empty cloud.
+ *     Default here: the ROI is honoured for every N (the 5-step atan2f formula then has pixels to work on).
+ *   - the reference tests selected_region == 1; default here: any non-zero ROI byte selects the pixel
+ *     (image_scissor only ever writes 0 and 1, m_tech_project_console.cpp:186-229).
  */
 #ifndef SCAN3D_ORACLE_H
 #define SCAN3D_ORACLE_H
@@ -55,6 +62,8 @@ extern "C" {
 /* ---- stage 3 : 3/wrapped_phase.cpp ---- */
 /* check_I_mod_criteria :64-143 (live part :78-82,106-115): valid0 = (roi != 0). */
 void o3d_check_roi(const uint8_t *roi, int W, int H, int32_t *valid);
+/* the same as committed: selected_region == 1, and only for N == 3 or 4 (:106; the 5-step block :117-127 is commented out) */
+void o3d_check_roi_strict(const uint8_t *roi, int N, int W, int H, int32_t *valid);
 /* the disabled modulation criterion of the same function (:84-104, 3-step): fringe = [3][H][W] */
 void o3d_check_I_mod_criteria(const uint8_t *fringe, const uint8_t *roi, int W, int H, int32_t *valid);
 

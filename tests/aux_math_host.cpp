@@ -28,42 +28,13 @@ void s3a_host_remap(const uint8_t* src, int W, int H, const int16_t* xy, const u
     }
 }
 
-// k_remap_frames with S3D_VAR_REMAP_WINDOW: groups of 4 pixels, window path when the group allows it.
-// Returns the number of groups that took the window path.
-long long s3a_host_remap_window(const uint8_t* src, int W, int H, const int16_t* xy, const uint16_t* frac, uint8_t* dst)
-{
-    const size_t plane = (size_t)W * H;
-    long long n_fast = 0;
-    for (size_t p = 0; p + 4 <= plane; p += 4) {
-        const s3a::RemapGroup g = s3a::remap_group_prepare(xy + 2 * p, W, H, W % 8 == 0);
-        int fr[4];
-        for (int k = 0; k < 4; k++) fr[k] = frac[p + k];
-        uint32_t packed = 0;
-        if (g.fast) {
-            uint32_t r0[4], r1[4];
-            memcpy(r0, src + g.base, 16);          // the kernel: two 8-byte loads per row
-            memcpy(r1, src + g.base + W, 16);
-            packed = s3a::remap_group_blend(g, r0, r1, fr);
-            n_fast++;
-        } else {
-            for (int k = 0; k < 4; k++) {
-                const int x = xy[2 * (p + k)], y = xy[2 * (p + k) + 1];
-                packed |= (uint32_t)s3a::bilinear_u8(tap(src, W, H, x, y), tap(src, W, H, x + 1, y), tap(src, W, H, x, y + 1),
-                                                     tap(src, W, H, x + 1, y + 1), fr[k]) << (8 * k);
-            }
-        }
-        memcpy(dst + p, &packed, 4);
-    }
-    return n_fast;
-}
-
-// k_remap_tiled (S3D_VAR_REMAP_TILED): per output tile the source box from the map's extremes, the box staged in a
+// k_remap_tiled: per output tile the source box from the map's extremes, the box staged in a
 // buffer with the kernel's pitch, taps gathered from the buffer; tiles whose box does not qualify take the per-tap path.
 // Returns the number of tiles that were staged.
 long long s3a_host_remap_tiled(const uint8_t* src, int W, int H, const int16_t* xy, const uint16_t* frac, uint8_t* dst)
 {
     using namespace s3a;
-    static uint8_t box[REMAP_BOX_H * REMAP_BOX_W];
+    alignas(16) static uint8_t box[REMAP_BOX_H * REMAP_BOX_W + 16];
     long long staged = 0;
     for (int ty0 = 0; ty0 < H; ty0 += REMAP_TILE_H)
         for (int tx0 = 0; tx0 < W; tx0 += REMAP_TILE_W) {
@@ -90,8 +61,11 @@ long long s3a_host_remap_tiled(const uint8_t* src, int W, int H, const int16_t* 
                     const size_t p = (size_t)y * W + x;
                     const int sx = xy[2 * p], sy = xy[2 * p + 1];
                     if (b.ok) {
-                        const uint8_t* q = box + remap_box_offset(b, sx, sy);
-                        dst[p] = bilinear_u8(q[0], q[1], q[REMAP_BOX_W], q[REMAP_BOX_W + 1], frac[p]);
+                        // the kernel's blend: packed weight pairs, taps by funnel shift, two-way dot products
+                        const int off = remap_box_offset(b, sx, sy);
+                        uint32_t wA, wB;
+                        bilinear_weight_pairs(frac[p], &wA, &wB);
+                        dst[p] = (uint8_t)bilinear_u8_pairs(wA, wB, box_taps(box, off), box_taps(box, off + REMAP_BOX_W));
                     } else {
                         dst[p] = bilinear_u8(tap(src, W, H, sx, sy), tap(src, W, H, sx + 1, sy), tap(src, W, H, sx, sy + 1),
                                              tap(src, W, H, sx + 1, sy + 1), frac[p]);

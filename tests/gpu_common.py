@@ -24,11 +24,11 @@ def cfg_dict(cfg):
     return {k: getattr(cfg, k) for k in ("W", "H", "PW", "PH", "N", "M_v", "M_h", "fw_v", "fw_h", "dirs")}
 
 
-def run_oracle(cfg, ocal, stack, roi, threads=0, modulation=False):
+def run_oracle(cfg, ocal, stack, roi, threads=0, modulation=False, strict=False):
     d = s3.split_stack(cfg, stack)
     return o.reconstruct(cfg_dict(cfg), ocal, d["fringe_v"], d["gray_v"], d["inv_v"],
                          d.get("fringe_h"), d.get("gray_h"), d.get("inv_h"), roi, threads=threads,
-                         modulation=modulation)
+                         modulation=modulation, strict=strict)
 
 
 def compare(cfg, ref, ctx, fused=True, report=None):
@@ -64,10 +64,25 @@ def compare(cfg, ref, ctx, fused=True, report=None):
         st["pts_max_rel"] = float((np.abs(pts - ref.pts) / scale).max(initial=0))
         assert st["pts_max_rel"] <= 1e-5
     else:
-        # a phase that differs in the last float bit may move an lrint() correspondence;
-        # bound how many pixels that can touch and compare the rest
+        # a phase that differs in the last float bit may move an lrint() correspondence: bound how many pixels
+        # that can touch, and still hold every pixel it cannot have touched to the full bar
         assert st["cpmap_mismatch"] <= st["unw_v_nonidentical"] + st["unw_h_nonidentical"]
         assert st["valid_mismatch"] <= st["cpmap_mismatch"]
+        touched = ((unw_v.view(np.uint32) != ref.unwrapped_v.view(np.uint32)) |
+                   (unw_h.view(np.uint32) != ref.unwrapped_h.view(np.uint32))).reshape(-1)
+        assert not ((cp != ref.cpmap).any(axis=1) & ~touched).any(), "c_p_map differs at a pixel whose phases are identical"
+        assert not ((valid.reshape(-1) != ref.valid.reshape(-1)) & ~touched).any()
+        # points: match them by pixel (both lists are in raster order of their valid pixels)
+        g_pix = np.flatnonzero(valid.reshape(-1) == 1)
+        r_pix = np.flatnonzero(ref.valid.reshape(-1) == 1)
+        assert n == g_pix.size
+        common = np.intersect1d(g_pix[~touched[g_pix]], r_pix[~touched[r_pix]])
+        gi, ri = np.searchsorted(g_pix, common), np.searchsorted(r_pix, common)
+        scale = np.maximum(np.abs(ref.pts[ri]).max(axis=1, keepdims=True), 1e-30)
+        st["pts_max_rel"] = float((np.abs(pts[gi] - ref.pts[ri]) / scale).max(initial=0))
+        st["pts_compared"] = int(common.size)
+        assert st["pts_max_rel"] <= 1e-5
+        assert abs(n - ref.count) <= st["valid_mismatch"]
     if report is not None:
         report.update(st)
     return st

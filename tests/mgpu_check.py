@@ -1,7 +1,9 @@
 #!/usr/bin/env python
-"""Multi-GPU check (run under torchrun, NCCL): the row-sharded reconstruction gathered over NVLink
-is byte-identical to the single-GPU reconstruction of the same frame, and frame-parallel ranks
-agree with a serial replay.  Usage:
+"""Multi-GPU check (run under torchrun, NCCL): the row-sharded reconstruction gathered on rank 0 is byte-identical to
+the single-GPU reconstruction of the same frame -- through the NCCL send/recv gather and through the C++ row-shard
+group (include/scan3d_shard.h), the latter in exactly bench.py's overlapped schedule: SIX DISTINCT scans pipelined
+over two contexts / two streams / two output slots with no barrier between them, every gathered cloud compared.
+Usage:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/mgpu_check.py
 """
 import importlib
@@ -18,6 +20,7 @@ import torch.distributed as dist
 from gpu_common import calibs, s3
 
 sh = importlib.import_module("3dscan_b200.sharding")
+N_SCANS = 6
 
 
 def main():
@@ -27,52 +30,69 @@ def main():
     W, H, PW, PH = 2048, 1537, 2048, 1536
     cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
     full = s3.make_config(W, H, PW, PH, 8, 10, 10, 2, 2, 2)
-    stack, roi = s3.synth_stack(full, cal)          # every rank renders the same frame (deterministic)
     row0, rows = sh.row_block(H, rank, world)
     cfg = s3.make_config(W, rows, PW, PH, 8, 10, 10, 2, 2, 2, row0=row0, H_total=H)
+    # distinct scans: every rank renders the same frames (deterministic), keeps its rows; rank 0 also keeps the
+    # single-GPU result of every whole frame
+    stacks, rois, want = [], [], []
+    ref = s3.Scan3D(full, lr, cal) if rank == 0 else None
+    for k in range(N_SCANS):
+        stack, roi = s3.synth_stack(full, cal, s3.default_synth_params(seed=0x3D5CA9 + k, roi_fraction=0.75 - 0.07 * k))
+        if rank == 0:
+            ref.reconstruct(stack, roi)
+            want.append(ref.points().copy())
+        stacks.append(torch.from_numpy(np.ascontiguousarray(stack[:, row0:row0 + rows])).cuda())
+        rois.append(torch.from_numpy(roi).cuda())
+        del stack
+    if ref is not None:
+        ref.close()
+
+    # ---- 1. NCCL gather (all-gather of the counts + send/recv), scan 0
     ctx = s3.Scan3D(cfg, lr, cal)
-    n = ctx.reconstruct(np.ascontiguousarray(stack[:, row0:row0 + rows]), roi)
+    ctx.reconstruct_dev(stacks[0].data_ptr(), rois[0].data_ptr())
+    n = ctx.point_count()
     pts = torch.from_numpy(ctx.points()).cuda()
     got, counts = sh.gather_points(pts, n, dst=0)
     ok = True
     if rank == 0:
-        ref = s3.Scan3D(full, lr, cal)
-        n_ref = ref.reconstruct(stack, roi)
-        want = ref.points()
-        ok = n_ref == sum(counts) and np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
-        print("row-shard over %d GPUs: %d points, counts %s, identical to 1 GPU: %s" % (world, n_ref, counts, ok))
-        ref.close()
-    # same frame again with the exchange folded into the kernel: the other ranks' IO warps write their
-    # points into rank 0's memory over NVLink (PeerPointSink), rank 0 only moves the blocks into place
-    import bench
-    sink = sh.PeerPointSink(ctx, rows * W, dst=0, slots=2)
-    out = torch.empty((H * W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None
-    cnt = bench._wrap_device(torch, ctx.device_point_count(), (1,), "<i4")
-    st = torch.cuda.Stream()                               # (stream handle 0 would mean "ctx-owned stream")
-    torch.cuda.set_stream(st)
-    ctx.set_stream(st.cuda_stream)
-    stack_d = torch.from_numpy(np.ascontiguousarray(stack[:, row0:row0 + rows])).cuda()
-    roi_d = torch.from_numpy(roi).cuda()
+        ok = sum(counts) == len(want[0]) and np.array_equal(got.cpu().numpy().view(np.uint32), want[0].view(np.uint32))
+        print("row-shard over %d GPUs, NCCL gather: %d points, counts %s, identical to 1 GPU: %s" % (world, sum(counts), counts, ok))
+    ctx.close()
+
+    # ---- 2. the row-shard group in bench.py's schedule: decode(k+1) is enqueued before gather(k); no barrier anywhere
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    ctxs = [s3.Scan3D(cfg, lr, cal, stream=st.cuda_stream) for st in streams]
+    group = sh.RowShardGroup("chk%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid()), rank, world, lr, H * W, slots=2)
+    for i in range(2):
+        group.bind(i, ctxs[i])
+
+    def decode(k):
+        ctxs[k & 1].reconstruct_dev(stacks[k].data_ptr(), rois[k].data_ptr())
+
     ok2 = True
-    for rep in range(3):                                   # slot 0, 1, 0: exercises block reuse
+    decode(0)
+    for k in range(N_SCANS):
+        if k + 1 < N_SCANS:
+            decode(k + 1)
+        total, counts = group.gather(k & 1, ctxs[k & 1])
         if rank == 0:
-            out.zero_()
-        torch.cuda.synchronize(); dist.barrier()
-        sink.begin(rep % 2)
-        ctx.reconstruct_dev(stack_d.data_ptr(), roi_d.data_ptr())
-        own = bench._wrap_device(torch, ctx.device_points(), (rows * W, 3), "<f4") if rank == 0 else None
-        got2, counts2 = sink.finish(rep % 2, cnt, own, out)
-        torch.cuda.synchronize()
-        if rank == 0:
-            same = sum(counts2) == n_ref and np.array_equal(got2.cpu().numpy().view(np.uint32), want.view(np.uint32))
+            cloud = s3.wrap_device(group.output_ptr(k & 1), (total, 3), "<f4")
+            host = np.asarray(torch.as_tensor(cloud, device="cuda").cpu())
+            same = total == len(want[k]) and np.array_equal(host.view(np.uint32), want[k].view(np.uint32))
             ok2 = ok2 and same
+            if not same:
+                print("  scan %d: %d points (want %d), counts %s: MISMATCH" % (k, total, len(want[k]), counts))
+        group.release(k & 1)
     if rank == 0:
-        print("in-kernel NVLink point stream (PeerPointSink), 3 scans: identical to 1 GPU: %s" % ok2)
+        print("row-shard group (shared-memory board + copy-engine pushes over NVLink), %d distinct pipelined scans: "
+              "every cloud identical to 1 GPU: %s" % (N_SCANS, ok2))
     ok = ok and ok2
-    sink.close()
+    torch.cuda.synchronize()
+    group.close()
+    for c in ctxs:
+        c.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    ctx.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 

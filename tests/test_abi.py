@@ -269,3 +269,33 @@ def test_colour_bmp_loads_as_the_grey_image_opencv_returns(tmp_path):
     p = tmp_path / "colour.bmp"
     p.write_bytes(g["bmp24_bytes"].tobytes())
     assert np.array_equal(s3.read_bmp8(str(p)), g["bmp24_grey"])
+
+
+def test_colour_bmp_reader_and_malformed_files(tmp_path):
+    """scan3d_read_bmp_bgr = cvLoadImage in colour (8/save_point_cloud.cpp:59-66: texture.bmp, split into B, G, R);
+    truncated or inconsistent headers are refused instead of read past (palette and pixel-data bounds)."""
+    import cv2
+    g = np.load(os.path.join(GOLDEN, "f4_kat.npz"))
+    p = tmp_path / "colour.bmp"
+    raw = g["bmp24_bytes"].tobytes()
+    p.write_bytes(raw)
+    assert np.array_equal(s3.read_bmp_bgr(str(p)), cv2.imread(str(p), cv2.IMREAD_COLOR))
+    # an 8-bit palettised file through both readers
+    grey = (np.arange(12 * 20, dtype=np.uint32).reshape(12, 20) * 7 % 256).astype(np.uint8)
+    q = tmp_path / "grey.bmp"
+    s3.write_bmp8(str(q), grey) if hasattr(s3, "write_bmp8") else cv2.imwrite(str(q), grey)
+    assert np.array_equal(s3.read_bmp8(str(q)), grey)
+    assert np.array_equal(s3.read_bmp_bgr(str(q)), np.repeat(grey[:, :, None], 3, axis=2))
+    ok = q.read_bytes()
+    bad = []
+    bad.append(ok[:60])                                                     # cut inside the palette
+    bad.append(ok[:len(ok) - 5])                                            # cut inside the pixel data
+    bad.append(ok[:10] + (2 ** 31 - 1).to_bytes(4, "little") + ok[14:])     # pixel-data offset far outside the file
+    bad.append(ok[:14] + (5000).to_bytes(4, "little") + ok[18:])            # info-header size larger than the file
+    bad.append(ok[:10] + (20).to_bytes(4, "little") + ok[14:])              # pixel data overlapping the header
+    for i, b in enumerate(bad):
+        f = tmp_path / ("bad%d.bmp" % i)
+        f.write_bytes(b)
+        for reader in (s3.read_bmp8, s3.read_bmp_bgr):
+            with pytest.raises(s3.Scan3DError):
+                reader(str(f))

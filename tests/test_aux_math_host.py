@@ -66,31 +66,10 @@ def test_undistort_map_and_remap_match_oracle(shim):
         assert np.array_equal(_host_remap(shim, img, xy, fr), o.undistort_frames(img[None], K, d)[0]), (W, H)
 
 
-def test_window_gather_variant_matches_oracle(shim):
-    """The experimental windowed gather (S3D_VAR_REMAP_WINDOW: two aligned 8-byte loads per source row instead of
-    8 one-byte gathers) gives the same pixels, on mild maps (almost every group takes the window path) and on
-    strong / skewed ones (mixed paths, borders)."""
-    shim.s3a_host_remap_window.restype = C.c_longlong
-    rng = np.random.default_rng(6)
-    c = load_calib_c1()
-    cases = _cases() + [(1600, 96, c["Kc"].reshape(3, 3), c["dc"]), (1024, 64, np.array([[900.0, 0, 511.5], [0, 900.0, 31.5], [0, 0, 1]]), np.zeros(5))]
-    for W, H, K, d in cases:
-        if (W * H) % 4:
-            continue
-        xy, fr = _host_map(shim, K, d, W, H)
-        img = rng.integers(0, 256, (H, W), dtype=np.uint8)
-        out = np.zeros_like(img)
-        n_fast = shim.s3a_host_remap_window(_p(img), W, H, _p(xy), _p(fr), _p(out))
-        assert np.array_equal(out, o.undistort_frames(img[None], K, d)[0]), (W, H)
-        if (W, H) in ((1600, 96), (1024, 64)):
-            assert n_fast > 0.85 * (W * H // 4), (W, H, n_fast)    # realistic maps: the window path dominates (96 % at 12 MP)
-        if W % 8:
-            assert n_fast == 0
-
-
-def test_tiled_staging_variant_matches_oracle(shim):
-    """The experimental tiled remap (S3D_VAR_REMAP_TILED: the tile's source box staged in a buffer, taps gathered from
-    it) gives the same pixels; with the reference's calibration almost every tile qualifies for staging."""
+def test_tiled_remap_arithmetic_matches_oracle(shim):
+    """k_remap_tiled's arithmetic on the host (the tile's source box staged in a buffer, taps taken from it by funnel
+    shift, packed weight pairs, two-way dot products) gives the oracle's pixels; with the reference's calibration
+    almost every tile qualifies for staging."""
     shim.s3a_host_remap_tiled.restype = C.c_longlong
     rng = np.random.default_rng(7)
     c = load_calib_c1()

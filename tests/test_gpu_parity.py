@@ -289,6 +289,82 @@ def test_fused_long_runs_without_roi(kind):
     ctx.close()
 
 
+@pytest.mark.parametrize("N", [3, 5])
+def test_quirk_strict_reference_validity(N):
+    """check_I_mod_criteria as committed (3/wrapped_phase.cpp:106,117-127): the ROI is read as `== 1`, and only for
+    N == 3 or 4 -- the 5-step block is commented out, so the reference's own 5-step run ends with an all-zero valid map
+    and an empty cloud.  Default: every non-zero ROI byte selects, for every N (documented extension);
+    SCAN3D_FLAG_STRICT_REFERENCE: the committed behaviour.  Both against the oracle's two restatements."""
+    W, H, PW, PH = 640, 96, 512, 288
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    base = s3.make_config(W, H, PW, PH, N, 7, 6, 4, 5, 2)
+    stack, roi = s3.synth_stack(base, cal)
+    roi[20:40, 100:300] *= 7            # selected, but not with the value 1
+    for strict in (False, True):
+        cfg = s3.make_config(W, H, PW, PH, N, 7, 6, 4, 5, 2, flags=s3.FLAG_STRICT_REFERENCE if strict else 0)
+        ref = run_oracle(cfg, ocal, stack, roi, strict=strict)
+        ctx = _ctx(cfg, cal)
+        n = ctx.reconstruct(stack, roi)
+        compare(cfg, ref, ctx)
+        assert n == ref.count
+        v = ctx.plane(s3.PLANE_VALID)
+        if strict and N == 5:
+            assert n == 0 and not v.any()                 # the reference as committed: nothing survives a 5-step run
+        elif strict:
+            assert n > 0 and not v[20:40, 100:300].any()  # ROI bytes != 1 are not selected
+        else:
+            assert n > 0 and v[22:38, 110:290].any()
+        # the stage entries follow the same rule
+        d = s3.split_stack(cfg, stack)
+        ctx.compute_wrapped_phase(0, d["fringe_v"], roi)
+        m = ctx.plane(s3.PLANE_MASK)
+        assert np.array_equal(m.astype(np.int32), ref.valid_v)
+        ctx.close()
+
+
+def test_planes_nothing_has_written_are_not_handed_out():
+    """scan3d_get_plane / scan3d_device_plane refuse planes no compute entry has produced (after the single-pass
+    entry: the wrapped phases and per-direction masks, which it keeps in registers)."""
+    W, H, PW, PH = 640, 64, 512, 288
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, 3, 7, 6, 4, 5, 2)
+    stack, roi = s3.synth_stack(cfg, cal)
+    ctx = _ctx(cfg, cal)
+    for which in (s3.PLANE_UNWRAPPED_V, s3.PLANE_VALID, s3.PLANE_CPMAP, s3.PLANE_MASK, s3.PLANE_WRAPPED_V, s3.PLANE_XYZ):
+        with pytest.raises(RuntimeError):
+            ctx.plane(which)
+        assert not ctx.device_plane(which)
+    ctx.reconstruct(stack, roi)
+    ctx.plane(s3.PLANE_UNWRAPPED_H); ctx.plane(s3.PLANE_VALID); ctx.plane(s3.PLANE_CPMAP)
+    for which in (s3.PLANE_MASK, s3.PLANE_WRAPPED_V, s3.PLANE_XYZ):
+        with pytest.raises(RuntimeError):
+            ctx.plane(which)
+    d = s3.split_stack(cfg, stack)
+    ctx.compute_wrapped_phase(0, d["fringe_v"], roi)
+    ctx.plane(s3.PLANE_MASK); ctx.plane(s3.PLANE_WRAPPED_V)
+    with pytest.raises(RuntimeError):
+        ctx.plane(s3.PLANE_VALID)         # the inputs changed: the old final map no longer belongs to them
+    ctx.close()
+
+
+def test_c5_size_single_rank_matches_oracle():
+    """BASELINE.json configs[4] at its own size on ONE rank: 8192 x 6144 (50 MP), 8-step + 10-bit Gray code, both
+    directions -- every contract output against the oracle (multi-threaded, a few seconds), points bit for bit."""
+    W, H, PW, PH = 8192, 6144, 8192, 6144
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, 8, 10, 10, 8, 8, 2, flags=s3.FLAG_POINT_PIXELS)
+    stack, roi = s3.synth_stack(cfg, cal)
+    ref = run_oracle(cfg, ocal, stack, roi, threads=0)
+    ctx = _ctx(cfg, cal)
+    n = ctx.reconstruct(stack, roi)
+    st = compare(cfg, ref, ctx)
+    assert st["unw_v_nonidentical"] == 0 and st["unw_h_nonidentical"] == 0 and st["pts_nonidentical"] == 0
+    pts, pix = ctx.points(want_pix=True)
+    assert np.array_equal(pix, ref.pix) and n == ref.count and n > 25_000_000
+    print(st)
+    ctx.close()
+
+
 def test_modulation_mask_flag_matches_oracle():
     """SCAN3D_FLAG_MODULATION_MASK = the reference's commented-out criterion (3/wrapped_phase.cpp:84-104):
     every (I0,I1,I2) triple through scan3d_compute_wrapped_phase, then a whole scan with flat and

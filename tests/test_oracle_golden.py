@@ -166,3 +166,17 @@ def test_modulation_criterion_restatement_all_triples():
     assert got[0, 0] == 0 and 0 < got.sum() < got.size            # black pixel rejected; both outcomes occur
     roi[:, ::2] = 0
     assert np.array_equal(o.check_I_mod_criteria(fr, roi), want * (roi != 0))
+
+
+def test_quirk_check_I_mod_criteria_as_committed():
+    """3/wrapped_phase.cpp:106-127: the valid map is filled from selected_region == 1 only for N == 3 or 4; the 5-step
+    block is commented out.  o3d_check_roi_strict is that literal form, o3d_check_roi the default (documented)
+    extension: any non-zero byte, every N."""
+    import ctypes as C
+    roi = np.array([[0, 1, 2, 255, 1, 0, 1, 1]], np.uint8)
+    out = np.empty(roi.shape, np.int32)
+    L = o.lib()
+    for N, want in ((3, [0, 1, 0, 0, 1, 0, 1, 1]), (4, [0, 1, 0, 0, 1, 0, 1, 1]), (5, [0] * 8), (8, [0] * 8)):
+        L.o3d_check_roi_strict(roi.ctypes.data_as(C.c_void_p), N, roi.shape[1], roi.shape[0], out.ctypes.data_as(C.c_void_p))
+        assert out.ravel().tolist() == want, N
+    assert o.check_roi(roi).ravel().tolist() == [0, 1, 1, 1, 1, 0, 1, 1]
