@@ -288,7 +288,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rowshard", action="store_true", help="N > 1: skip the row-sharded 50 MP frame that rides along")
-    ap.add_argument("--contexts", type=int, default=2, help="contexts (each on its own stream) the batch alternates over")
+    ap.add_argument("--contexts", type=int, default=3, help="contexts (each on its own stream) the batch alternates over")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="row-shard workload, N>1: how the points reach rank 0")
     args = ap.parse_args()
     if args.warmup < 3:
