@@ -146,6 +146,9 @@ def cuda_lib():
     L.scan3d_roi_fill.argtypes = [vp, vp, vp, vp]
     L.scan3d_roi_fill_dev.argtypes = [vp, vp, vp, vp]
     L.scan3d_register_points.argtypes = [vp, vp, vp, i64, f32, f32, f32, f32]
+    L.scan3d_set_registration.argtypes = [vp, i32, f32, f32, f32, f32]
+    L.scan3d_reconstruct_raw.argtypes = [vp, vp, vp, C.POINTER(i64)]
+    L.scan3d_reconstruct_raw_dev.argtypes = [vp, vp, vp]
     L.scan3d_register_points_dev.argtypes = [vp, vp, vp, i64, f32, f32, f32, f32]
     L.scan3d_register_rotation.argtypes = [f32, vp]
     L.scan3d_peer_alloc.argtypes = [i32, i64, C.POINTER(vp), C.c_char_p]
@@ -368,6 +371,21 @@ class Scan3D:
         n = C.c_int64()
         self._ck(self.L.scan3d_reconstruct(self.h, _ptr(stack), _ptr(roi), C.byref(n)))
         return n.value
+
+    def set_registration(self, enable, theta_deg=0.0, tx=0.0, ty=0.0, tz=0.0):
+        """register_point_clouds' transform folded into the point store of the following reconstructions."""
+        self._ck(self.L.scan3d_set_registration(self.h, int(bool(enable)), theta_deg, tx, ty, tz))
+
+    def reconstruct_raw(self, raw_stack, roi):
+        """raw captures (before the capture loop's cvUndistort2) -> (registered) points in one call."""
+        raw_stack = np.ascontiguousarray(raw_stack, np.uint8)
+        roi = np.ascontiguousarray(roi, np.uint8)
+        n = C.c_int64()
+        self._ck(self.L.scan3d_reconstruct_raw(self.h, _ptr(raw_stack), _ptr(roi), C.byref(n)))
+        return n.value
+
+    def reconstruct_raw_dev(self, stack_ptr, roi_ptr):
+        self._ck(self.L.scan3d_reconstruct_raw_dev(self.h, C.c_void_p(stack_ptr), C.c_void_p(roi_ptr)))
 
     def reconstruct_dev(self, stack_ptr, roi_ptr):
         self._ck(self.L.scan3d_reconstruct_dev(self.h, C.c_void_p(stack_ptr), C.c_void_p(roi_ptr)))

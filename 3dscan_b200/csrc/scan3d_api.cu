@@ -12,6 +12,7 @@
 
 #include "scan3d_internal.h"
 #include "../common/scan3d_pattern_profile.h"
+#include "../common/scan3d_aux_math.h"
 
 using namespace s3d;
 
@@ -206,7 +207,7 @@ void scan3d_destroy(scan3d_ctx* ctx)
     void* ptrs[] = {ctx->cam_lut, ctx->proj_lut, ctx->atan_tab, ctx->nstep_w, ctx->wrapped[0], ctx->wrapped[1],
                     ctx->unwrapped[0], ctx->unwrapped[1], ctx->code[0], ctx->code[1], ctx->mask[0],
                     ctx->mask[1], ctx->valid, ctx->cpmap, ctx->xyz, ctx->pts, ctx->pix, ctx->rgb,
-                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->sched_ctr, ctx->stage_pts, ctx->stage_vb, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->roi_eff, ctx->roi_strict, ctx->pattern_profiles,
+                    ctx->texture, ctx->d_count, ctx->block_counts, ctx->tile_state, ctx->sched_ctr, ctx->stage_pts, ctx->stage_vb, ctx->tile_flags, ctx->tile_list, ctx->trace, ctx->d_stack, ctx->d_roi, ctx->d_undist, ctx->roi_eff, ctx->roi_eff_h, ctx->roi_strict, ctx->pattern_profiles,
                     ctx->undist_xy[0], ctx->undist_xy[1], ctx->undist_frac[0], ctx->undist_frac[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -494,7 +495,14 @@ static int reconstruct_stagewise(scan3d_ctx* ctx, const uint8_t* stack, const ui
     if (rc) return rc;
     rc = scan3d_triangulate(ctx);
     if (rc) return rc;
-    return scan3d_compact_points(ctx, nullptr);
+    rc = scan3d_compact_points(ctx, nullptr);
+    if (rc || !ctx->reg_on) return rc;
+    // scan3d_set_registration on the shape-generic route: the same transform over the compacted points, in place
+    // (all n = W*H slots: the count stays on the device; slots past it hold stale floats nobody reads)
+    CK(launch_register_points(points_of(ctx), points_of(ctx), (long long)n, ctx->reg_R, ctx->reg_t[0], ctx->reg_t[1], ctx->reg_t[2],
+                              ctx->sm_count, ctx->stream));
+    ctx->launches++;
+    return SCAN3D_OK;
 }
 
 int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint8_t* roi_dev)
@@ -506,7 +514,7 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
         const int rc = strict_roi(ctx, &roi_dev);
         if (rc) return rc;
     }
-    if (!ctx->fast_div_ok || (ctx->cfg.flags & SCAN3D_FLAG_MODULATION_MASK) || !fused7_supported(ctx->cfg)) {
+    if (!ctx->fast_div_ok || !fused7_supported(ctx->cfg)) {
         ctx->in_reconstruct = true;
         const int rc = reconstruct_stagewise(ctx, stack_dev, roi_dev);
         ctx->in_reconstruct = false;
@@ -515,6 +523,24 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     const scan3d_config& c = ctx->cfg;
     FusedArgs a{};
     a.stack = stack_dev; a.roi = roi_dev;
+    if (c.flags & SCAN3D_FLAG_MODULATION_MASK) {
+        // check_I_mod_criteria's modulation criterion (3/wrapped_phase.cpp:84-104): one effective ROI plane per
+        // direction from that direction's three fringe images (a pre-pass: the mask recurrence needs it two rows up)
+        const Shape s = shape_of(c);
+        const size_t n = npix(ctx);
+        if (!ctx->roi_eff) CK(dalloc(&ctx->roi_eff, n));
+        CK(launch_modulation_roi(s, stack_dev, roi_dev, ctx->roi_eff, ctx->stream));
+        ctx->launches++;
+        a.roi = ctx->roi_eff;
+        a.roi2 = ctx->roi_eff;
+        a.roi_list = roi_dev;
+        if (c.dirs == 2) {
+            if (!ctx->roi_eff_h) CK(dalloc(&ctx->roi_eff_h, n));
+            CK(launch_modulation_roi(s, stack_dev + (size_t)(c.N + 2 * c.M_v) * n, roi_dev, ctx->roi_eff_h, ctx->stream));
+            ctx->launches++;
+            a.roi2 = ctx->roi_eff_h;
+        }
+    }
     a.unw_v = ctx->unwrapped[0]; a.unw_h = ctx->unwrapped[1];
     a.code_v = ctx->code[0]; a.code_h = ctx->code[1];
     a.valid = ctx->valid; a.cpmap = ctx->cpmap;
@@ -528,6 +554,9 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
         CK(cudaMemsetAsync(ctx->tile_state, 0, ((size_t)fused_num_tiles(c) + 1) * 8, ctx->stream));
         a.epoch = ++ctx->epoch;
     }
+    a.reg_on = ctx->reg_on ? 1 : 0;
+    memcpy(a.reg_R, ctx->reg_R, sizeof(a.reg_R));
+    memcpy(a.reg_t, ctx->reg_t, sizeof(a.reg_t));
     a.W = c.W; a.H = c.H; a.row0 = c.row0; a.H_total = c.H_total; a.PW = c.PW; a.PH = c.PH;
     a.N = c.N; a.M_v = c.M_v; a.M_h = c.M_h; a.fw_v = c.fw_v; a.fw_h = c.fw_h;
 #if S3D_BUILD_V8
@@ -573,6 +602,50 @@ int scan3d_reconstruct(scan3d_ctx* ctx, const uint8_t* stack_host, const uint8_t
     CK(cudaMemcpyAsync(ctx->d_stack, stack_host, sb, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_roi, roi_host, rb, cudaMemcpyHostToDevice, ctx->stream));
     int rc = scan3d_reconstruct_dev(ctx, ctx->d_stack, ctx->d_roi);
+    if (rc) return rc;
+    if (count_out) {
+        if (ctx->cfg.dirs == 2) return scan3d_point_count(ctx, count_out);
+        *count_out = 0;
+    }
+    return scan3d_sync(ctx);
+}
+
+int scan3d_set_registration(scan3d_ctx* ctx, int enable, float theta_deg, float tx, float ty, float tz)
+{
+    if (!ctx) return SCAN3D_ERR_ARG;
+    if (ctx->cfg.dirs != 2) return fail(ctx, SCAN3D_ERR_STATE, "no point cloud in a one-direction configuration");
+    ctx->reg_on = enable != 0;
+    if (ctx->reg_on) {
+        s3a::register_rotation(theta_deg, ctx->reg_R);
+        ctx->reg_t[0] = tx; ctx->reg_t[1] = ty; ctx->reg_t[2] = tz;
+    }
+    return SCAN3D_OK;
+}
+
+int scan3d_reconstruct_raw_dev(scan3d_ctx* ctx, const uint8_t* raw_stack_dev, const uint8_t* roi_dev)
+{
+    if (!ctx || !raw_stack_dev || !roi_dev) return fail(ctx, SCAN3D_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const size_t sb = (size_t)scan3d_stack_bytes(&ctx->cfg);
+    if (!ctx->d_undist) CK(cudaMalloc((void**)&ctx->d_undist, sb));
+    const int frames = (int)(sb / npix(ctx));
+    int rc = scan3d_undistort_frames_dev(ctx, 0, raw_stack_dev, frames, ctx->d_undist);      // 2/project_pattern.cpp:220,234
+    if (rc) return rc;
+    return scan3d_reconstruct_dev(ctx, ctx->d_undist, roi_dev);
+}
+
+int scan3d_reconstruct_raw(scan3d_ctx* ctx, const uint8_t* raw_stack_host, const uint8_t* roi_host, int64_t* count_out)
+{
+    if (!ctx || !raw_stack_host || !roi_host) return fail(ctx, SCAN3D_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const size_t sb = (size_t)scan3d_stack_bytes(&ctx->cfg);
+    size_t rb;
+    roi_bytes(ctx, &rb);
+    if (!ctx->d_stack) CK(cudaMalloc((void**)&ctx->d_stack, sb));
+    if (!ctx->d_roi) CK(cudaMalloc((void**)&ctx->d_roi, rb));
+    CK(cudaMemcpyAsync(ctx->d_stack, raw_stack_host, sb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_roi, roi_host, rb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = scan3d_reconstruct_raw_dev(ctx, ctx->d_stack, ctx->d_roi);
     if (rc) return rc;
     if (count_out) {
         if (ctx->cfg.dirs == 2) return scan3d_point_count(ctx, count_out);

@@ -4,6 +4,7 @@
 #pragma once
 #include "scan3d_internal.h"
 #include "scan3d_fused_math.cuh"
+#include "../common/scan3d_aux_math.h"
 
 namespace s3d {
 

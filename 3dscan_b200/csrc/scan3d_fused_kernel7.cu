@@ -43,10 +43,13 @@ static int num_frames7(const scan3d_config& c)
 {
     return c.dirs == 2 ? 2 * c.N + 2 * (c.M_v + c.M_h) : c.N + 2 * c.M_v;
 }
+static bool mod7(const scan3d_config& c) { return (c.flags & SCAN3D_FLAG_MODULATION_MASK) != 0; }
 static size_t smem7(const scan3d_config& c, int cw)
 {
     const int T = 128 * cw;
-    return (size_t)num_frames7(c) * T + geom7(T).roi_bytes + (c.dirs == 2 ? 2 * 12 * T + 2 * (T / 4) : 0) + FIXED7;
+    // (with the modulation criterion the two directions have their own validity planes: a second ROI window)
+    return (size_t)num_frames7(c) * T + geom7(T).roi_bytes * (mod7(c) && c.dirs == 2 ? 2 : 1) +
+           (c.dirs == 2 ? 2 * 12 * T + 2 * (T / 4) : 0) + FIXED7;
 }
 
 struct Plan7 {
@@ -58,6 +61,7 @@ static bool plan7(const scan3d_config& c, Plan7* out)
 {
     if (c.W % 16 != 0) return false;
     if (!(c.N == 3 || c.N == 4 || c.N == 5 || c.N == 8)) return false;
+    if (mod7(c) && c.N != 3) return false;
     // Shapes are bounded by the register file of an SM sub-partition (16 K registers): warps are
     // dealt round-robin to the 4 sub-partitions, so ceil(warps per SM / 4) * 32 * regs <= 16384:
     // 20 warps at 96 registers, 16 at 128, 24 at 80.
@@ -70,6 +74,7 @@ static bool plan7(const scan3d_config& c, Plan7* out)
     for (int i = 0; i < 7; i++) {
         const int w = shapes[i][0], b = shapes[i][1];
         if (!((w == 7 && b == 2) || (w == 7 && b == 3) || (w == 9 && b == 2) || (w == 4 && b == 4) || (w == 6 && b == 2) || (w == 5 && b == 4))) continue;
+        if (mod7(c) && !(w == 7 && (b == 2 || b == 3))) continue;      // (the modulation variant is built for these two shapes)
         const size_t sm = smem7(c, w);
         if ((sm + 1024) * b <= (size_t)SMEM_MAX + 1024) {
             out->cw = w; out->minb = b; out->smem = sm;
@@ -95,7 +100,10 @@ constexpr int regs7(int cw, int minb)
 
 
 
-template <int N, int DIRS, int CW, int MINB, bool EXACT>
+// MOD: check_I_mod_criteria's modulation criterion (3/wrapped_phase.cpp:84-104, SCAN3D_FLAG_MODULATION_MASK): a pre-pass
+// has written one effective ROI plane per direction (a.roi = vertical, a.roi2 = horizontal); the mask recurrence runs
+// on each, so the two directions have their own masks (the reference's valid_map_vertical / _horizontal).
+template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false>
 __global__ void __launch_bounds__((CW + 1) * 32) __maxnreg__(regs7(CW, MINB))
 k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal, const __grid_constant__ CUtensorMap stack_map)
 {
@@ -109,7 +117,9 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
     const int NF = DIRS == 2 ? 2 * N + 2 * (a.M_v + a.M_h) : N + 2 * a.M_v;
     uint8_t* slot = smem;
     uint8_t* sroi = smem + (size_t)NF * T;
-    float* cxb = reinterpret_cast<float*>(sroi + G.roi_bytes);                 // [2][3*T]
+    constexpr int NROI = (MOD && DIRS == 2) ? 2 : 1;                           // ROI windows: one per direction with MOD
+    uint8_t* sroi2 = sroi + (NROI - 1) * G.roi_bytes;
+    float* cxb = reinterpret_cast<float*>(sroi + NROI * G.roi_bytes);          // [2][3*T]
     uint8_t* vfl = reinterpret_cast<uint8_t*>(cxb + (DIRS == 2 ? 2 * 3 * T : 0));   // [2][T/4] 4 valid bits per thread
     uint64_t* bars = reinterpret_cast<uint64_t*>(vfl + (DIRS == 2 ? 2 * (T / 4) : 0));
     double* tab = reinterpret_cast<double*>(bars + 8);
@@ -190,7 +200,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                         trace(a.trace, load_it, 0);
                         ctl[0] = pos;
                         posr[load_it & 7] = pos;
-                        mbar_expect_tx(bar_full, (uint32_t)NF * (a.use_tmap ? T : wt) + roi_sum);
+                        mbar_expect_tx(bar_full, (uint32_t)NF * (a.use_tmap ? T : wt) + NROI * roi_sum);
                     }
                     __syncwarp();
                     const uint32_t dst = smem_u32(slot);
@@ -203,9 +213,13 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                         const uint8_t* src = a.stack + p0;
                         for (int f = lane; f < NF; f += 32) bulk_g2s(dst + f * T, src + (size_t)f * plane, (uint32_t)wt, bar_full);
                     }
-                    if (roi_tx)
+                    if (roi_tx) {
                         bulk_g2s(smem_u32(sroi) + lane * G.roi_row + (uint32_t)(seg0 - (gbase + (long long)(lane - 2) * W)),
                                  a.roi + seg0, roi_tx, bar_full);
+                        if (NROI == 2)
+                            bulk_g2s(smem_u32(sroi2) + lane * G.roi_row + (uint32_t)(seg0 - (gbase + (long long)(lane - 2) * W)),
+                                     a.roi2 + seg0, roi_tx, bar_full);
+                    }
                     if (lane == 0) trace(a.trace, load_it, 1);
                     load_it++;
                 } else {
@@ -371,40 +385,44 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(slot);
 
         // ---------------- integer phase: mask, fringe terms, Gray bits ----------------
-        uint32_t mbits = 0;
+        uint32_t mbits = 0, mbits_h = 0;      // mask of the vertical direction (of both without MOD) / of the horizontal one
         Terms Tv, Th;
         uint32_t gvA = 0, gvB = 0, ghA = 0, ghB = 0;
         if (active) {
             const bool window_ok = y >= 2 && y + 1 < a.H_total && xt >= 4 && xt + 7 < W;
-            bool fast = false;
-            if (window_ok) {
-                uint32_t any_zero = 0;
+            // the mask recurrence's closed form on one ROI window -> the thread's 4 mask bits
+            auto mask_of = [&](const uint8_t* win) -> uint32_t {
+                if (window_ok) {
+                    uint32_t any_zero = 0;
 #pragma unroll
-                for (int r = 0; r < 4; r++)
+                    for (int r = 0; r < 4; r++)
 #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const uint32_t v = *reinterpret_cast<const uint32_t*>(sroi + r * G.roi_row + (lp0 + ROI_HALO - 4) + 4 * c);
-                        any_zero |= (v - 0x01010101u) & ~v & 0x80808080u;
-                    }
-                if (any_zero == 0) { mbits = 0xf; fast = true; }
-            }
-            if (!fast) {
-                const uint32_t centre = *reinterpret_cast<const uint32_t*>(sroi + 2 * G.roi_row + lp0 + ROI_HALO);
+                        for (int c = 0; c < 3; c++) {
+                            const uint32_t v = *reinterpret_cast<const uint32_t*>(win + r * G.roi_row + (lp0 + ROI_HALO - 4) + 4 * c);
+                            any_zero |= (v - 0x01010101u) & ~v & 0x80808080u;
+                        }
+                    if (any_zero == 0) return 0xfu;
+                }
+                uint32_t mb = 0;
+                const uint32_t centre = *reinterpret_cast<const uint32_t*>(win + 2 * G.roi_row + lp0 + ROI_HALO);
                 if (centre != 0) {
 #pragma unroll 1
                     for (int j = 0; j < 4; j++) {
                         const int x = xt + j;
                         auto inv = [&](int gx, int gy) {
-                            return sroi[(gy - y + 2) * G.roi_row + (lp0 + j + (gx - x) + ROI_HALO)] == 0;
+                            return win[(gy - y + 2) * G.roi_row + (lp0 + j + (gx - x) + ROI_HALO)] == 0;
                         };
                         bool v = !inv(x, y);
                         const bool border = x == 0 || y == 0 || x == W - 1 || y == a.H_total - 1;
                         if (v && !border) v = !mask_trigger(x, y, W, a.H_total, inv);
-                        mbits |= (v ? 1u : 0u) << j;
+                        mb |= (v ? 1u : 0u) << j;
                     }
                 }
-            }
-            if (mbits) {
+                return mb;
+            };
+            mbits = mask_of(sroi);
+            mbits_h = NROI == 2 ? mask_of(sroi2) : mbits;
+            if (mbits | mbits_h) {
                 fringe_terms<N>(sw, 0, WPF, tid, Tv);
                 gray_bits(sw, N, N + a.M_v, a.M_v, WPF, tid, gvA, gvB);
                 if (DIRS == 2) {
@@ -424,7 +442,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
         int4 cp01 = make_int4(0, 0, 0, 0), cp23 = cp01;   // the 4 pixels' correspondences, for the triangulation below
         // a warp whose 128 pixels hold no pixel of the mask writes the constant outputs and leaves its issue slots
         // to the other warps of the SM (about one warp in ten inside a tile that does hold ROI pixels)
-        const bool warp_has_px = __any_sync(0xffffffffu, mbits != 0);
+        const bool warp_has_px = __any_sync(0xffffffffu, (mbits | mbits_h) != 0);
         if (active && !warp_has_px) {
             const size_t g = (size_t)p0 + lp0;
             *reinterpret_cast<float4*>(a.unw_v + g) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -452,18 +470,19 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 for (int u = 0; u < 2; u++) {
                     const int j = 2 * h + u;
                     const int x = xt + j;
-                    const bool m = (mbits >> j) & 1u;
+                    const bool mv = (mbits >> j) & 1u, mh = (mbits_h >> j) & 1u;
+                    const bool m = mv && mh;                                             // merge_valid_maps, 5/compute_correspondance.cpp:60-77
                     const int cv = code_of(gvA, gvB, j, a.M_v);
                     const float wv = add_pi(phase_of<N>(Tv, j, tab));                    // 4/phase_unwrap.cpp:290
                     float unwv = (x == 0 || x == W - 1) ? 0.0f : unwrap_abs(wv, cv, fastdiv);  // :285, :291
-                    unwv = m ? unwv : 0.0f;
-                    bool v = m;
-                    r_cv[u] = m ? cv : -1;
+                    unwv = mv ? unwv : 0.0f;
+                    bool v = mv;
+                    r_cv[u] = mv ? cv : -1;
                     if (DIRS == 2) {
                         const int ch = code_of(ghA, ghB, j, a.M_h);
                         const float wh = add_pi(phase_of<N>(Th, j, tab));
                         float unwh = (y == 0 || y == a.H_total - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);  // :304, :309
-                        unwh = m ? unwh : 0.0f;
+                        unwh = mh ? unwh : 0.0f;
                         int px, py;                                                       // 5/compute_correspondance.cpp:648-675
                         const bool okx = correspond32(unwv, a.fw_v, &px);
                         const bool oky = correspond32(unwh, a.fw_h, &py);
@@ -473,7 +492,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                         // 0 <= p <= P-1 as one unsigned compare (saturated values fall outside as well)
                         v = m && okx && oky && (unsigned)px <= (unsigned)(a.PW - 1) && (unsigned)py <= (unsigned)(a.PH - 1);
                         r_unwh[u] = unwh;
-                        r_ch[u] = m ? ch : -1;
+                        r_ch[u] = mh ? ch : -1;
                     }
                     r_unwv[u] = unwv;
                     vb |= (v ? 1u : 0u) << u;
@@ -556,9 +575,12 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 }
                 if (EXACT) triangulate_point(cal.Ac, cal.Ap, uc, vc, up, vp, Xd);
                 else triangulate_point_fast(cal.Ac, cal.Ap, uc, vc, up, vp, Xd);
-                cx[3 * rank + 0] = __double2float_rn(Xd[0]);                       // 8/save_point_cloud.cpp:94-96
-                cx[3 * rank + 1] = __double2float_rn(Xd[1]);
-                cx[3 * rank + 2] = __double2float_rn(Xd[2]);
+                float px = __double2float_rn(Xd[0]), py = __double2float_rn(Xd[1]), pz = __double2float_rn(Xd[2]);   // 8/save_point_cloud.cpp:94-96
+                // optional: register_point_clouds' turntable transform on the float point (9/register_point_clouds.cpp:117-137)
+                if (a.reg_on) s3a::register_point(a.reg_R, a.reg_t[0], a.reg_t[1], a.reg_t[2], px, py, pz);
+                cx[3 * rank + 0] = px;
+                cx[3 * rank + 1] = py;
+                cx[3 * rank + 2] = pz;
                 rank++;
             }
             if (tid == 0) trace(a.trace, it, 4);
@@ -595,10 +617,10 @@ static bool stack_tensor_map(CUtensorMap* map, const uint8_t* stack, size_t plan
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int N, int DIRS, int CW, int MINB, bool EXACT>
+template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false>
 static cudaError_t launch7_t(const FusedArgs& a, const DeviceCalib& cal, int sm_count, const Plan7& p, cudaStream_t st)
 {
-    auto kern = k_fused7<N, DIRS, CW, MINB, EXACT>;
+    auto kern = k_fused7<N, DIRS, CW, MINB, EXACT, MOD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -639,6 +661,22 @@ static cudaError_t launch7_nd(const FusedArgs& a, const DeviceCalib& cal, int sm
     return cudaErrorInvalidValue;
 }
 
+// the modulation-criterion variant (3-step only, two launch shapes)
+template <int DIRS>
+static cudaError_t launch7_mod(const FusedArgs& a, const DeviceCalib& cal, int sm_count, const Plan7& p, bool exact, cudaStream_t st)
+{
+    if (p.cw != 7) return cudaErrorInvalidValue;
+    if (p.minb == 3) {
+        if (exact || DIRS == 1) return launch7_t<3, DIRS, 7, 3, true, true>(a, cal, sm_count, p, st);
+        return launch7_t<3, DIRS, 7, 3, (DIRS == 1), true>(a, cal, sm_count, p, st);
+    }
+    if (p.minb == 2) {
+        if (exact || DIRS == 1) return launch7_t<3, DIRS, 7, 2, true, true>(a, cal, sm_count, p, st);
+        return launch7_t<3, DIRS, 7, 2, (DIRS == 1), true>(a, cal, sm_count, p, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_fused7(const scan3d_config& c, const FusedArgs& a_in, const DeviceCalib& cal, int sm_count,
                           cudaStream_t st)
 {
@@ -652,6 +690,10 @@ cudaError_t launch_fused7(const scan3d_config& c, const FusedArgs& a_in, const D
     a.dynamic = 1;
     if (const char* e = getenv("SCAN3D_FUSED_DYN")) a.dynamic = atoi(e) != 0;
     const bool exact = !(c.flags & SCAN3D_FLAG_FAST_TRIANGULATION);
+    if (mod7(c)) {
+        if (!a.roi2 || !a.roi_list) return cudaErrorInvalidValue;
+        return c.dirs == 2 ? launch7_mod<2>(a, cal, sm_count, p, exact, st) : launch7_mod<1>(a, cal, sm_count, p, exact, st);
+    }
 #define S3D_F7(NN) (c.dirs == 2 ? launch7_nd<NN, 2>(a, cal, sm_count, p, exact, st) : launch7_nd<NN, 1>(a, cal, sm_count, p, exact, st))
     switch (c.N) {
         case 3: return S3D_F7(3);

@@ -42,6 +42,7 @@ struct scan3d_ctx {
     uint8_t* pattern_profiles = nullptr;   // scan3d_generate_patterns: 1-D profiles of both directions' patterns
     bool have_profiles[2] = {false, false};
     uint8_t* roi_eff = nullptr;    // SCAN3D_FLAG_MODULATION_MASK: ROI && modulation criterion of the current direction
+    uint8_t* roi_eff_h = nullptr;  // ... single-pass entry: the horizontal direction's plane (roi_eff = the vertical one's)
     uint8_t* roi_strict = nullptr; // SCAN3D_FLAG_STRICT_REFERENCE: (ROI == 1) && N in {3, 4}, whole frame
     double* nstep_w = nullptr;     // sin[64] then cos[64] (generic-N extension)
     short2* undist_xy[2] = {nullptr, nullptr};     // cv::undistort's fixed-point map of the camera [0] / projector [1]
@@ -77,6 +78,11 @@ struct scan3d_ctx {
     // staging for the host-buffer entries
     uint8_t* d_stack = nullptr;
     uint8_t* d_roi = nullptr;
+    uint8_t* d_undist = nullptr;   // scan3d_reconstruct_raw: the undistorted stack
+
+    // scan3d_set_registration
+    bool reg_on = false;
+    float reg_R[16] = {}, reg_t[3] = {};
 
     // stage bookkeeping
     bool have_wrapped[2] = {false, false};
@@ -131,6 +137,8 @@ cudaError_t launch_compact(const Shape& s, const double* xyz, const uint8_t* val
 struct FusedArgs {
     const uint8_t* stack;   // [NF][H][W]
     const uint8_t* roi;     // [H_total][W]
+    const uint8_t* roi2;    // modulation criterion: the horizontal direction's effective ROI (roi = the vertical one's)
+    const uint8_t* roi_list;   // ... and the caller's ROI, a superset of both: the work list is built from it
     float* unw_v; float* unw_h;
     int16_t* code_v; int16_t* code_h;
     uint8_t* valid;         // final valid (dirs==2) or mask (dirs==1)
@@ -144,6 +152,8 @@ struct FusedArgs {
     int dynamic;                  // v7: draw work-list positions from that counter instead of b, b+G, ...
     uint32_t* sched_ctr;          // v8: work-position counter (monotonic across launches)
     uint32_t pos_base;            // v8: the counter's value when this launch starts
+    int reg_on;                   // fold register_point_clouds' transform into the point store (scan3d_set_registration)
+    float reg_R[16], reg_t[3];
     float* stage_pts;             // v8: per-warp rings of staging slots for triangulated points (L2 resident)
     uint32_t* stage_vb;           // v8: ... and for the ballots of their valid bits (pixel indices / colours)
     int use_tmap;                 // v7: tile loads are one 2-D tensor copy (set by the launcher)

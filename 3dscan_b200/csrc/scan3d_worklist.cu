@@ -87,7 +87,7 @@ __global__ void k_tile_list(const uint8_t* __restrict__ flags, int n_tiles, int*
 
 cudaError_t launch_worklist(const FusedArgs& a, int T, int dirs, cudaStream_t st)
 {
-    k_tile_flags<<<(a.n_tiles + 7) / 8, 256, 0, st>>>(a.roi, T, a.W * a.H, a.n_tiles, (size_t)a.row0 * a.W, a.tile_flags,
+    k_tile_flags<<<(a.n_tiles + 7) / 8, 256, 0, st>>>(a.roi_list ? a.roi_list : a.roi, T, a.W * a.H, a.n_tiles, (size_t)a.row0 * a.W, a.tile_flags,
                                                       a.unw_v, a.unw_h, a.code_v, a.code_h, a.valid, a.cpmap, dirs);
     k_tile_list<<<1, 1024, 0, st>>>(a.tile_flags, a.n_tiles, a.tile_list, a.n_list, a.d_count);
     return cudaGetLastError();

@@ -259,6 +259,19 @@ int scan3d_register_points_dev(scan3d_ctx *ctx, const float *src_dev, float *dst
 /* the 4x4 float matrix R it uses (row-major), for diffing */
 int scan3d_register_rotation(float theta_deg, float R[16]);
 
+/* Both steps folded into the single-pass entry:
+ * scan3d_set_registration: the points scan3d_reconstruct[_dev] produces from now on are already rotated by
+ * theta_deg about the Y axis through (tx,ty,tz) -- register_point_clouds' transform applied to each float point where
+ * the kernel stores it, bit-identical to scan3d_register_points run afterwards, without another pass over the cloud.
+ * enable = 0 switches it off.
+ * scan3d_reconstruct_raw[_dev]: raw = the captured stack BEFORE the capture loop's cvUndistort2 (same plane order as
+ * scan3d_reconstruct): undistorts every frame (camera calibration) into a ctx-owned stack and runs the single-pass
+ * kernel on it, chained on the ctx's stream -- one call from raw captures to (registered) points, equal to
+ * scan3d_undistort_frames + scan3d_reconstruct (+ scan3d_register_points).  Whole-frame contexts only. */
+int scan3d_set_registration(scan3d_ctx *ctx, int enable, float theta_deg, float tx, float ty, float tz);
+int scan3d_reconstruct_raw(scan3d_ctx *ctx, const uint8_t *raw_stack_host, const uint8_t *roi_host, int64_t *count_out);
+int scan3d_reconstruct_raw_dev(scan3d_ctx *ctx, const uint8_t *raw_stack_dev, const uint8_t *roi_dev);
+
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t scan3d_launch_count(const scan3d_ctx *ctx);
 

@@ -392,11 +392,22 @@ def test_modulation_mask_flag_matches_oracle():
     stack[17:20, 300:340, 100:220] = rng.integers(118, 122, (3, 40, 120), dtype=np.uint8)   # around the threshold, H only
     stack[0:3, 200:230, 400:470] = 0                                                    # black: 0/0
     ctx = _ctx(cfg, cal)
+    l0 = ctx.launch_count()
     n = ctx.reconstruct(stack, roi)
+    # the single-pass kernel, not the stage chain: 2 pre-pass launches (one effective ROI plane per direction),
+    # the 2 work-list launches and the persistent kernel (the stage chain takes 13)
+    assert ctx.launch_count() - l0 == 5
     ref = run_oracle(cfg, ocal, stack, roi, modulation=True)
     assert (ref.valid_v != ref.valid_h).any() and 0 < ref.count == n
     st = compare(cfg, ref, ctx, fused=True)
     assert st["pts_nonidentical"] == 0
+    # fast triangulation + one direction through the same variant
+    cfg1 = s3.make_config(W, H, PW, PH, 3, 7, 7, 8, 8, 1, flags=s3.FLAG_MODULATION_MASK)
+    ctx1 = _ctx(cfg1, cal)
+    ctx1.reconstruct(stack[:17], roi)
+    ref1 = run_oracle(cfg1, ocal, stack[:17], roi, modulation=True)
+    compare(cfg1, ref1, ctx1, fused=True)
+    ctx1.close()
     plain = run_oracle(cfg, ocal, stack, roi)
     assert plain.count > ref.count                                                      # the criterion removed pixels
     ctx.close()

@@ -158,3 +158,33 @@ def test_register_point_clouds_call(tmp_path):
     assert np.array_equal(sel.T, oroi.astype(np.int32))          # the reference's [col][row] layout
     assert np.array_equal(s3.read_bmp8(f"{root}/i1.bmp"), ofilled)
     getattr(L, "_Z22scan3d_compat_shutdownv")()
+
+
+@pytest.mark.parametrize("shape", [(640, 480), (1000, 40)])
+def test_raw_entry_and_folded_registration_equal_the_separate_calls(shape):
+    """scan3d_reconstruct_raw (capture-side cvUndistort2 of every frame + the single-pass kernel, one call)
+    with scan3d_set_registration (register_point_clouds' transform in the kernel's point store) gives, bit for bit,
+    what scan3d_undistort_frames -> scan3d_reconstruct -> scan3d_register_points give (2/project_pattern.cpp:220-234,
+    9/register_point_clouds.cpp:83-148).  The second shape takes the shape-generic stage route (W % 16 != 0)."""
+    W, H = shape
+    PW, PH = 512, 288
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, 3, 7, 6, 4, 5, 2)
+    raw, roi = s3.synth_stack(cfg, cal)
+    theta, t = 36.0, (12.5, -3.25, 903.1)
+    a = s3.Scan3D(cfg, 0, cal)
+    und = a.undistort_frames(raw)
+    n = a.reconstruct(und, roi)
+    want = a.register_points(a.points(), theta, *t)
+    cp = a.plane(s3.PLANE_CPMAP)
+    a.close()
+    b = s3.Scan3D(cfg, 0, cal)
+    b.set_registration(True, theta, *t)
+    n2 = b.reconstruct_raw(raw, roi)
+    assert n2 == n and n > 1000
+    assert np.array_equal(b.plane(s3.PLANE_CPMAP), cp)
+    assert np.array_equal(b.points().view(np.uint32), want.view(np.uint32))
+    b.set_registration(False)
+    b.reconstruct_raw(raw, roi)
+    assert not np.array_equal(b.points().view(np.uint32), want.view(np.uint32))
+    b.close()
