@@ -554,7 +554,9 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
         CK(cudaMemsetAsync(ctx->tile_state, 0, ((size_t)fused_num_tiles(c) + 1) * 8, ctx->stream));
         a.epoch = ++ctx->epoch;
     }
-    a.reg_on = ctx->reg_on ? 1 : 0;
+    a.tmap_cache = &ctx->tmaps;
+    const bool fold_reg = ctx->reg_on && fused7_folds_registration(c);
+    a.reg_on = fold_reg ? 1 : 0;
     memcpy(a.reg_R, ctx->reg_R, sizeof(a.reg_R));
     memcpy(a.reg_t, ctx->reg_t, sizeof(a.reg_t));
     a.W = c.W; a.H = c.H; a.row0 = c.row0; a.H_total = c.H_total; a.PW = c.PW; a.PH = c.PH;
@@ -579,6 +581,12 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     {
         CK(launch_fused7(c, a, ctx->dcal, ctx->sm_count, ctx->stream));
         ctx->launches += 3;   // work-list flags, work-list scan, persistent fused kernel
+    }
+    if (ctx->reg_on && !fold_reg && c.dirs == 2) {
+        // shapes without the folding variant: the same transform as one more pass over the compacted points
+        CK(launch_register_points(points_of(ctx), points_of(ctx), (long long)npix(ctx), ctx->reg_R, ctx->reg_t[0], ctx->reg_t[1],
+                                  ctx->reg_t[2], ctx->sm_count, ctx->stream));
+        ctx->launches++;
     }
     ctx->have_wrapped[0] = ctx->have_wrapped[1] = false;
     ctx->have_unwrapped[0] = true;

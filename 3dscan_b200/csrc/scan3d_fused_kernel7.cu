@@ -1,5 +1,5 @@
 // scan3d_fused_kernel7.cu -- second-generation fused kernel ("v7").  Same work, same results and
-// same warp-specialised idea as scan3d_fused_kernel.cu, re-cut so that more consumer warps fit on
+// same warp-specialised idea as the first-generation kernel of round 1 (gone), re-cut so that more consumer warps fit on
 // an SM (throughput of this path follows the number of consumer warps: it is latency/issue bound,
 // see DESIGN.md section 7):
 //
@@ -90,6 +90,13 @@ bool fused7_supported(const scan3d_config& c)
     return plan7(c, &p);
 }
 
+// does the single-pass kernel for this configuration apply scan3d_set_registration's transform itself?
+bool fused7_folds_registration(const scan3d_config& c)
+{
+    Plan7 p;
+    return plan7(c, &p) && c.dirs == 2 && !mod7(c) && p.cw == 7 && (p.minb == 2 || p.minb == 3);
+}
+
 constexpr int regs7(int cw, int minb)
 {
     // per sub-partition: ceil(resident warps / 4) warps share 16384 registers
@@ -103,7 +110,8 @@ constexpr int regs7(int cw, int minb)
 // MOD: check_I_mod_criteria's modulation criterion (3/wrapped_phase.cpp:84-104, SCAN3D_FLAG_MODULATION_MASK): a pre-pass
 // has written one effective ROI plane per direction (a.roi = vertical, a.roi2 = horizontal); the mask recurrence runs
 // on each, so the two directions have their own masks (the reference's valid_map_vertical / _horizontal).
-template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false>
+// REG: register_point_clouds' turntable transform applied to every point where it is staged (scan3d_set_registration).
+template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false, bool REG = false>
 __global__ void __launch_bounds__((CW + 1) * 32) __maxnreg__(regs7(CW, MINB))
 k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal, const __grid_constant__ CUtensorMap stack_map)
 {
@@ -577,7 +585,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 else triangulate_point_fast(cal.Ac, cal.Ap, uc, vc, up, vp, Xd);
                 float px = __double2float_rn(Xd[0]), py = __double2float_rn(Xd[1]), pz = __double2float_rn(Xd[2]);   // 8/save_point_cloud.cpp:94-96
                 // optional: register_point_clouds' turntable transform on the float point (9/register_point_clouds.cpp:117-137)
-                if (a.reg_on) s3a::register_point(a.reg_R, a.reg_t[0], a.reg_t[1], a.reg_t[2], px, py, pz);
+                if (REG) s3a::register_point(a.reg_R, a.reg_t[0], a.reg_t[1], a.reg_t[2], px, py, pz);
                 cx[3 * rank + 0] = px;
                 cx[3 * rank + 1] = py;
                 cx[3 * rank + 2] = pz;
@@ -617,33 +625,60 @@ static bool stack_tensor_map(CUtensorMap* map, const uint8_t* stack, size_t plan
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false>
+template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false, bool REG = false>
 static cudaError_t launch7_t(const FusedArgs& a, const DeviceCalib& cal, int sm_count, const Plan7& p, cudaStream_t st)
 {
-    auto kern = k_fused7<N, DIRS, CW, MINB, EXACT, MOD>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-    if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (CW + 1) * 32, p.smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    if (getenv("SCAN3D_DEBUG")) {
-        cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, kern);
-        fprintf(stderr, "k_fused7<%d,%d,%d,%d,%d>: occupancy %d CTAs/SM, %d regs, %zu B dyn smem, %zu B static, local %zu B\n", N, DIRS, CW, MINB,
-                (int)EXACT, per_sm, fa.numRegs, p.smem, fa.sharedSizeBytes, fa.localSizeBytes);
+    auto kern = k_fused7<N, DIRS, CW, MINB, EXACT, MOD, REG>;
+    // per instantiation, once per process and shared-memory size: attributes and occupancy (a scan of a small frame
+    // is a few tens of microseconds: the host side of a launch must not cost as much)
+    static size_t smem_cached = 0;
+    static int per_sm_cached = 0;
+    cudaError_t e;
+    if (smem_cached != p.smem) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (CW + 1) * 32, p.smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        if (getenv("SCAN3D_DEBUG")) {
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, kern);
+            fprintf(stderr, "k_fused7<%d,%d,%d,%d,%d,%d>: occupancy %d CTAs/SM, %d regs, %zu B dyn smem, %zu B static, local %zu B\n", N, DIRS, CW, MINB,
+                    (int)EXACT, (int)MOD, per_sm, fa.numRegs, p.smem, fa.sharedSizeBytes, fa.localSizeBytes);
+        }
+        per_sm_cached = per_sm > MINB ? MINB : per_sm;
+        smem_cached = p.smem;
     }
-    if (per_sm > MINB) per_sm = MINB;
+    const int per_sm = per_sm_cached;
     const int grid = a.n_tiles < sm_count * per_sm ? a.n_tiles : sm_count * per_sm;   // all CTAs resident
     e = launch_worklist(a, 128 * CW, DIRS, st);
     if (e != cudaSuccess) return e;
     FusedArgs a2 = a;
-    alignas(64) CUtensorMap map;
-    memset(&map, 0, sizeof(map));
     const int NF = DIRS == 2 ? 2 * N + 2 * (a.M_v + a.M_h) : N + 2 * a.M_v;
-    a2.use_tmap = !getenv("SCAN3D_NO_TMAP") && stack_tensor_map(&map, a.stack, (size_t)a.W * a.H, NF, 128 * CW) ? 1 : 0;
-    kern<<<grid, (CW + 1) * 32, p.smem, st>>>(a2, cal, map);
+    // the tensor map depends on the stack's address only: the context keeps the last few
+    static const bool no_tmap = getenv("SCAN3D_NO_TMAP") != nullptr;
+    const CUtensorMap* map = nullptr;
+    alignas(64) CUtensorMap local;
+    TensorMapCache* cache = a.tmap_cache;
+    if (!no_tmap) {
+        if (cache)
+            for (int i = 0; i < TensorMapCache::SLOTS; i++)
+                if (cache->stack[i] == a.stack && cache->box[i] == 128 * CW) map = &cache->map[i];
+        if (!map) {
+            CUtensorMap* dst = &local;
+            int slot = -1;
+            if (cache) { slot = cache->next++ % TensorMapCache::SLOTS; cache->stack[slot] = nullptr; dst = &cache->map[slot]; }
+            if (stack_tensor_map(dst, a.stack, (size_t)a.W * a.H, NF, 128 * CW)) {
+                map = dst;
+                if (cache) { cache->stack[slot] = a.stack; cache->box[slot] = 128 * CW; }
+            }
+        }
+    }
+    if (!map) { memset(&local, 0, sizeof(local)); map = &local; a2.use_tmap = 0; }
+    else a2.use_tmap = 1;
+    kern<<<grid, (CW + 1) * 32, p.smem, st>>>(a2, cal, *map);
     return cudaGetLastError();
 }
 
@@ -655,6 +690,13 @@ static cudaError_t launch7_nd(const FusedArgs& a, const DeviceCalib& cal, int sm
     if (p.cw == CWV && p.minb == MB) {                                                            \
         if (exact || DIRS == 1) return launch7_t<N, DIRS, CWV, MB, true>(a, cal, sm_count, p, st); \
         return launch7_t<N, DIRS, CWV, MB, (DIRS == 1)>(a, cal, sm_count, p, st);                  \
+    }
+    // the variant that folds the turntable transform into the point store exists for the two default shapes
+    if (DIRS == 2 && a.reg_on && p.cw == 7) {
+        if (p.minb == 3) return exact ? launch7_t<N, 2, 7, 3, true, false, true>(a, cal, sm_count, p, st)
+                                      : launch7_t<N, 2, 7, 3, false, false, true>(a, cal, sm_count, p, st);
+        if (p.minb == 2) return exact ? launch7_t<N, 2, 7, 2, true, false, true>(a, cal, sm_count, p, st)
+                                      : launch7_t<N, 2, 7, 2, false, false, true>(a, cal, sm_count, p, st);
     }
     S3D_CASE7(7, 2) S3D_CASE7(7, 3) S3D_CASE7(9, 2) S3D_CASE7(4, 4) S3D_CASE7(6, 2) S3D_CASE7(5, 4)
 #undef S3D_CASE7

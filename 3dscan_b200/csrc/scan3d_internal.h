@@ -12,13 +12,15 @@
 #define S3D_PLANE_MASK_H 10   // internal: valid_map_horizontal when the stage API is used
 
 namespace s3d {
-// k_fused8: tensor maps of the last few capture stacks (a map depends on the stack's address only)
-struct Fused8Cache {
+// tensor maps of the last few capture stacks (a map depends on the stack's address and the tile size only)
+struct TensorMapCache {
     static constexpr int SLOTS = 8;
     const uint8_t* stack[SLOTS] = {};
+    int box[SLOTS] = {};
     alignas(64) CUtensorMap map[SLOTS];
     int next = 0;
 };
+typedef TensorMapCache Fused8Cache;
 }  // namespace s3d
 
 struct scan3d_ctx {
@@ -157,6 +159,7 @@ struct FusedArgs {
     float* stage_pts;             // v8: per-warp rings of staging slots for triangulated points (L2 resident)
     uint32_t* stage_vb;           // v8: ... and for the ballots of their valid bits (pixel indices / colours)
     int use_tmap;                 // v7: tile loads are one 2-D tensor copy (set by the launcher)
+    TensorMapCache* tmap_cache;   // host pointer (the launcher's cache of tensor maps; unused on the device)
     unsigned long long* trace;    // optional timeline buffer (SCAN3D_TRACE), else null
     const double2* cam_lut; const double2* proj_lut;
     const double* atan_tab;
@@ -169,6 +172,7 @@ int fused_num_tiles(const scan3d_config& c);
 
 // the single-pass kernel (scan3d_fused_kernel7.cu)
 bool fused7_supported(const scan3d_config& c);
+bool fused7_folds_registration(const scan3d_config& c);
 cudaError_t launch_fused7(const scan3d_config& c, const FusedArgs& a, const DeviceCalib& cal,
                           int sm_count, cudaStream_t st);
 

@@ -16,7 +16,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "v8w5": "-DS3D_K8_WARPS=5 -DS3D_K8_MINB=4 -DS3D_VAR_COLD_OUTLINE=1",
     "v8cold": "-DS3D_VAR_COLD_OUTLINE=1",
-    "noskip": "-DS3D_VAR_WARP_SKIP=0",
     "cold": "-DS3D_VAR_COLD_OUTLINE=1",
     "rowsel": "-DS3D_VAR_ROWSEL_RCP=1",
     "rot": "-DS3D_VAR_TERM_ROTATE=1",
