@@ -474,21 +474,24 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 int r_cv[2], r_ch[2];
                 int2 r_cp[2];
                 uint32_t vb = 0;
+                // the pair's term registers, Gray accumulators and mask bits, selected once by h
+                const TermsPair Pv = terms_pair(Tv, h), Ph = terms_pair(Th, h);
+                const uint32_t gvA_h = gvA >> (16 * h), gvB_h = gvB >> (16 * h), ghA_h = ghA >> (16 * h), ghB_h = ghB >> (16 * h);
+                const uint32_t mb_v = mbits >> (2 * h), mb_h = mbits_h >> (2 * h);
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
-                    const int j = 2 * h + u;
-                    const int x = xt + j;
-                    const bool mv = (mbits >> j) & 1u, mh = (mbits_h >> j) & 1u;
+                    const int x = xt + 2 * h + u;
+                    const bool mv = (mb_v >> u) & 1u, mh = (mb_h >> u) & 1u;
                     const bool m = mv && mh;                                             // merge_valid_maps, 5/compute_correspondance.cpp:60-77
-                    const int cv = code_of(gvA, gvB, j, a.M_v);
-                    const float wv = add_pi(phase_of<N>(Tv, j, tab));                    // 4/phase_unwrap.cpp:290
+                    const int cv = code_of_pair(gvA_h, gvB_h, u, a.M_v);
+                    const float wv = add_pi(phase_of_pair<N>(Pv, u, tab));               // 4/phase_unwrap.cpp:290
                     float unwv = (x == 0 || x == W - 1) ? 0.0f : unwrap_abs(wv, cv, fastdiv);  // :285, :291
                     unwv = mv ? unwv : 0.0f;
                     bool v = mv;
                     r_cv[u] = mv ? cv : -1;
                     if (DIRS == 2) {
-                        const int ch = code_of(ghA, ghB, j, a.M_h);
-                        const float wh = add_pi(phase_of<N>(Th, j, tab));
+                        const int ch = code_of_pair(ghA_h, ghB_h, u, a.M_h);
+                        const float wh = add_pi(phase_of_pair<N>(Ph, u, tab));
                         float unwh = (y == 0 || y == a.H_total - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);  // :304, :309
                         unwh = mh ? unwh : 0.0f;
                         int px, py;                                                       // 5/compute_correspondance.cpp:648-675

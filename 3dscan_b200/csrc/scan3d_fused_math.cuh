@@ -98,11 +98,47 @@ __device__ __forceinline__ int code_of(uint32_t binA, uint32_t binB, int j, int 
 
 // biased 16-bit lane -> exact double without the conversion pipe: the lane value u (< 2^16) is
 // dropped into the mantissa of 2^52 and (2^52 + bias) is subtracted
+__device__ __forceinline__ double lane_f64(uint32_t u, int bias)
+{
+    return __hiloint2double(0x43300000, (int)u) - (bias == 512 ? K_2P52_512 : K_2P52_1024);
+}
 __device__ __forceinline__ double term_f64(const Terms& T, int k, int j, int bias)
 {
     const uint32_t r = (j & 2) ? T.t[k][1] : T.t[k][0];
-    const uint32_t u = (j & 1) ? (r >> 16) : (r & 0xffffu);
-    return __hiloint2double(0x43300000, (int)u) - (4503599627370496.0 + (double)bias);
+    return lane_f64((j & 1) ? (r >> 16) : (r & 0xffffu), bias);
+}
+
+// The pair of pixels (2h, 2h + 1) of a thread shares its term registers: selecting them once per pair (by h, which
+// is a run-time value in the rolled pass loop) leaves only compile-time lane extractions per pixel.
+struct TermsPair {
+    uint32_t r[4];      // T.t[k][h]
+};
+__device__ __forceinline__ TermsPair terms_pair(const Terms& T, int h)
+{
+    TermsPair P;
+#pragma unroll
+    for (int k = 0; k < 4; k++) P.r[k] = h ? T.t[k][1] : T.t[k][0];
+    return P;
+}
+
+// wrapped phase of pixel u (0 / 1, compile time) of a pair
+template <int N>
+__device__ __forceinline__ float phase_of_pair(const TermsPair& P, int u, const double* tab)
+{
+    auto lane = [&](int k) { return u ? (P.r[k] >> 16) : (P.r[k] & 0xffffu); };
+    if (N == 8) {
+        const double a1 = lane_f64(lane(0), 512), b1 = lane_f64(lane(1), 1024);
+        const double a2 = lane_f64(lane(2), 512), b2 = lane_f64(lane(3), 1024);
+        const double d1 = dadd(a1, dmul(b1, K_SQRT_HALF));
+        const double d2 = dadd(a2, dmul(b2, K_SQRT_HALF));
+        return atan2_to_float(d1, d2, 0.0f, 0.0f, tab);
+    } else {
+        const int t1 = (int)lane(0) - (N == 5 ? 1024 : 512);
+        const int t2 = (int)lane(1) - (N == 4 ? 512 : 1024);
+        if (N == 5) return atan2f_fdlibm((float)t1, (float)t2);   // 3/wrapped_phase.cpp:220 (float atan2f)
+        // exact int -> double without the conversion pipe (|t| < 2^11)
+        return atan2_to_float(lane_f64(lane(0), N == 5 ? 1024 : 512), lane_f64(lane(1), N == 4 ? 512 : 1024), 0.0f, 0.0f, tab);
+    }
 }
 
 template <int N>
@@ -114,14 +150,20 @@ __device__ __forceinline__ float phase_of(const Terms& T, int j, const double* t
         const double r = 0.70710678118654752440;
         const double d1 = dadd(a1, dmul(b1, r));
         const double d2 = dadd(a2, dmul(b2, r));
-        // float approximations only pick the atan table row
-        return atan2_to_float(d1, d2, __double2float_rz(d1), __double2float_rz(d2), tab);
+        return atan2_to_float(d1, d2, 0.0f, 0.0f, tab);
     } else {
         const int t1 = term_of(T, 0, j, N == 5 ? 1024 : 512);
         const int t2 = term_of(T, 1, j, N == 4 ? 512 : 1024);
         if (N == 5) return atan2f_fdlibm((float)t1, (float)t2);   // 3/wrapped_phase.cpp:220 (float atan2f)
-        return atan2_to_float((double)t1, (double)t2, (float)t1, (float)t2, tab);
+        return atan2_to_float((double)t1, (double)t2, 0.0f, 0.0f, tab);
     }
+}
+
+// fringe order of pixel u (0 / 1, compile time) of a pair whose accumulators have been shifted down by 16 * h
+__device__ __forceinline__ int code_of_pair(uint32_t binA_h, uint32_t binB_h, int u, int M)
+{
+    const uint32_t a = (binA_h >> (8 * u)) & 0xffu, b = (binB_h >> (8 * u)) & 0xffu;
+    return (int)(((a << 8) | b) >> (16 - M));
 }
 
 __device__ __forceinline__ int sat32(long long v)

@@ -24,6 +24,25 @@ double s3d_host_rcp_seed(double x);
 
 namespace s3d {
 
+// Double constants of the hot loops live in the constant bank (the FP64 pipe takes a constant-bank operand directly;
+// as literals each one costs two moves per use at 80 registers per thread).  Host builds see plain constants.
+#if defined(__CUDACC__)
+#define S3D_KCONST static __constant__ double
+#else
+#define S3D_KCONST static const double
+#endif
+S3D_KCONST K_ATAN_P9 = 1.0 / 9.0;
+S3D_KCONST K_ATAN_P7 = -1.0 / 7.0;
+S3D_KCONST K_ATAN_P5 = 1.0 / 5.0;
+S3D_KCONST K_ATAN_P3 = -1.0 / 3.0;
+S3D_KCONST K_SQRT_HALF = 0.70710678118654752440;
+S3D_KCONST K_2P52_512 = 4503599627370496.0 + 512.0;
+S3D_KCONST K_2P52_1024 = 4503599627370496.0 + 1024.0;
+S3D_KCONST K_PI_REF = 22.0 / 7.0;
+S3D_KCONST K_TWO_PI_REF = 2.0 * 22.0 / 7.0;
+S3D_KCONST K_RCP_TWO_PI_REF = 1.0 / (2.0 * 22.0 / 7.0);
+S3D_KCONST K_RCP_7 = 1.0 / 7.0;
+
 // "Pi" as the reference's macro expands inside each expression.
 #define S3D_PI_REF (22.0 / 7.0)              // x += Pi            -> x + 22.0/7.0
 #define S3D_TWO_PI_REF (2.0 * 22.0 / 7.0)    // (2.0*Pi)           -> (2.0*22.0)/7.0
@@ -112,19 +131,22 @@ __device__ __forceinline__ float atan2_to_float(double y, double x, float yf, fl
     const bool swap = ay > ax;
     const bool xneg = x < 0.0;
     const double mx = swap ? ay : ax, mn = swap ? ax : ay;
-    const float axf = fabsf(xf), ayf = fabsf(yf);
-    // 0/0 -> NaN -> cvt.rni gives 0: row 0, and the result is forced to 0 below
-    int i = __float2int_rn(__fdividef(fminf(axf, ayf), fmaxf(axf, ayf)) * 32.0f);
-    i = min(max(i, 0), 32);
-    // c = i/32 exactly: (2^47 + i/32) - 2^47 with the integer dropped into the mantissa
-    const double c = __hiloint2double(0x42e00000, i) - 140737488355328.0;
+    (void)yf; (void)xf;
+    // Table row i = round(32 * mn / mx) and c = i / 32, both out of ONE double: 2^47 + q has an ulp of exactly 1/32,
+    // so adding q = mn * (reciprocal seed of mx) to 2^47 rounds it to a multiple of 1/32, leaves i in the low word of
+    // the sum and c after subtracting 2^47 again (a 20-bit seed is plenty: the row only has to be near, the degree-9
+    // polynomial has 2^-60 head-room).  mx == 0: seed = inf, 0 * inf = NaN, whose low word is 0 -> row 0, and the
+    // result is forced to 0 below.
+    const double s47 = fma(mn, rcp_seed(mx), 140737488355328.0);
+    const int i = __double2loint(s47) & 63;
+    const double c = s47 - 140737488355328.0;
     const double num = fma(-c, mx, mn);
     const double den = fma(c, mn, mx);
     const double t = fast_div(num, den);
     const double s = t * t;
-    double p = fma(s, 1.0 / 9.0, -1.0 / 7.0);
-    p = fma(s, p, 1.0 / 5.0);
-    p = fma(s, p, -1.0 / 3.0);
+    double p = fma(s, K_ATAN_P9, K_ATAN_P7);
+    p = fma(s, p, K_ATAN_P5);
+    p = fma(s, p, K_ATAN_P3);
     p = fma(t * s, p, t);
     double res = tab[i] + (tab[33 + i] + p);
     // s*res: flip the sign when exactly one of (swap, xneg) holds
@@ -268,13 +290,13 @@ __device__ __forceinline__ double div_const(double a, double b, double rcp_b, bo
 // 4/phase_unwrap.cpp:290 :  wrapped += Pi          (float <- double sum)
 __device__ __forceinline__ float add_pi(float wrapped)
 {
-    return __double2float_rn(dadd((double)wrapped, S3D_PI_REF));
+    return __double2float_rn(dadd((double)wrapped, K_PI_REF));
 }
 // 4/phase_unwrap.cpp:291 :  unwrapped = wrapped + code*2.0*Pi   == w + ((code*2.0)*22.0)/7.0
 __device__ __forceinline__ float unwrap_abs(float wrapped_plus_pi, int code, bool fast = false)
 {
     // (code*2.0)*22.0 is an exact integer, so only the division rounds
-    const double k = div_const((double)(code * 44), 7.0, 1.0 / 7.0, fast);   // code*44 < 2^21: exact
+    const double k = div_const((double)(code * 44), 7.0, K_RCP_7, fast);   // code*44 < 2^21: exact
     return __double2float_rn(dadd((double)wrapped_plus_pi, k));
 }
 // 5/compute_correspondance.cpp:648 : lrint(fw * (Phi / (2.0*Pi))), round-half-even; FE_INVALID
@@ -289,7 +311,7 @@ __device__ __forceinline__ bool correspond(float phi_abs, int fw, long long* out
 // clamp of the 64-bit lrint to int, NaN converts to 0 and fails the |v| < 2^63 test (FE_INVALID).
 __device__ __forceinline__ bool correspond32(float phi_abs, int fw, int* out)
 {
-    const double v = dmul((double)fw, div_const((double)phi_abs, S3D_TWO_PI_REF, 1.0 / (S3D_TWO_PI_REF), true));
+    const double v = dmul((double)fw, div_const((double)phi_abs, K_TWO_PI_REF, K_RCP_TWO_PI_REF, true));
     *out = __double2int_rn(v);
     return fabs(v) < 9223372036854775808.0;
 }

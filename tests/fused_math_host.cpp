@@ -71,22 +71,27 @@ void run(const HostArgs& a, const DeviceCalib& cal, const uint8_t* stack, const 
             }
         }
         for (int j = 0; j < 4; j++) {
+            // the kernel's pass structure: pairs (2h, 2h + 1), registers selected once per pair by h
+            const int h = j >> 1, u = j & 1;
+            const TermsPair Pv = terms_pair(Tv, h), Ph = terms_pair(Th, h);
+            const uint32_t gvA_h = gvA >> (16 * h), gvB_h = gvB >> (16 * h), ghA_h = ghA >> (16 * h), ghB_h = ghB >> (16 * h);
             const int x = xt + j;
             const size_t p = g + j;
             const bool m = (mbits >> j) & 1u;
-            const int cv = code_of(gvA, gvB, j, a.M_v);
+            const int cv = code_of_pair(gvA_h, gvB_h, u, a.M_v);
+            if (cv != code_of(gvA, gvB, j, a.M_v)) abort();
             float unwv = 0.0f, unwh = 0.0f;
             if (m) {                                   // the kernel evaluates unconditionally and selects; same values
-                const float wv = add_pi(phase_of<N>(Tv, j, tab));
+                const float wv = add_pi(phase_of_pair<N>(Pv, u, tab));
                 unwv = (x == 0 || x == W - 1) ? 0.0f : unwrap_abs(wv, cv, fastdiv);
             }
             bool v = m;
             unw_v[p] = unwv;
             code_v[p] = (int16_t)(m ? cv : -1);
             if (a.dirs == 2) {
-                const int ch = code_of(ghA, ghB, j, a.M_h);
+                const int ch = code_of_pair(ghA_h, ghB_h, u, a.M_h);
                 if (m) {
-                    const float wh = add_pi(phase_of<N>(Th, j, tab));
+                    const float wh = add_pi(phase_of_pair<N>(Ph, u, tab));
                     unwh = (y == 0 || y == H - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);
                 }
                 int px = 0, py = 0;
