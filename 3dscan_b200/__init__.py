@@ -147,6 +147,7 @@ def cuda_lib():
     L.scan3d_roi_fill_dev.argtypes = [vp, vp, vp, vp]
     L.scan3d_register_points.argtypes = [vp, vp, vp, i64, f32, f32, f32, f32]
     L.scan3d_set_registration.argtypes = [vp, i32, f32, f32, f32, f32]
+    L.scan3d_set_cta_limit.argtypes = [vp, i32]
     L.scan3d_reconstruct_raw.argtypes = [vp, vp, vp, C.POINTER(i64)]
     L.scan3d_reconstruct_raw_dev.argtypes = [vp, vp, vp]
     L.scan3d_register_points_dev.argtypes = [vp, vp, vp, i64, f32, f32, f32, f32]
@@ -371,6 +372,10 @@ class Scan3D:
         n = C.c_int64()
         self._ck(self.L.scan3d_reconstruct(self.h, _ptr(stack), _ptr(roi), C.byref(n)))
         return n.value
+
+    def set_cta_limit(self, ctas_per_sm):
+        """several contexts on several streams of one GPU: this context's kernel takes at most that many CTA slots per SM"""
+        self._ck(self.L.scan3d_set_cta_limit(self.h, int(ctas_per_sm)))
 
     def set_registration(self, enable, theta_deg=0.0, tx=0.0, ty=0.0, tz=0.0):
         """register_point_clouds' transform folded into the point store of the following reconstructions."""

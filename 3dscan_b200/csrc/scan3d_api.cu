@@ -555,6 +555,7 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
         a.epoch = ++ctx->epoch;
     }
     a.tmap_cache = &ctx->tmaps;
+    a.ctas_per_sm = ctx->cta_limit;
     const bool fold_reg = ctx->reg_on && fused7_folds_registration(c);
     a.reg_on = fold_reg ? 1 : 0;
     memcpy(a.reg_R, ctx->reg_R, sizeof(a.reg_R));
@@ -616,6 +617,13 @@ int scan3d_reconstruct(scan3d_ctx* ctx, const uint8_t* stack_host, const uint8_t
         *count_out = 0;
     }
     return scan3d_sync(ctx);
+}
+
+int scan3d_set_cta_limit(scan3d_ctx* ctx, int ctas_per_sm)
+{
+    if (!ctx || ctas_per_sm < 0) return SCAN3D_ERR_ARG;
+    ctx->cta_limit = ctas_per_sm;
+    return SCAN3D_OK;
 }
 
 int scan3d_set_registration(scan3d_ctx* ctx, int enable, float theta_deg, float tx, float ty, float tz)

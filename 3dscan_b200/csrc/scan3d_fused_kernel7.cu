@@ -654,7 +654,10 @@ static cudaError_t launch7_t(const FusedArgs& a, const DeviceCalib& cal, int sm_
         per_sm_cached = per_sm > MINB ? MINB : per_sm;
         smem_cached = p.smem;
     }
-    const int per_sm = per_sm_cached;
+    // a.ctas_per_sm > 0 (scan3d_set_cta_limit): this context's launches take only that many of the SM's CTA slots, so
+    // that the persistent kernels of several contexts (streams) are resident side by side and one scan's pipeline
+    // fill and drain overlap the other scans' steady state
+    const int per_sm = a.ctas_per_sm > 0 && a.ctas_per_sm < per_sm_cached ? a.ctas_per_sm : per_sm_cached;
     const int grid = a.n_tiles < sm_count * per_sm ? a.n_tiles : sm_count * per_sm;   // all CTAs resident
     e = launch_worklist(a, 128 * CW, DIRS, st);
     if (e != cudaSuccess) return e;

@@ -82,6 +82,8 @@ struct scan3d_ctx {
     uint8_t* d_roi = nullptr;
     uint8_t* d_undist = nullptr;   // scan3d_reconstruct_raw: the undistorted stack
 
+    int cta_limit = 0;             // scan3d_set_cta_limit
+
     // scan3d_set_registration
     bool reg_on = false;
     float reg_R[16] = {}, reg_t[3] = {};
@@ -159,6 +161,7 @@ struct FusedArgs {
     float* stage_pts;             // v8: per-warp rings of staging slots for triangulated points (L2 resident)
     uint32_t* stage_vb;           // v8: ... and for the ballots of their valid bits (pixel indices / colours)
     int use_tmap;                 // v7: tile loads are one 2-D tensor copy (set by the launcher)
+    int ctas_per_sm;              // 0 = all the kernel can have; else the launch takes at most this many CTA slots per SM
     TensorMapCache* tmap_cache;   // host pointer (the launcher's cache of tensor maps; unused on the device)
     unsigned long long* trace;    // optional timeline buffer (SCAN3D_TRACE), else null
     const double2* cam_lut; const double2* proj_lut;

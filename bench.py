@@ -288,7 +288,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rowshard", action="store_true", help="N > 1: skip the row-sharded 50 MP frame that rides along")
-    ap.add_argument("--contexts", type=int, default=3, help="contexts (each on its own stream) the batch alternates over")
+    ap.add_argument("--contexts", type=int, default=4, help="contexts (each on its own stream) the batch alternates over")
+    ap.add_argument("--cta-limit", type=int, default=1, help="CTA slots per SM each context's kernel may take (0 = all)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="row-shard workload, N>1: how the points reach rank 0")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -312,7 +313,7 @@ def main():
     cfg = s3.make_config(W, H, PW, PH, N, Mv, Mh, fwv, fwh, dirs, flags=flags)
     config = {"workload": args.workload, "frame": [W, H], "projector": [PW, PH], "phase_steps": N,
               "gray_bits": [Mv, Mh][:dirs], "directions": dirs, "frames_per_scan": s3.stack_planes(cfg),
-              "scans_per_gpu_per_step": args.batch, "resident_ring": args.ring, "contexts_per_gpu": args.contexts,
+              "scans_per_gpu_per_step": args.batch, "resident_ring": args.ring, "contexts_per_gpu": args.contexts, "cta_slots_per_sm_per_context": args.cta_limit or "all",
               "sharding": "frame-parallel scans, no collective" if world > 1 else "single GPU",
               "l2_policy": "inputs larger than L2 (ring of distinct stacks, %.2f GB per GPU)"
                            % (args.ring * s3.stack_planes(cfg) * npix / 1e9),
@@ -396,10 +397,16 @@ def main():
         rois.append(torch.roll(base_roi, shifts=shift, dims=1) if shift else base_roi)
     torch.cuda.synchronize()
 
-    # --contexts 2: the scans of a batch alternate over two contexts on two streams (still one GPU, still
-    # frame-parallel): the tail of one scan's persistent kernel overlaps the start of the next one's
+    # --contexts C --cta-limit L: the scans of a batch alternate over C contexts on C streams (still one GPU, still
+    # frame-parallel), each context's persistent kernel taking L of the SM's 3 CTA slots: the kernels of 3 scans are
+    # resident side by side and the fourth waits in the queue, so one scan's pipeline fill and drain (and its two
+    # work-list launches) overlap the steady state of the others
     side_streams = [torch.cuda.Stream() for _ in range(args.contexts - 1)]
     ctxs = [ctx] + [s3.Scan3D(cfg, local_rank, cal, stream=st.cuda_stream) for st in side_streams]
+
+    if args.cta_limit:
+        for c in ctxs:
+            c.set_cta_limit(args.cta_limit)
 
     def step():
         for b in range(args.batch):

@@ -272,6 +272,12 @@ int scan3d_set_registration(scan3d_ctx *ctx, int enable, float theta_deg, float 
 int scan3d_reconstruct_raw(scan3d_ctx *ctx, const uint8_t *raw_stack_host, const uint8_t *roi_host, int64_t *count_out);
 int scan3d_reconstruct_raw_dev(scan3d_ctx *ctx, const uint8_t *raw_stack_dev, const uint8_t *roi_dev);
 
+/* Several contexts on several streams of ONE GPU (a batch of scans, BASELINE configs[3]): limit the persistent kernel
+ * of this context to ctas_per_sm of the SM's CTA slots (it can hold 2-4, depending on the frame stack), so that the
+ * kernels of the other contexts are resident beside it and the pipeline fill and drain of one scan overlap the
+ * steady state of the others.  0 = no limit (default: one context then uses the whole GPU). */
+int scan3d_set_cta_limit(scan3d_ctx *ctx, int ctas_per_sm);
+
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t scan3d_launch_count(const scan3d_ctx *ctx);
 
