@@ -464,6 +464,8 @@ def main():
         h2d = (nf + 1) * npix
         lanes = args.e2e_scans if args.e2e_scans <= 4 else 2
         e_ctxs = [ctx] + [s3.Scan3D(cfg, local_rank, cal, stream=torch.cuda.Stream().cuda_stream) for _ in range(lanes - 1)]
+        for c in e_ctxs:
+            c.set_cta_limit(args.cta_limit)
         pts_hosts = [torch.empty((npix, 3), dtype=torch.float32, pin_memory=True) if dirs == 2 else None for _ in e_ctxs]
         out_hosts = [torch.empty((H, W), dtype=torch.float32, pin_memory=True) for _ in e_ctxs]
 
@@ -536,6 +538,12 @@ def main():
                 cpu["single_thread"] = {"value": npix / sec1 / 1e6, "unit": "Mpix/s", "cores": 1, "seconds_per_scan": sec1}
                 cpu["single_thread_value"] = npix / sec1 / 1e6      # (flat copies: nested objects get dropped by some parsers)
                 cpu["single_thread_seconds_per_scan"] = sec1
+                # BASELINE.md section 3 "ref-faithful": one thread AND the reference's own [col][row] plane layout
+                # (row-outer loops striding every plane by H elements, 3/wrapped_phase.cpp:164-183)
+                from gpu_common import run_oracle
+                rr = run_oracle(cfg, ocal, host_stack.numpy(), host_roi.numpy(), colrow=True)
+                cpu["reference_layout_single_thread_value"] = npix / rr.seconds / 1e6
+                cpu["reference_layout_single_thread_seconds_per_scan"] = rr.seconds
             except Exception as e:   # the all-core figure above is the contract; this one is extra
                 cpu["single_thread"] = {"error": str(e)}
 

@@ -233,8 +233,10 @@ class Result:
 
 
 def reconstruct(cfg, cal, fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi, threads=1,
-                want_xyz=True, modulation=False, strict=False):
-    """cfg: dict with W,H,PW,PH,N,M_v,M_h,fw_v,fw_h,dirs.  Returns a Result of numpy planes."""
+                want_xyz=True, modulation=False, strict=False, colrow=False):
+    """cfg: dict with W,H,PW,PH,N,M_v,M_h,fw_v,fw_h,dirs.  Returns a Result of numpy planes.
+    colrow=True: the reference-faithful leg (o3d_reconstruct_colrow: the reference's [col][row] plane layout, one
+    thread); r.seconds is the time of the C call alone, the planes come back transposed to [H][W] for comparison."""
     c = Config(**{k: int(cfg[k]) for k in
                   ("W", "H", "PW", "PH", "N", "M_v", "M_h", "fw_v", "fw_h", "dirs")})
     H, W = c.H, c.W
@@ -258,8 +260,21 @@ def reconstruct(cfg, cal, fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi,
                 _p(r.cpmap), _p(r.xyz), _p(r.pts), _p(r.pix), 0)
     u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
     keep = [u8(x) for x in (fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi)]
-    lib().o3d_reconstruct_ex(C.byref(c), C.byref(cal), *[_p(k) for k in keep], int(bool(modulation)) | (2 if strict else 0),
-                             C.byref(o), int(threads))
+    import time as _time
+    flags = int(bool(modulation)) | (2 if strict else 0)
+    t0 = _time.perf_counter()
+    if colrow:
+        lib().o3d_reconstruct_colrow(C.byref(c), C.byref(cal), *[_p(k) for k in keep], flags, C.byref(o))
+    else:
+        lib().o3d_reconstruct_ex(C.byref(c), C.byref(cal), *[_p(k) for k in keep], flags, C.byref(o), int(threads))
+    r.seconds = _time.perf_counter() - t0
+    if colrow:      # [W][H] -> [H][W]
+        for name in ("wrapped_v", "unwrapped_v", "code_v", "valid_v", "wrapped_h", "unwrapped_h", "code_h", "valid_h", "valid"):
+            a = getattr(r, name)
+            if a is not None:
+                setattr(r, name, np.ascontiguousarray(a.reshape(W, H).T))
+        if two:
+            r.xyz = np.ascontiguousarray(r.xyz.reshape(W, H, 3).transpose(1, 0, 2))
     r.count = int(o.count)
     if two:
         r.pts = r.pts[:r.count]

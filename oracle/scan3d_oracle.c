@@ -22,6 +22,16 @@
 
 #define PAR_FOR _Pragma("omp parallel for schedule(static) num_threads(nth) if (nth > 1)")
 
+/* Layout of the intermediate planes (valid maps, wrapped / unwrapped phases, fringe orders, intersection_points):
+ * 0 = row-major [row][col] (the default, what every test and the product compare in); 1 = the reference's own
+ * arrays, int (*)[H] etc. indexed [col][row] from row-outer loops (common_variables.h:12-21, e.g.
+ * 3/wrapped_phase.cpp:164-183): every plane access then strides by H elements.  Same values either way; the switch
+ * exists for the reference-faithful single-thread timing of BASELINE.md section 3 (o3d_reconstruct_colrow).
+ * Input images, c_p_map ([W*H][2], row-major in the reference too, 5/...:648) and the look-up tables keep their
+ * layout.  Not thread-safe across concurrent calls with different layouts (the timing leg is single-threaded). */
+static int g_colrow = 0;
+#define PL(row, col) (g_colrow ? (long)(col) * H + (row) : (long)(row) * W + (col))
+
 static int clamp_threads(int threads)
 {
 #ifdef _OPENMP
@@ -51,7 +61,8 @@ int o3d_max_threads(void)
  * The modulation test :84-104 is commented out in the reference and is not applied. */
 void o3d_check_roi(const uint8_t *roi, int W, int H, int32_t *valid)
 {
-    for (long i = 0; i < (long)W * H; i++) valid[i] = roi[i] != 0 ? 1 : 0;
+    for (int i = 0; i < H; i++)
+        for (int j = 0; j < W; j++) valid[PL(i, j)] = roi[(long)i * W + j] != 0 ? 1 : 0;
 }
 
 /* The same function exactly as committed (3/wrapped_phase.cpp:78-127): the map is cleared, then filled from
@@ -61,10 +72,12 @@ void o3d_check_roi(const uint8_t *roi, int W, int H, int32_t *valid)
  * form backs SCAN3D_FLAG_STRICT_REFERENCE. */
 void o3d_check_roi_strict(const uint8_t *roi, int N, int W, int H, int32_t *valid)
 {
-    for (long i = 0; i < (long)W * H; i++) valid[i] = 0;
+    for (int i = 0; i < H; i++)
+        for (int j = 0; j < W; j++) valid[PL(i, j)] = 0;
     if (N == 4 || N == 3)
-        for (long i = 0; i < (long)W * H; i++)
-            if (roi[i] == 1) valid[i] = 1;
+        for (int i = 0; i < H; i++)
+            for (int j = 0; j < W; j++)
+                if (roi[(long)i * W + j] == 1) valid[PL(i, j)] = 1;
 }
 
 /* Extension weights for N not in {3,4,5,8}: shifts delta_k = 2*pi*k/N (true pi), libm. */
@@ -77,15 +90,17 @@ void o3d_check_roi_strict(const uint8_t *roi, int N, int W, int H, int32_t *vali
 void o3d_check_I_mod_criteria(const uint8_t *fringe, const uint8_t *roi, int W, int H, int32_t *valid)
 {
     const size_t n = (size_t)W * H;
-    for (size_t i = 0; i < n; i++) {
-        const int i0 = fringe[i], i1 = fringe[n + i], i2 = fringe[2 * n + i];
-        const double d = i0 - i2;
-        const double e = 2.0 * i1 - i0 - i2;
-        const float t1 = sqrtf((float)(3.0 * (d * d) + e * e));
-        const float t2 = (float)(i0 + i1 + i2);
-        const float t3 = t1 / t2;
-        valid[i] = (t3 > 0.01 && roi[i] != 0) ? 1 : 0;
-    }
+    for (int row = 0; row < H; row++)
+        for (int col = 0; col < W; col++) {
+            const size_t i = (size_t)row * W + col;
+            const int i0 = fringe[i], i1 = fringe[n + i], i2 = fringe[2 * n + i];
+            const double d = i0 - i2;
+            const double e = 2.0 * i1 - i0 - i2;
+            const float t1 = sqrtf((float)(3.0 * (d * d) + e * e));
+            const float t2 = (float)(i0 + i1 + i2);
+            const float t3 = t1 / t2;
+            valid[PL(row, col)] = (t3 > 0.01 && roi[i] != 0) ? 1 : 0;
+        }
 }
 
 static void nstep_weights(int N, double *s, double *c)
@@ -109,26 +124,27 @@ void o3d_wrapped_phase(const uint8_t *fringe, int N, int W, int H, const int32_t
     PAR_FOR
     for (int row = 0; row < H; row++) {
         for (int col = 0; col < W; col++) {
-            const long p = (long)row * W + col;
-            if (valid[p] != 1) continue;
+            const long p = (long)row * W + col;     /* in the input images */
+            const long q = PL(row, col);            /* in the planes */
+            if (valid[q] != 1) continue;
             float t1, t2, t3;
             if (N == 3) { /* :171-179 */
                 t1 = (float)fringe[0 * plane + p] - (float)fringe[2 * plane + p];
                 t2 = 2.0 * ((float)fringe[1 * plane + p]) - (float)fringe[0 * plane + p] -
                      (float)fringe[2 * plane + p];
-                wrapped[p] = atan2(t1, t2); /* double atan2, stored as float */
-                t3 = 128.0f + 127.0f * (wrapped[p] / (Pi));
+                wrapped[q] = atan2(t1, t2); /* double atan2, stored as float */
+                t3 = 128.0f + 127.0f * (wrapped[q] / (Pi));
             } else if (N == 4) { /* :195-201 */
                 t1 = (float)fringe[3 * plane + p] - (float)fringe[1 * plane + p];
                 t2 = (float)fringe[0 * plane + p] - (float)fringe[2 * plane + p];
-                wrapped[p] = atan2(t1, t2);
-                t3 = 127.0f + 128.0f * (wrapped[p] / (Pi));
+                wrapped[q] = atan2(t1, t2);
+                t3 = 127.0f + 128.0f * (wrapped[q] / (Pi));
             } else if (N == 5) { /* :217-222 (Hariharan), float atan2f */
                 t1 = 2.0 * ((float)fringe[1 * plane + p] - (float)fringe[3 * plane + p]);
                 t2 = 2.0 * (float)fringe[2 * plane + p] - (float)fringe[0 * plane + p] -
                      (float)fringe[4 * plane + p];
-                wrapped[p] = atan2f(t1, t2);
-                t3 = 127.0 + 128.0 * (wrapped[p] / (Pi));
+                wrapped[q] = atan2f(t1, t2);
+                t3 = 127.0 + 128.0 * (wrapped[q] / (Pi));
             } else if (N == 8) {
                 /* EXTENSION (no reference counterpart): 8-step, shifts k*pi/4, same phase
                  * origin as the reference's 4-step (phi = theta - pi).  Integer parts are
@@ -140,8 +156,8 @@ void o3d_wrapped_phase(const uint8_t *fringe, int N, int W, int H, const int32_t
                 const double r = 0.70710678118654752440;
                 const double d1 = (double)(I6 - I2) + (double)(I5 + I7 - I1 - I3) * r;
                 const double d2 = (double)(I0 - I4) + (double)(I1 + I7 - I3 - I5) * r;
-                wrapped[p] = atan2(d1, d2);
-                t3 = 127.0f + 128.0f * (wrapped[p] / (Pi));
+                wrapped[q] = atan2(d1, d2);
+                t3 = 127.0f + 128.0f * (wrapped[q] / (Pi));
             } else {
                 /* EXTENSION: generic N-step, sequential double sums, k ascending. */
                 double S = 0.0, C = 0.0;
@@ -150,8 +166,8 @@ void o3d_wrapped_phase(const uint8_t *fringe, int N, int W, int H, const int32_t
                     S = S + I * ws[k];
                     C = C + I * wc[k];
                 }
-                wrapped[p] = atan2(0.0 - S, C); /* 0.0 - S: S == +0 must not become -0 */
-                t3 = 127.0f + 128.0f * (wrapped[p] / (Pi));
+                wrapped[q] = atan2(0.0 - S, C); /* 0.0 - S: S == +0 must not become -0 */
+                t3 = 127.0f + 128.0f * (wrapped[q] / (Pi));
             }
             if (dbg) dbg[p] = (unsigned char)(int)(t3);
         }
@@ -237,8 +253,8 @@ long o3d_atan2f_restated_mismatches(void)
 void o3d_mask_recurrence(int32_t *valid, int W, int H, uint8_t *dbg)
 {
     uint8_t *visited = (uint8_t *)calloc((size_t)W * H, 1);
-#define V(u, y) valid[(long)(y) * W + (u)]
-#define S(u, y) visited[(long)(y) * W + (u)]
+#define V(u, y) valid[PL(y, u)]
+#define S(u, y) visited[PL(y, u)]
     for (int y = 1; y < H - 1; y++)
         for (int u = 1; u < W - 1; u++) {
             if (((V(u - 1, y - 1) != 1) && !S(u - 1, y - 1)) ||
@@ -300,9 +316,9 @@ void o3d_decode_gray(const uint8_t *gray, const uint8_t *inv, int M, int W, int 
     PAR_FOR
     for (int row = 0; row < H; row++)
         for (int col = 0; col < W; col++) {
-            const long p = (long)row * W + col;
-            code[p] = -1; /* :141-143 */
-            if (valid[p] != 1) continue;
+            const long p = (long)row * W + col, q = PL(row, col);
+            code[q] = -1; /* :141-143 */
+            if (valid[q] != 1) continue;
             int c = 0, Bprev = 0;
             for (int i = 0; i < M; i++) {
                 /* :183 -- uchar - uchar is int arithmetic; tie (==0) decodes as 1 */
@@ -311,7 +327,7 @@ void o3d_decode_gray(const uint8_t *gray, const uint8_t *inv, int M, int W, int 
                 c += B * (1 << (M - 1 - i));               /* :193, bit 0 = MSB */
                 Bprev = B;
             }
-            code[p] = c; /* no range reject (:196-200 is a no-op) */
+            code[q] = c; /* no range reject (:196-200 is a no-op) */
         }
 }
 
@@ -325,7 +341,7 @@ void o3d_unwrap(int dir, float *wrapped, const int32_t *code, const int32_t *val
     PAR_FOR
     for (int row = r0; row < r1; row++)
         for (int col = c0; col < c1; col++) {
-            const long p = (long)row * W + col;
+            const long p = PL(row, col);
             if (valid[p] != 1) continue;
             wrapped[p] += Pi;                              /* :290 / :308 */
             unwrapped[p] = wrapped[p] + code[p] * 2.0 * Pi; /* :291 / :309 */
@@ -363,20 +379,21 @@ void o3d_compute_c_p_map(const float *unw_v, const float *unw_h, const int32_t *
     PAR_FOR
     for (int r = 0; r < H; r++)
         for (int c = 0; c < W; c++) {
-            const long p = (long)r * W + c;
-            valid[p] = (valid_v[p] == 1 && valid_h[p] == 1) ? 1 : 0; /* :60-77 */
-            if (valid[p] != 1) continue;
-            if (!lrint_checked(fw_v * (unw_v[p] / (2.0 * Pi)), &cpmap[2 * p + 0])) { /* :648 */
-                valid[p] = 0;
+            const long p = (long)r * W + c;         /* c_p_map row */
+            const long q = PL(r, c);                /* planes */
+            valid[q] = (valid_v[q] == 1 && valid_h[q] == 1) ? 1 : 0; /* :60-77 */
+            if (valid[q] != 1) continue;
+            if (!lrint_checked(fw_v * (unw_v[q] / (2.0 * Pi)), &cpmap[2 * p + 0])) { /* :648 */
+                valid[q] = 0;
                 continue;
             }
-            if (!lrint_checked(fw_h * (unw_h[p] / (2.0 * Pi)), &cpmap[2 * p + 1])) { /* :659 */
-                valid[p] = 0;
+            if (!lrint_checked(fw_h * (unw_h[q] / (2.0 * Pi)), &cpmap[2 * p + 1])) { /* :659 */
+                valid[q] = 0;
                 continue;
             }
             if (cpmap[2 * p] > (PW - 1) || cpmap[2 * p + 1] > (PH - 1) || cpmap[2 * p] < 0 ||
                 cpmap[2 * p + 1] < 0) /* :671-675 */
-                valid[p] = 0;
+                valid[q] = 0;
         }
 }
 
@@ -550,12 +567,12 @@ void o3d_triangulate(const double A_cam[12], const double A_proj[12], const doub
     PAR_FOR
     for (int i = 0; i < H; i++)
         for (int j = 0; j < W; j++) {
-            const long p = (long)i * W + j;
-            if (valid[p] != 1) continue;
+            const long p = (long)i * W + j, q = PL(i, j);
+            if (valid[q] != 1) continue;
             const int cx = (int)cpmap[2 * p], cy = (int)cpmap[2 * p + 1]; /* :1146-1147 */
-            const long q = (long)cy * PW + cx;
-            o3d_triangulate_point(A_cam, A_proj, cam_lut[p], cam_lut[n + p], proj_lut[q],
-                                  proj_lut[np + q], &xyz[3 * p]);
+            const long ql = (long)cy * PW + cx;
+            o3d_triangulate_point(A_cam, A_proj, cam_lut[p], cam_lut[n + p], proj_lut[ql],
+                                  proj_lut[np + ql], &xyz[3 * q]);
         }
 }
 
@@ -568,8 +585,8 @@ int64_t o3d_compact(const double *xyz, const int32_t *valid, const uint8_t *text
     int64_t y = 0;
     for (int i = 0; i < H; i++)
         for (int j = 0; j < W; j++) {
-            const long p = (long)i * W + j;
-            if (valid[p] != 1) continue;
+            const long p = (long)i * W + j, q = PL(i, j);
+            if (valid[q] != 1) continue;
             if (out_rgb) {
                 /* cvSplit(I1, blue, green, red): texture is BGR-interleaved */
                 out_rgb[3 * y + 0] = texture ? texture[3 * p + 2] : 0;
@@ -577,9 +594,9 @@ int64_t o3d_compact(const double *xyz, const int32_t *valid, const uint8_t *text
                 out_rgb[3 * y + 2] = texture ? texture[3 * p + 0] : 0;
             }
             if (out_xyz) {
-                out_xyz[3 * y + 0] = (float)xyz[3 * p + 0];
-                out_xyz[3 * y + 1] = (float)xyz[3 * p + 1];
-                out_xyz[3 * y + 2] = (float)xyz[3 * p + 2];
+                out_xyz[3 * y + 0] = (float)xyz[3 * q + 0];
+                out_xyz[3 * y + 1] = (float)xyz[3 * q + 1];
+                out_xyz[3 * y + 2] = (float)xyz[3 * q + 2];
             }
             if (out_pix) out_pix[y] = (uint32_t)p;
             y++;
@@ -647,4 +664,18 @@ void o3d_reconstruct_ex(const o3d_config *cfg, const o3d_calib *cal, const uint8
     out->count = o3d_compact(out->xyz, out->valid, NULL, W, H, out->pts, NULL, out->pix);
     free(cam_lut);
     free(proj_lut);
+}
+
+/* The reference's CPU pipeline as it lays its data out: every intermediate plane [col][row], row-outer loops, one
+ * thread ("ref-faithful").  Outputs come back in that layout too: valid_*, wrapped_*,
+ * unwrapped_*, code_*, valid are [W][H], xyz is [W][H][3]; cpmap, pts and pix as in o3d_reconstruct (row-major
+ * c_p_map, raster-ordered points).  tests/test_oracle_golden.py checks it against o3d_reconstruct plane by plane. */
+void o3d_reconstruct_colrow(const o3d_config *cfg, const o3d_calib *cal, const uint8_t *fringe_v,
+                            const uint8_t *gray_v, const uint8_t *inv_v, const uint8_t *fringe_h,
+                            const uint8_t *gray_h, const uint8_t *inv_h, const uint8_t *roi,
+                            int modulation, o3d_outputs *out)
+{
+    g_colrow = 1;
+    o3d_reconstruct_ex(cfg, cal, fringe_v, gray_v, inv_v, fringe_h, gray_h, inv_h, roi, modulation, out, 1);
+    g_colrow = 0;
 }

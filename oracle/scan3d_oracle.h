@@ -171,6 +171,12 @@ void o3d_reconstruct_ex(const o3d_config *cfg, const o3d_calib *cal, const uint8
                         const uint8_t *gray_v, const uint8_t *inv_v, const uint8_t *fringe_h,
                         const uint8_t *gray_h, const uint8_t *inv_h, const uint8_t *roi,
                         int modulation, o3d_outputs *out, int threads);
+/* the same pipeline with the reference's own plane layout ([col][row] planes from row-outer loops) on ONE thread: the
+ * reference-faithful CPU leg of BASELINE.md section 3.  Planes of `out` come back [W][H] ([W][H][3] for xyz). */
+void o3d_reconstruct_colrow(const o3d_config *cfg, const o3d_calib *cal, const uint8_t *fringe_v,
+                            const uint8_t *gray_v, const uint8_t *inv_v, const uint8_t *fringe_h,
+                            const uint8_t *gray_h, const uint8_t *inv_h, const uint8_t *roi,
+                            int modulation, o3d_outputs *out);
 
 /* ---- either side of the path (scan3d_oracle_f4.c) ---- */
 /* cvUndistort2 (2/project_pattern.cpp:220 ...): fixed-point map of cv::undistort, the bilinear

@@ -24,11 +24,11 @@ def cfg_dict(cfg):
     return {k: getattr(cfg, k) for k in ("W", "H", "PW", "PH", "N", "M_v", "M_h", "fw_v", "fw_h", "dirs")}
 
 
-def run_oracle(cfg, ocal, stack, roi, threads=0, modulation=False, strict=False):
+def run_oracle(cfg, ocal, stack, roi, threads=0, modulation=False, strict=False, colrow=False):
     d = s3.split_stack(cfg, stack)
     return o.reconstruct(cfg_dict(cfg), ocal, d["fringe_v"], d["gray_v"], d["inv_v"],
                          d.get("fringe_h"), d.get("gray_h"), d.get("inv_h"), roi, threads=threads,
-                         modulation=modulation, strict=strict)
+                         modulation=modulation, strict=strict, colrow=colrow)
 
 
 def compare(cfg, ref, ctx, fused=True, report=None):

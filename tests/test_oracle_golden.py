@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_ffi as o
-from helpers import GOLDEN, REF, have_reference, load_c1_crop, load_calib_c1, read_bmp8
+from helpers import GOLDEN, REF, have_reference, load_c1_crop, load_calib_c1, read_bmp8, scaled_calib
 
 
 def _stage34(fr, g, gi, gw, direction):
@@ -180,3 +180,32 @@ def test_quirk_check_I_mod_criteria_as_committed():
         L.o3d_check_roi_strict(roi.ctypes.data_as(C.c_void_p), N, roi.shape[1], roi.shape[0], out.ctypes.data_as(C.c_void_p))
         assert out.ravel().tolist() == want, N
     assert o.check_roi(roi).ravel().tolist() == [0, 1, 1, 1, 1, 0, 1, 1]
+
+
+def test_colrow_layout_leg_equals_the_row_major_oracle():
+    """o3d_reconstruct_colrow (the reference's [col][row] planes, row-outer loops, one thread)
+    produces exactly the planes, c_p_map and points of o3d_reconstruct -- the layout changes the memory traffic of the
+    timed CPU leg, not a single value."""
+    import importlib
+    s3 = importlib.import_module("3dscan_b200")
+    W, H, PW, PH = 336, 200, 256, 160
+    c = scaled_calib(load_calib_c1(), W / 1600.0, PW / 1280.0)
+    args = [c[k] for k in ("Kc", "dc", "Kp", "dp", "rc", "tc", "rp", "tp")]
+    ocal = o.make_calib(*args)
+    for N, M in ((3, 6), (8, 7)):
+        cfg = s3.make_config(W, H, PW, PH, N, M, M, 4, 4, 2)
+        stack, roi = s3.synth_stack(cfg, s3.make_calib(*args))
+        d = s3.split_stack(cfg, stack)
+        cd = {k: getattr(cfg, k) for k in ("W", "H", "PW", "PH", "N", "M_v", "M_h", "fw_v", "fw_h", "dirs")}
+        inp = (d["fringe_v"], d["gray_v"], d["inv_v"], d["fringe_h"], d["gray_h"], d["inv_h"], roi)
+        a = o.reconstruct(cd, ocal, *inp, threads=2)
+        b = o.reconstruct(cd, ocal, *inp, colrow=True)
+        assert a.count == b.count > 1000
+        for name in ("valid_v", "valid_h", "valid", "code_v", "code_h"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), name
+        for name in ("wrapped_v", "wrapped_h", "unwrapped_v", "unwrapped_h"):
+            assert np.array_equal(getattr(a, name).view(np.uint32), getattr(b, name).view(np.uint32)), name
+        assert np.array_equal(a.cpmap, b.cpmap) and np.array_equal(a.pix, b.pix)
+        assert np.array_equal(a.pts.view(np.uint32), b.pts.view(np.uint32))
+        m = a.valid == 1
+        assert np.array_equal(a.xyz[m], b.xyz[m])
