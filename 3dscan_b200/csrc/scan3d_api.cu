@@ -562,6 +562,7 @@ int scan3d_reconstruct_dev(scan3d_ctx* ctx, const uint8_t* stack_dev, const uint
     memcpy(a.reg_t, ctx->reg_t, sizeof(a.reg_t));
     a.W = c.W; a.H = c.H; a.row0 = c.row0; a.H_total = c.H_total; a.PW = c.PW; a.PH = c.PH;
     a.N = c.N; a.M_v = c.M_v; a.M_h = c.M_h; a.fw_v = c.fw_v; a.fw_h = c.fw_h;
+    a.fw_v_d = (double)c.fw_v; a.fw_h_d = (double)c.fw_h;
 #if S3D_BUILD_V8
     static const int impl = getenv("SCAN3D_FUSED_IMPL") ? atoi(getenv("SCAN3D_FUSED_IMPL")) : 7;
     if (impl >= 8 && fused8_supported(c)) {

@@ -495,8 +495,8 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                         float unwh = (y == 0 || y == a.H_total - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);  // :304, :309
                         unwh = mh ? unwh : 0.0f;
                         int px, py;                                                       // 5/compute_correspondance.cpp:648-675
-                        const bool okx = correspond32(unwv, a.fw_v, &px);
-                        const bool oky = correspond32(unwh, a.fw_h, &py);
+                        const bool okx = correspond32(unwv, a.fw_v_d, &px);
+                        const bool oky = correspond32(unwh, a.fw_h_d, &py);
                         // FE_INVALID on x rejects before y is computed (:650-655); on y after x is stored
                         r_cp[u].x = (m && okx) ? px : 0;
                         r_cp[u].y = (m && okx && oky) ? py : 0;

@@ -169,6 +169,7 @@ struct FusedArgs {
     uint32_t epoch;
     int W, H, row0, H_total, PW, PH;
     int N, M_v, M_h, fw_v, fw_h;
+    double fw_v_d, fw_h_d;        // the fringe widths as doubles (5/compute_correspondance.cpp:648: fw * (Phi / 2Pi) in double)
     int n_tiles, tiles_per_row;
 };
 int fused_num_tiles(const scan3d_config& c);

@@ -309,9 +309,10 @@ __device__ __forceinline__ bool correspond(float phi_abs, int fw, long long* out
 }
 // Same decision in 32 bits for the fused kernels: cvt.rni.s32.f64 saturates exactly like the
 // clamp of the 64-bit lrint to int, NaN converts to 0 and fails the |v| < 2^63 test (FE_INVALID).
-__device__ __forceinline__ bool correspond32(float phi_abs, int fw, int* out)
+// (fw as a double: the caller converts the fringe width once, not per pixel)
+__device__ __forceinline__ bool correspond32(float phi_abs, double fw, int* out)
 {
-    const double v = dmul((double)fw, div_const((double)phi_abs, K_TWO_PI_REF, K_RCP_TWO_PI_REF, true));
+    const double v = dmul(fw, div_const((double)phi_abs, K_TWO_PI_REF, K_RCP_TWO_PI_REF, true));
     *out = __double2int_rn(v);
     return fabs(v) < 9223372036854775808.0;
 }

@@ -95,8 +95,8 @@ void run(const HostArgs& a, const DeviceCalib& cal, const uint8_t* stack, const 
                     unwh = (y == 0 || y == H - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);
                 }
                 int px = 0, py = 0;
-                const bool okx = correspond32(unwv, a.fw_v, &px);
-                const bool oky = correspond32(unwh, a.fw_h, &py);
+                const bool okx = correspond32(unwv, (double)a.fw_v, &px);
+                const bool oky = correspond32(unwh, (double)a.fw_h, &py);
                 const int cpx = (m && okx) ? px : 0, cpy = (m && okx && oky) ? py : 0;
                 v = m && okx && oky && (unsigned)px <= (unsigned)(a.PW - 1) && (unsigned)py <= (unsigned)(a.PH - 1);
                 unw_h[p] = unwh;
