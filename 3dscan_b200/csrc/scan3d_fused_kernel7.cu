@@ -30,6 +30,10 @@
 
 #include "scan3d_fused_common.cuh"
 
+#ifndef S3D_IO_IDLE_NS
+#define S3D_IO_IDLE_NS 250   // the IO warp's back-off when an event-loop pass found nothing to do
+#endif
+
 namespace s3d {
 
 struct Geom7 {
@@ -372,7 +376,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     }
                 }
             }
-            if (!progressed) __nanosleep(250);
+            if (!progressed) __nanosleep(S3D_IO_IDLE_NS);
         }
         return;
     }
@@ -547,6 +551,9 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
             if (!mbar_try(bar_cxfree + 8 * b, ((it >> 1) & 1) ^ 1))
                 while (!mbar_try(bar_cxfree + 8 * b, ((it >> 1) & 1) ^ 1)) __nanosleep(64);
             if (lane == 31) cnts[b * 16 + warp] = incl;
+            // the camera-table entries of the thread's surviving pixels (64 contiguous bytes): into L1 while the warp
+            // waits at the barrier -- the triangulation's first use of them was 5 % of all stall samples (-1 % time)
+            if (a.cam_lut && vbits) prefetch_l1(a.cam_lut + (size_t)p0 + lp0);
             cons_sync<NCONS>();
             uint32_t rank = incl - cnt, total = 0;
 #pragma unroll

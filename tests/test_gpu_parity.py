@@ -415,6 +415,49 @@ def test_modulation_mask_flag_matches_oracle():
         s3.Scan3D(s3.make_config(W, H, PW, PH, 4, 7, 7, 8, 8, 2, flags=s3.FLAG_MODULATION_MASK), 0, cal)
 
 
+def test_concurrent_contexts_with_cta_limit_equal_serial():
+    """bench.py's default schedule: four contexts on four streams, each limited to one CTA slot per SM
+    (scan3d_set_cta_limit), reconstruct DIFFERENT scans at the same time.  Every context's planes and point cloud
+    must equal what an unrestricted context produces for the same scan alone, over several rounds."""
+    import torch
+    W, H, PW, PH = 1024, 611, 1024, 768
+    cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)
+    cfg = s3.make_config(W, H, PW, PH, 8, 10, 10, 2, 2, 2)
+    NCTX, ROUNDS = 4, 3
+    scans = [s3.synth_stack(cfg, cal, s3.default_synth_params(seed=0xC0FFEE + k, roi_fraction=0.9 - 0.1 * (k % 5)))
+             for k in range(NCTX * ROUNDS)]
+    solo = _ctx(cfg, cal)
+    want = []
+    for stack, roi in scans:
+        solo.reconstruct(stack, roi)
+        want.append((solo.points().copy(), solo.plane(s3.PLANE_VALID).copy(), solo.code_i32(0).copy(),
+                     solo.plane(s3.PLANE_UNWRAPPED_V).copy()))
+    solo.close()
+    ref = run_oracle(cfg, ocal, *scans[0])
+    assert np.array_equal(want[0][0].view(np.uint32), ref.pts.view(np.uint32))
+    streams = [torch.cuda.Stream() for _ in range(NCTX)]
+    ctxs = [s3.Scan3D(cfg, 0, cal, stream=st.cuda_stream) for st in streams]
+    for c in ctxs:
+        c.set_cta_limit(1)
+    d_stacks = [torch.from_numpy(st).cuda() for st, _ in scans]
+    d_rois = [torch.from_numpy(r).cuda() for _, r in scans]
+    torch.cuda.synchronize()
+    for r in range(ROUNDS):
+        for i, c in enumerate(ctxs):                      # enqueue all four without waiting in between
+            k = r * NCTX + i
+            c.reconstruct_dev(d_stacks[k].data_ptr(), d_rois[k].data_ptr())
+        for i, c in enumerate(ctxs):
+            k = r * NCTX + i
+            pts, valid, code, unw = want[k]
+            assert c.point_count() == len(pts), (r, i)
+            assert np.array_equal(c.points().view(np.uint32), pts.view(np.uint32)), (r, i)
+            assert np.array_equal(c.plane(s3.PLANE_VALID), valid), (r, i)
+            assert np.array_equal(c.code_i32(0), code), (r, i)
+            assert np.array_equal(c.plane(s3.PLANE_UNWRAPPED_V).view(np.uint32), unw.view(np.uint32)), (r, i)
+    for c in ctxs:
+        c.close()
+
+
 def test_fused_row_shards_concatenate_to_full_frame():
     W, H, PW, PH = 1024, 90, 1024, 768
     cal, ocal, _ = calibs(W / 1600.0, PW / 1280.0)

@@ -1,8 +1,12 @@
-D=gpurun_out/ab; mkdir -p $D
-B="python bench.py --no-e2e --no-cpu-baseline --steps 20 --batch 16 --contexts 1"
+# A/B of kernel build variants inside ONE box (box-to-box variance is ~3 %): usage  r2_ab.sh <libdir-suffix>...
+D=gpurun_out/ab; rm -rf $D; mkdir -p $D
+# AB_ARGS overrides the short single-context run, e.g. AB_ARGS="" for the driver-style default (1.4 s under the power cap)
+B="python bench.py --no-e2e --no-cpu-baseline --no-rowshard ${AB_ARGS---steps 20 --batch 16 --contexts 1 --cta-limit 0}"
 for i in 1 2 3; do
-SCAN3D_LIBDIR=$PWD/3dscan_b200/lib_var_noreg timeout 200 $B > $D/noreg_$i.json 2>/dev/null
 timeout 200 $B > $D/cur_$i.json 2>/dev/null
+for v in "$@"; do
+SCAN3D_LIBDIR=$PWD/3dscan_b200/lib_var_$v timeout 200 $B > $D/${v}_$i.json 2>/dev/null
+done
 done
 python - <<'PY'
 import glob, json
