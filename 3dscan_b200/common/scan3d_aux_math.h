@@ -140,10 +140,13 @@ S3A_HD uint8_t bilinear_u8(int v0, int v1, int v2, int v3, int frac)
 // is barely larger than the tile (the map is close to the identity); per frame that box is staged in shared
 // memory with aligned 16-byte copies and the taps are gathered from there.  The box is frame-independent.
 constexpr int REMAP_TILE_W = 256, REMAP_TILE_H = 8;      // output tile
-constexpr int REMAP_BOX_W = 288, REMAP_BOX_H = 16;       // staging buffer (bytes per row, rows)
+// staging buffer: rows and row pitch in bytes.  The pitch is a multiple of 128 B, so the shared-memory bank of a
+// staged byte does not depend on its row (with a 288-byte pitch a warp whose pixels straddle two source rows paid a
+// two-way bank conflict on most loads: 40 % of the shared-memory wavefronts of the round-2 kernel)
+constexpr int REMAP_BOX_W = 384, REMAP_BOX_H = 16;
 
 struct RemapBox {
-    int ok;         // 1: the box fits the buffer (it may reach outside the image: those vectors are staged as zeros,
+    int ok;         // 1: the box fits the buffer (it may reach outside the image: those bytes are staged as zeros,
                     //    which is cv::remap's constant border)
     int x0, y0;     // first staged source column (multiple of 16) and row
     int w, rows;    // staged bytes per row (multiple of 16, <= REMAP_BOX_W) and rows (<= REMAP_BOX_H)
@@ -162,39 +165,70 @@ S3A_HD RemapBox remap_tile_box(int minx, int maxx, int miny, int maxy, int W, in
     return b;
 }
 
-// is the 16-byte vector at staged row r, vector column c inside the image?  (x0 and W are multiples of 16, so a
-// vector is inside or outside as a whole)
-S3A_HD bool remap_box_vector_inside(const RemapBox& b, int r, int c, int W, int H)
+// The part of staged row r that lies inside the image, as ONE aligned copy: *dst_off = offset in the staging buffer,
+// *src_off = offset in a frame, returns the byte count (a multiple of 16; 0: the whole row is border).  x0 and W are
+// multiples of 16, so the inside part starts and ends on 16-byte boundaries.  What it does not cover stays zero.
+S3A_HD int remap_box_row_copy(const RemapBox& b, int r, int W, int H, int* dst_off, long long* src_off)
 {
-    const int y = b.y0 + r, x = b.x0 + 16 * c;
-    return y >= 0 && y < H && x >= 0 && x + 16 <= W;
+    const int y = b.y0 + r;
+    const int xa = b.x0 < 0 ? 0 : b.x0, xb = b.x0 + b.w > W ? W : b.x0 + b.w;
+    *dst_off = r * REMAP_BOX_W + (xa - b.x0);
+    *src_off = (long long)y * W + xa;
+    if (r >= b.rows || y < 0 || y >= H || xb <= xa) return 0;
+    return xb - xa;
 }
 
 // offset of source pixel (sx, sy) inside the staging buffer (row pitch REMAP_BOX_W)
 S3A_HD int remap_box_offset(const RemapBox& b, int sx, int sy) { return (sy - b.y0) * REMAP_BOX_W + (sx - b.x0); }
 
-// The blend of one output pixel from the staged box in ~10 instructions: the frame-independent weights are kept
-// as two packed pairs of 16-bit integers (wA = row y: w00 | w01 << 16, wB = row y + 1), the taps (x, x + 1) of a
-// row come out of two aligned 32-bit words of the box with one funnel shift, and two 16-bit x 8-bit two-way dot
-// products (IDP.2A) accumulate bilinear_u8()'s sum exactly (integers: the order of the products does not matter).
-S3A_HD void bilinear_weight_pairs(int frac, uint32_t* wA, uint32_t* wB)
+// The blend of one output pixel from the staged box.  Neighbouring output pixels (2j, 2j + 1) of a row nearly always
+// read neighbouring source pixels of ONE row pair: both pixels' taps (x, x + 1) then lie inside the two aligned
+// 32-bit words that hold the first pixel's first tap, and one byte permute with a frame-independent selector cuts
+// all four out of them -- 2 shared-memory loads + 1 permute per pixel PAIR and row instead of 4 loads + 2 funnel
+// shifts.  A pair that does not qualify (the second pixel on another source row, or more than 6 bytes further on)
+// takes its second pixel from that pixel's own two words.
+//   off0, off1: remap_box_offset of the two pixels.  *base = offset of the first word (multiple of 4),
+//   *sel = permute selector giving [t0(x) t0(x+1) t1(x) t1(x+1)] out of {word(base), word(base + 4)};
+//   returns true if the pair qualifies (else *sel's upper half selects nothing useful and must not be used).
+S3A_HD bool remap_pair_window(int off0, int off1, int* base, uint32_t* sel)
 {
-    const uint32_t ax = frac & 31, ay = (frac >> 5) & 31;
-    *wA = (32 * (32 - ay) * (32 - ax)) | ((32 * (32 - ay) * ax) << 16);      // each <= 32768: fits 16 unsigned bits
-    *wB = (32 * ay * (32 - ax)) | ((32 * ay * ax) << 16);
+    *base = off0 & ~3;
+    const int o0 = off0 & 3, o1 = off1 - *base;
+    const bool regular = o1 >= 0 && o1 <= 6;
+    const uint32_t p1 = regular ? (uint32_t)o1 : 0u;
+    *sel = (uint32_t)o0 | ((uint32_t)(o0 + 1) << 4) | (p1 << 8) | ((p1 + 1) << 12);
+    return regular;
 }
-// bytes box[off], box[off + 1] in bits 0..15 (the box is 4-byte aligned and padded by one word)
-S3A_HD uint32_t box_taps(const uint8_t* box, int off)
+// selector of a single pixel's taps (low two bytes) out of its own two words
+S3A_HD uint32_t remap_own_selector(int off) { return (uint32_t)(off & 3) | ((uint32_t)((off & 3) + 1) << 4); }
+
+// bytes of the word pair {lo, hi} picked by four 4-bit indices (PRMT, default mode: index 0..7)
+S3A_HD uint32_t permute_bytes(uint32_t lo, uint32_t hi, uint32_t sel)
 {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(box + (off & ~3));
-    const uint32_t lo = w[0], hi = w[1];
-    const int sh = 8 * (off & 3);
 #if defined(__CUDA_ARCH__)
-    return __funnelshift_r(lo, hi, sh);
+    return __byte_perm(lo, hi, sel);
 #else
-    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+    const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7))) & 0xffu) << (8 * k);
+    return r;
 #endif
 }
+
+// The four bilinear weights of cv::remap's table (bilinear_u8: products of two 5-bit fractions times 32, summing
+// to 2^15) DOUBLED and packed as two pairs of unsigned 16-bit integers (wA = row y: w00 | w01 << 16, wB = row y + 1):
+// with a sum of 2^16 the rounded result (S + 2^14) >> 15 = (2 S + 2^15) >> 16 is byte 2 of the accumulator, which a
+// byte permute packs without shifts.  The only weight that does not fit, 2 * 32768 (fraction 0), is stored as 65535:
+// 65535 t + 2^15 = 65536 t + (2^15 - t), and 0 < 2^15 - t < 2^16 for a byte t, so byte 2 is still exactly t.
+S3A_HD void bilinear_weight_pairs_x2(int frac, uint32_t* wA, uint32_t* wB)
+{
+    const uint32_t ax = frac & 31, ay = (frac >> 5) & 31;
+    uint32_t w00 = 64 * (32 - ay) * (32 - ax);
+    if (w00 > 65535u) w00 = 65535u;
+    *wA = w00 | ((64 * (32 - ay) * ax) << 16);
+    *wB = (64 * ay * (32 - ax)) | ((64 * ay * ax) << 16);
+}
+// acc + w.lo * taps.byte0 + w.hi * taps.byte1  (IDP.2A.LO)  /  ... taps.byte2, taps.byte3  (IDP.2A.HI)
 S3A_HD uint32_t dot2_u16_u8(uint32_t w, uint32_t taps, uint32_t acc)
 {
 #if defined(__CUDA_ARCH__)
@@ -203,9 +237,24 @@ S3A_HD uint32_t dot2_u16_u8(uint32_t w, uint32_t taps, uint32_t acc)
     return acc + (w & 0xffffu) * (taps & 0xffu) + (w >> 16) * ((taps >> 8) & 0xffu);
 #endif
 }
-S3A_HD uint32_t bilinear_u8_pairs(uint32_t wA, uint32_t wB, uint32_t taps_row0, uint32_t taps_row1)
+S3A_HD uint32_t dot2_u16_u8_hi(uint32_t w, uint32_t taps, uint32_t acc)
 {
-    return dot2_u16_u8(wB, taps_row1, dot2_u16_u8(wA, taps_row0, 1u << 14)) >> 15;
+#if defined(__CUDA_ARCH__)
+    return __dp2a_hi(w, taps, acc);
+#else
+    return acc + (w & 0xffffu) * ((taps >> 16) & 0xffu) + (w >> 16) * ((taps >> 24) & 0xffu);
+#endif
+}
+// accumulators of the pixel in the low (hi = false) / high (hi = true) half of the tap words; the result is byte 2
+S3A_HD uint32_t blend_acc_x2(uint32_t wA, uint32_t wB, uint32_t taps_row0, uint32_t taps_row1, bool hi)
+{
+    return hi ? dot2_u16_u8_hi(wB, taps_row1, dot2_u16_u8_hi(wA, taps_row0, 1u << 15))
+              : dot2_u16_u8(wB, taps_row1, dot2_u16_u8(wA, taps_row0, 1u << 15));
+}
+// byte 2 of four accumulators -> one word of four output pixels
+S3A_HD uint32_t pack_acc_bytes(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3)
+{
+    return permute_bytes(permute_bytes(a0, a1, 0x0062), permute_bytes(a2, a3, 0x0062), 0x5410);
 }
 
 // register_point_clouds' rotation about Y for a cloud captured at turntable angle theta (degrees,

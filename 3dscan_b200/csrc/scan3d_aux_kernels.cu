@@ -84,70 +84,123 @@ __global__ void __launch_bounds__(256) k_remap_frames(const uint8_t* __restrict_
     }
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+// ---- PTX helpers of the staged remap (mbarrier pipeline fed by bulk copies) -------------------------------------
+__device__ __forceinline__ uint32_t rm_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rm_bar_init(uint32_t bar, uint32_t count)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void rm_bar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void rm_bar_expect(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rm_bar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "RM_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra RM_WAIT_%=;\n\t}"
+        ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void rm_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// the four words of a pair window: {base, base + 4} of the row and of the row below (immediate offsets: one address
+// computation per window)
+__device__ __forceinline__ void rm_window(uint32_t addr, uint32_t& t0, uint32_t& t1, uint32_t& b0, uint32_t& b1)
+{
+    static_assert(s3a::REMAP_BOX_W == 384, "the offsets below are the row pitch");
+    asm volatile("ld.shared.u32 %0, [%4];\n\tld.shared.u32 %1, [%4+4];\n\tld.shared.u32 %2, [%4+384];\n\tld.shared.u32 %3, [%4+388];"
+                 : "=r"(t0), "=r"(t1), "=r"(b0), "=r"(b1)
+                 : "r"(addr)
+                 : "memory");
+}
 
 #ifndef S3D_REMAP_STAGES
 #define S3D_REMAP_STAGES 6
 #endif
 constexpr int REMAP_STAGES = S3D_REMAP_STAGES;
-// One CTA (256 threads) per output tile of REMAP_TILE_H x REMAP_TILE_W pixels; thread t owns the 4-pixel groups
-// (row t/64, columns 4*(t%64)..+3) and (row t/64 + 4, same columns).  W % 16 == 0.
-__global__ void __launch_bounds__(256, 3) k_remap_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                      const short2* __restrict__ map_xy, const uint16_t* __restrict__ map_frac,
-                                                      int W, int H, int n_frames)
+constexpr int REMAP_CONSUMERS = 256;                                // 8 blending warps
+constexpr int REMAP_THREADS = REMAP_CONSUMERS + 32;                 // + 1 copy warp
+constexpr int REMAP_STAGE_BYTES = s3a::REMAP_BOX_H * s3a::REMAP_BOX_W + 128;   // + padding: a window's second word may lie past the last row
+constexpr int REMAP_SMEM_BYTES = REMAP_STAGES * REMAP_STAGE_BYTES + 2 * REMAP_STAGES * 8 + 16;
+
+// One CTA per output tile of REMAP_TILE_H x REMAP_TILE_W pixels and all the frames of the stack.  Warp 8 copies the
+// tile's source box of frame after frame into a ring of shared-memory stages (one bulk copy per box row, completion
+// on the stage's "full" mbarrier); warps 0..7 blend: thread t owns the 4-pixel groups (row t/64, columns
+// 4*(t%64)..+3) and (row t/64 + 4, same columns), waits for the stage, cuts the taps of each pixel PAIR out of two
+// aligned words per source row (scan3d_aux_math.h: remap_pair_window) and stores 4 output bytes per group; a warp
+// hands the stage back through its "empty" mbarrier.  No CTA-wide barrier inside the frame loop.  W % 16 == 0.
+__global__ void __launch_bounds__(REMAP_THREADS, 3) k_remap_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                const short2* __restrict__ map_xy,
+                                                                const uint16_t* __restrict__ map_frac, int W, int H, int n_frames)
 {
-    // ring of staged source boxes: REMAP_STAGES - 1 frames are in flight per CTA while one is blended (the kernel is
-    // bound by the bytes it keeps in flight: 2 buffers gave 0.31 of the HBM roofline) (+ one vector per buffer: the
-    // taps are cut out of word pairs)
     constexpr int NS = REMAP_STAGES;
-    __shared__ __align__(16) uint8_t box[NS][s3a::REMAP_BOX_H * s3a::REMAP_BOX_W + 16];
-    __shared__ int ext[4];   // min sx, max sx, min sy, max sy over the tile
+    extern __shared__ __align__(128) uint8_t rm_smem_raw[];
+    uint8_t* box = rm_smem_raw;                                                   // [NS][REMAP_STAGE_BYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(box + NS * REMAP_STAGE_BYTES);   // full[NS], empty[NS]
+    int* ext = reinterpret_cast<int*>(bars + 2 * NS);                             // min sx, max sx, min sy, max sy over the tile
     const size_t plane = (size_t)W * H;
     const int tiles_x = (W + s3a::REMAP_TILE_W - 1) / s3a::REMAP_TILE_W;
     const int tx0 = (blockIdx.x % tiles_x) * s3a::REMAP_TILE_W, ty0 = (blockIdx.x / tiles_x) * s3a::REMAP_TILE_H;
     const int t = threadIdx.x;
+    const bool consumer = t < REMAP_CONSUMERS;
     short2 xy[2][4];
     int fr[2][4];
-    bool have[2];
-    size_t pix[2];
+    bool have[2] = {false, false};
+    size_t pix[2] = {0, 0};
     int lo_x = 0x7fffffff, hi_x = -0x7fffffff, lo_y = 0x7fffffff, hi_y = -0x7fffffff;
+    if (consumer) {
 #pragma unroll
-    for (int g = 0; g < 2; g++) {
-        const int x = tx0 + 4 * (t & 63), y = ty0 + (t >> 6) + 4 * g;
-        have[g] = x < W && y < H;     // W % 4 == 0: a group is inside or outside as a whole
-        pix[g] = (size_t)y * W + x;
-        if (have[g]) {
-            const int4 m = __ldg(reinterpret_cast<const int4*>(map_xy + pix[g]));
-            const int mm[4] = {m.x, m.y, m.z, m.w};
-            const uint2 f = __ldg(reinterpret_cast<const uint2*>(map_frac + pix[g]));
-            fr[g][0] = f.x & 0xffff; fr[g][1] = f.x >> 16; fr[g][2] = f.y & 0xffff; fr[g][3] = f.y >> 16;
+        for (int g = 0; g < 2; g++) {
+            const int x = tx0 + 4 * (t & 63), y = ty0 + (t >> 6) + 4 * g;
+            have[g] = x < W && y < H;     // W % 4 == 0: a group is inside or outside as a whole
+            pix[g] = (size_t)y * W + x;
+            if (have[g]) {
+                const int4 m = __ldg(reinterpret_cast<const int4*>(map_xy + pix[g]));
+                const int mm[4] = {m.x, m.y, m.z, m.w};
+                const uint2 f = __ldg(reinterpret_cast<const uint2*>(map_frac + pix[g]));
+                fr[g][0] = f.x & 0xffff; fr[g][1] = f.x >> 16; fr[g][2] = f.y & 0xffff; fr[g][3] = f.y >> 16;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                xy[g][k].x = (short)(mm[k] & 0xffff);
-                xy[g][k].y = (short)(mm[k] >> 16);
-                lo_x = min(lo_x, (int)xy[g][k].x); hi_x = max(hi_x, (int)xy[g][k].x);
-                lo_y = min(lo_y, (int)xy[g][k].y); hi_y = max(hi_y, (int)xy[g][k].y);
+                for (int k = 0; k < 4; k++) {
+                    xy[g][k].x = (short)(mm[k] & 0xffff);
+                    xy[g][k].y = (short)(mm[k] >> 16);
+                    lo_x = min(lo_x, (int)xy[g][k].x); hi_x = max(hi_x, (int)xy[g][k].x);
+                    lo_y = min(lo_y, (int)xy[g][k].y); hi_y = max(hi_y, (int)xy[g][k].y);
+                }
             }
         }
     }
-    if (t == 0) { ext[0] = 0x7fffffff; ext[1] = -0x7fffffff; ext[2] = 0x7fffffff; ext[3] = -0x7fffffff; }
+    if (t == 0) {
+        ext[0] = 0x7fffffff; ext[1] = -0x7fffffff; ext[2] = 0x7fffffff; ext[3] = -0x7fffffff;
+        for (int s = 0; s < NS; s++) {
+            rm_bar_init(rm_smem(bars + s), 1);                          // full: the copy warp's arrive + the bytes
+            rm_bar_init(rm_smem(bars + NS + s), REMAP_CONSUMERS / 32);  // empty: one arrival per blending warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
         lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
     }
-    if ((t & 31) == 0) { atomicMin(&ext[0], lo_x); atomicMax(&ext[1], hi_x); atomicMin(&ext[2], lo_y); atomicMax(&ext[3], hi_y); }
+    if ((t & 31) == 0 && consumer) { atomicMin(&ext[0], lo_x); atomicMax(&ext[1], hi_x); atomicMin(&ext[2], lo_y); atomicMax(&ext[3], hi_y); }
     __syncthreads();
     const s3a::RemapBox b = s3a::remap_tile_box(ext[0], ext[1], ext[2], ext[3], W, H);
 
     if (!b.ok) {   // strong distortion (the box does not fit): per-tap gathers from global memory, as k_remap_frames
+        if (!consumer) return;
         for (int f = 0; f < n_frames; f++) {
             const uint8_t* s = src + (size_t)f * plane;
 #pragma unroll
@@ -166,65 +219,102 @@ __global__ void __launch_bounds__(256, 3) k_remap_tiled(const uint8_t* __restric
         return;
     }
 
-    // the box's 16-byte vectors, at most 2 per thread (16 rows x 18 vectors = 288): where each lands in the buffer and
-    // where it comes from in a frame -- the same for every frame
-    const int vec_per_row = b.w >> 4, n_vec = b.rows * vec_per_row;
-    int v_dst[2], v_kind[2];          // kind: 0 = none, 1 = copy, 2 = outside the image (constant border: zeros)
-    long long v_src[2];
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int v = t + 256 * q;
-        v_kind[q] = 0; v_dst[q] = 0; v_src[q] = 0;
-        if (v < n_vec) {
-            const int r = v / vec_per_row, c = v - r * vec_per_row;
-            v_dst[q] = r * s3a::REMAP_BOX_W + 16 * c;
-            v_src[q] = (long long)(b.y0 + r) * W + (b.x0 + 16 * c);
-            v_kind[q] = s3a::remap_box_vector_inside(b, r, c, W, H) ? 1 : 2;
-        }
+    // a box that reaches outside the image: the border bytes are zeros in every stage, written once (the copies
+    // never touch them); inside the image every staged byte is overwritten per frame and needs no initial value
+    if (b.x0 < 0 || b.y0 < 0 || b.x0 + b.w > W || b.y0 + b.rows > H) {
+        for (int i = t; i < NS * REMAP_STAGE_BYTES / 16; i += REMAP_THREADS) reinterpret_cast<uint4*>(box)[i] = make_uint4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    auto stage = [&](int f, int buf) {
-        const uint8_t* s = src + (size_t)f * plane;
+    __syncthreads();
+    if (n_frames <= 0) return;
+
+    if (!consumer) {
+        // ---------------- copy warp: lane r owns box row r ----------------
+        const int lane = t & 31;
+        int d_off = 0;
+        long long s_off = 0;
+        const int bytes = lane < s3a::REMAP_BOX_H ? s3a::remap_box_row_copy(b, lane, W, H, &d_off, &s_off) : 0;
+        int total = bytes;
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-            if (v_kind[q] == 1) cp_async16(&box[buf][v_dst[q]], s + v_src[q]);
-            else if (v_kind[q] == 2) *reinterpret_cast<uint4*>(&box[buf][v_dst[q]]) = make_uint4(0, 0, 0, 0);
+        for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        const uint8_t* from = src + s_off;
+        int s = 0;
+        uint32_t ph = 1;      // parity of the "empty" phase that precedes the stage's first use: passes at once
+        for (int f = 0; f < n_frames; f++) {
+            const uint32_t full = rm_smem(bars + s), empty = rm_smem(bars + NS + s);
+            rm_bar_wait(empty, ph);
+            if (lane == 0) rm_bar_expect(full, (uint32_t)total);
+            __syncwarp();
+            if (bytes) rm_bulk_g2s(rm_smem(box + (size_t)s * REMAP_STAGE_BYTES + d_off), from, (uint32_t)bytes, full);
+            from += plane;
+            if (++s == NS) { s = 0; ph ^= 1u; }
         }
-        cp_async_commit();
-    };
-    // frame-independent per pixel: offset of its first tap in the box, the 4 weights as two packed pairs
-    int off[2][4];
+        return;
+    }
+
+    // ---------------- blending warps ----------------
+    // frame-independent per pixel pair: byte address of its first window word in stage 0, the permute selector, the
+    // doubled weight pairs; per thread 4 pairs.  A pair that does not qualify keeps its second pixel's own address.
+    uint32_t w_off[2][2], w_sel[2][2], own_off[2][2];
     uint32_t wA[2][4], wB[2][4];
+    uint32_t irregular = 0;
 #pragma unroll
     for (int g = 0; g < 2; g++)
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            off[g][k] = have[g] ? s3a::remap_box_offset(b, xy[g][k].x, xy[g][k].y) : 0;
-            s3a::bilinear_weight_pairs(fr[g][k], &wA[g][k], &wB[g][k]);
+        for (int j = 0; j < 2; j++) {
+            const int off0 = have[g] ? s3a::remap_box_offset(b, xy[g][2 * j].x, xy[g][2 * j].y) : 0;
+            const int off1 = have[g] ? s3a::remap_box_offset(b, xy[g][2 * j + 1].x, xy[g][2 * j + 1].y) : 0;
+            int base;
+            uint32_t sel;
+            if (!s3a::remap_pair_window(off0, off1, &base, &sel)) irregular |= 1u << (2 * g + j);
+            w_off[g][j] = (uint32_t)base;
+            w_sel[g][j] = sel;
+            own_off[g][j] = (uint32_t)(off1 & ~3) | ((uint32_t)(off1 & 3) << 30);   // box offsets are far below 2^30
+            s3a::bilinear_weight_pairs_x2(fr[g][2 * j], &wA[g][2 * j], &wB[g][2 * j]);
+            s3a::bilinear_weight_pairs_x2(fr[g][2 * j + 1], &wA[g][2 * j + 1], &wB[g][2 * j + 1]);
         }
+    // pair slots in which SOME lane of the warp is irregular: the fix-up below is skipped warp-wide for the others
+    uint32_t warp_irregular = irregular;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) warp_irregular |= __shfl_xor_sync(0xffffffffu, warp_irregular, o);
 
-    if (n_frames <= 0) return;
-    // every iteration commits exactly one copy group (an empty one past the last frame), so "at most NS - 2 groups
-    // pending" always means "frame f has landed"
-    for (int f = 0; f < NS - 1; f++) {
-        if (f < n_frames) stage(f, f);
-        else cp_async_commit();
-    }
+    uint8_t* out0 = dst + pix[0];
+    uint8_t* out1 = dst + pix[1];
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t box0 = rm_smem(box);
+    uint32_t sb = box0;                            // shared-memory address of the current stage
     for (int f = 0; f < n_frames; f++) {
-        cp_async_wait<NS - 2>();
-        __syncthreads();               // frame f is visible to everybody, and everybody is done with frame f - 1 ...
-        if (f + NS - 1 < n_frames) stage(f + NS - 1, (f + NS - 1) % NS);      // ... whose buffer this refills
-        else cp_async_commit();
-        const uint8_t* sb = box[f % NS];
+        rm_bar_wait(rm_smem(bars + s), ph);
 #pragma unroll
         for (int g = 0; g < 2; g++) {
             if (!have[g]) continue;
-            uint32_t packed = 0;
+            uint32_t acc[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                packed |= s3a::bilinear_u8_pairs(wA[g][k], wB[g][k], s3a::box_taps(sb, off[g][k]),
-                                                 s3a::box_taps(sb, off[g][k] + s3a::REMAP_BOX_W)) << (8 * k);
-            *reinterpret_cast<uint32_t*>(dst + (size_t)f * plane + pix[g]) = packed;
+            for (int j = 0; j < 2; j++) {
+                uint32_t t0, t1, b0, b1;
+                rm_window(sb + w_off[g][j], t0, t1, b0, b1);
+                const uint32_t top = s3a::permute_bytes(t0, t1, w_sel[g][j]);
+                const uint32_t bot = s3a::permute_bytes(b0, b1, w_sel[g][j]);
+                acc[2 * j] = s3a::blend_acc_x2(wA[g][2 * j], wB[g][2 * j], top, bot, false);
+                acc[2 * j + 1] = s3a::blend_acc_x2(wA[g][2 * j + 1], wB[g][2 * j + 1], top, bot, true);
+                if (warp_irregular & (1u << (2 * g + j))) {
+                    if (irregular & (1u << (2 * g + j))) {
+                        const uint32_t o = own_off[g][j] >> 30, osel = o | ((o + 1) << 4);
+                        rm_window(sb + (own_off[g][j] & 0x3fffffffu), t0, t1, b0, b1);
+                        acc[2 * j + 1] = s3a::blend_acc_x2(wA[g][2 * j + 1], wB[g][2 * j + 1], s3a::permute_bytes(t0, t1, osel),
+                                                           s3a::permute_bytes(b0, b1, osel), false);
+                    }
+                }
+            }
+            *reinterpret_cast<uint32_t*>(g == 0 ? out0 : out1) = s3a::pack_acc_bytes(acc[0], acc[1], acc[2], acc[3]);
         }
+        out0 += plane;
+        out1 += plane;
+        __syncwarp();
+        if ((t & 31) == 0) rm_bar_arrive(rm_smem(bars + NS + s));
+        sb += REMAP_STAGE_BYTES;
+        if (++s == NS) { s = 0; ph ^= 1u; sb = box0; }
     }
 }
 
@@ -299,7 +389,16 @@ cudaError_t launch_remap_frames(const uint8_t* src, uint8_t* dst, const short2* 
     const size_t plane = (size_t)W * H;
     if (W % 16 == 0 && (((uintptr_t)src | (uintptr_t)dst) % 16 == 0)) {
         const int tiles = ((W + s3a::REMAP_TILE_W - 1) / s3a::REMAP_TILE_W) * ((H + s3a::REMAP_TILE_H - 1) / s3a::REMAP_TILE_H);
-        k_remap_tiled<<<tiles, 256, 0, st>>>(src, dst, map_xy, map_frac, W, H, n_frames);
+        static bool attr_set[64] = {};    // the attribute is per device
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            e = cudaFuncSetAttribute(k_remap_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, REMAP_SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+        k_remap_tiled<<<tiles, REMAP_THREADS, REMAP_SMEM_BYTES, st>>>(src, dst, map_xy, map_frac, W, H, n_frames);
         return cudaGetLastError();
     }
     const bool vec = (plane % 4 == 0) && (((uintptr_t)src | (uintptr_t)dst) % 4 == 0);

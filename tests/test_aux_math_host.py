@@ -67,9 +67,11 @@ def test_undistort_map_and_remap_match_oracle(shim):
 
 
 def test_tiled_remap_arithmetic_matches_oracle(shim):
-    """k_remap_tiled's arithmetic on the host (the tile's source box staged in a buffer, taps taken from it by funnel
-    shift, packed weight pairs, two-way dot products) gives the oracle's pixels; with the reference's calibration
-    almost every tile qualifies for staging."""
+    """k_remap_tiled's arithmetic on the host (the tile's source box staged row by row in a buffer with the kernel's
+    pitch, the taps of a pixel pair cut out of two words per row by one byte permute, doubled weight pairs, two-way
+    dot products, byte 2 of the accumulators packed) gives the oracle's pixels; with the reference's calibration
+    almost every tile qualifies for staging, and the strongly distorted cases exercise the pairs that do not
+    qualify for the shared window."""
     shim.s3a_host_remap_tiled.restype = C.c_longlong
     rng = np.random.default_rng(7)
     c = load_calib_c1()
@@ -78,14 +80,28 @@ def test_tiled_remap_arithmetic_matches_oracle(shim):
              (640, 480, c["Kc"].reshape(3, 3) * np.array([[0.4], [0.4], [1.0]]), c["dc"] * 8, 0.0),
              (800, 48, np.array([[700.0, 0.7, 400.0], [0, 705.0, 20.0], [0, 0, 1]]), np.array([-0.3, 0.1, 0.01, -0.01, 0.0]), 0.0),
              (1280, 720, c["Kp"].reshape(3, 3), c["dp"], 0.95)]
+    seen_irregular = 0
     for W, H, K, d, min_staged in cases:
         xy, fr = _host_map(shim, K, d, W, H)
         img = rng.integers(0, 256, (H, W), dtype=np.uint8)
         out = np.zeros_like(img)
-        staged = shim.s3a_host_remap_tiled(_p(img), W, H, _p(xy), _p(fr), _p(out))
+        irregular = C.c_longlong(0)
+        staged = shim.s3a_host_remap_tiled(_p(img), W, H, _p(xy), _p(fr), _p(out), C.byref(irregular))
         assert np.array_equal(out, o.undistort_frames(img[None], K, d)[0]), (W, H)
         tiles = -(-W // 256) * -(-H // 8)
         assert staged >= min_staged * tiles, (W, H, staged, tiles)
+        seen_irregular += irregular.value
+    assert seen_irregular > 100                          # the fix-up path is covered
+
+
+def test_doubled_weights_give_the_reference_byte(shim):
+    """bilinear_weight_pairs_x2 (weights doubled so that the result is a whole byte of the accumulator, the one weight
+    that overflows 16 bits saturated) == bilinear_u8 for every fraction, on extreme and random taps."""
+    rng = np.random.default_rng(11)
+    taps = [(0, 0, 0, 0), (255, 255, 255, 255), (255, 0, 0, 0), (0, 255, 0, 0), (0, 0, 255, 0), (0, 0, 0, 255),
+            (255, 0, 255, 0), (1, 254, 127, 128)] + [tuple(int(v) for v in rng.integers(0, 256, 4)) for _ in range(300)]
+    for t in taps:
+        assert shim.s3a_host_blend_x2_equals_reference(*t) == 0, t
 
 
 def test_oracle_undistort_matches_cv2_golden(shim):
