@@ -126,6 +126,12 @@ __device__ __forceinline__ void rm_window(uint32_t addr, uint32_t& t0, uint32_t&
                  : "memory");
 }
 
+#ifndef S3D_REMAP_CTAS
+#define S3D_REMAP_CTAS 3
+#endif
+#ifndef S3D_REMAP_BULK
+#define S3D_REMAP_BULK 0     // 1: one cp.async.bulk per box row (measured: the copy engine's request rate, ~35 cycles per
+#endif                       //    request and SM, then bounds the kernel); 0: 16-byte cp.async vectors, one instruction per row
 #ifndef S3D_REMAP_STAGES
 #define S3D_REMAP_STAGES 6
 #endif
@@ -141,7 +147,7 @@ constexpr int REMAP_SMEM_BYTES = REMAP_STAGES * REMAP_STAGE_BYTES + 2 * REMAP_ST
 // 4*(t%64)..+3) and (row t/64 + 4, same columns), waits for the stage, cuts the taps of each pixel PAIR out of two
 // aligned words per source row (scan3d_aux_math.h: remap_pair_window) and stores 4 output bytes per group; a warp
 // hands the stage back through its "empty" mbarrier.  No CTA-wide barrier inside the frame loop.  W % 16 == 0.
-__global__ void __launch_bounds__(REMAP_THREADS, 3) k_remap_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+__global__ void __launch_bounds__(REMAP_THREADS, S3D_REMAP_CTAS) k_remap_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                 const short2* __restrict__ map_xy,
                                                                 const uint16_t* __restrict__ map_frac, int W, int H, int n_frames)
 {
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(REMAP_THREADS, 3) k_remap_tiled(const uint8_t*
     if (t == 0) {
         ext[0] = 0x7fffffff; ext[1] = -0x7fffffff; ext[2] = 0x7fffffff; ext[3] = -0x7fffffff;
         for (int s = 0; s < NS; s++) {
-            rm_bar_init(rm_smem(bars + s), 1);                          // full: the copy warp's arrive + the bytes
+            rm_bar_init(rm_smem(bars + s), S3D_REMAP_BULK ? 1 : 32);    // full: the copy warp's arrive(s) (+ the bytes)
             rm_bar_init(rm_smem(bars + NS + s), REMAP_CONSUMERS / 32);  // empty: one arrival per blending warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -229,8 +235,11 @@ __global__ void __launch_bounds__(REMAP_THREADS, 3) k_remap_tiled(const uint8_t*
     if (n_frames <= 0) return;
 
     if (!consumer) {
-        // ---------------- copy warp: lane r owns box row r ----------------
         const int lane = t & 31;
+        int s = 0;
+        uint32_t ph = 1;      // parity of the "empty" phase that precedes the stage's first use: passes at once
+#if S3D_REMAP_BULK
+        // ---------------- copy warp: lane r owns box row r ----------------
         int d_off = 0;
         long long s_off = 0;
         const int bytes = lane < s3a::REMAP_BOX_H ? s3a::remap_box_row_copy(b, lane, W, H, &d_off, &s_off) : 0;
@@ -238,8 +247,6 @@ __global__ void __launch_bounds__(REMAP_THREADS, 3) k_remap_tiled(const uint8_t*
 #pragma unroll
         for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
         const uint8_t* from = src + s_off;
-        int s = 0;
-        uint32_t ph = 1;      // parity of the "empty" phase that precedes the stage's first use: passes at once
         for (int f = 0; f < n_frames; f++) {
             const uint32_t full = rm_smem(bars + s), empty = rm_smem(bars + NS + s);
             rm_bar_wait(empty, ph);
@@ -249,6 +256,36 @@ __global__ void __launch_bounds__(REMAP_THREADS, 3) k_remap_tiled(const uint8_t*
             from += plane;
             if (++s == NS) { s = 0; ph ^= 1u; }
         }
+#else
+        // ---------------- copy warp: lane c owns the box's 16-byte vector column c, one cp.async per box row ----------------
+        // (rows and vector columns outside the image are never written: they hold the zero border)
+        const int xv = b.x0 + 16 * lane;
+        const bool lane_in = lane < (b.w >> 4) && xv >= 0 && xv + 16 <= W;
+        const int r_lo = b.y0 < 0 ? -b.y0 : 0, r_hi = b.y0 + b.rows > H ? H - b.y0 : b.rows;
+        const uint8_t* from = src + (long long)(b.y0 + r_lo) * W + (lane_in ? xv : 0);
+        const uint32_t d0 = rm_smem(box) + (uint32_t)(r_lo * s3a::REMAP_BOX_W + 16 * lane);
+        uint32_t sbase = d0;
+        for (int f = 0; f < n_frames; f++) {
+            const uint32_t full = rm_smem(bars + s), empty = rm_smem(bars + NS + s);
+            rm_bar_wait(empty, ph);
+            if (lane_in) {
+                const uint8_t* g = from;
+                uint32_t d = sbase;
+#pragma unroll 4
+                for (int r = r_lo; r < r_hi; r++) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+                    g += W;
+                    d += s3a::REMAP_BOX_W;
+                }
+            }
+            // the lane's arrival on "full" fires when its copies above have landed
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full) : "memory");
+            from += plane;
+            sbase += REMAP_STAGE_BYTES;
+            if (++s == NS) { s = 0; ph ^= 1u; sbase = d0; }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
         return;
     }
 
