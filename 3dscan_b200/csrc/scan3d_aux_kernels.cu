@@ -5,9 +5,10 @@
 //                     (2/project_pattern.cpp:220: the reference rebuilds it for every captured frame)
 //   k_remap_tiled     cv::remap of a whole captured stack through that map: the map entry of a pixel is read once
 //                     and applied to every frame (F bytes in + F bytes out + 6 B map per pixel).  One CTA per
-//                     8 x 256 output tile; per frame the tile's source box (the map is close to the identity) is
-//                     staged in shared memory with 16-byte cp.async copies, double-buffered over the frame loop,
-//                     and blended from there: ~10 instructions per output byte (scan3d_aux_math.h)
+//                     8 x 256 output tile: a copy warp stages the tile's source box (the map is close to the
+//                     identity) frame after frame into a ring of shared-memory stages (cp.async vectors, completion
+//                     on mbarriers), 8 warps blend from there: 2 loads + 1 byte permute per pixel pair and source row,
+//                     two-way dot products with doubled weights (scan3d_aux_math.h), ~7 instructions per output byte
 //   k_remap_frames    the same through per-tap global gathers: any width, any distortion (fallback)
 //   k_roi_fill        image_scissor's scan-line fill (m_tech_project_console.cpp:186-229)
 //   k_register_points register_point_clouds' rigid transform (9/register_point_clouds.cpp:117-137)
@@ -142,11 +143,12 @@ constexpr int REMAP_STAGE_BYTES = s3a::REMAP_BOX_H * s3a::REMAP_BOX_W + 128;   /
 constexpr int REMAP_SMEM_BYTES = REMAP_STAGES * REMAP_STAGE_BYTES + 2 * REMAP_STAGES * 8 + 16;
 
 // One CTA per output tile of REMAP_TILE_H x REMAP_TILE_W pixels and all the frames of the stack.  Warp 8 copies the
-// tile's source box of frame after frame into a ring of shared-memory stages (one bulk copy per box row, completion
-// on the stage's "full" mbarrier); warps 0..7 blend: thread t owns the 4-pixel groups (row t/64, columns
-// 4*(t%64)..+3) and (row t/64 + 4, same columns), waits for the stage, cuts the taps of each pixel PAIR out of two
-// aligned words per source row (scan3d_aux_math.h: remap_pair_window) and stores 4 output bytes per group; a warp
-// hands the stage back through its "empty" mbarrier.  No CTA-wide barrier inside the frame loop.  W % 16 == 0.
+// tile's source box of frame after frame into a ring of shared-memory stages (16-byte cp.async vectors, one
+// instruction per box row; the lanes' arrivals on the stage's "full" mbarrier fire when their copies have landed);
+// warps 0..7 blend: thread t owns the 4-pixel groups (row t/64, columns 4*(t%64)..+3) and (row t/64 + 4, same
+// columns), waits for the stage, cuts the taps of each pixel PAIR out of two aligned words per source row
+// (scan3d_aux_math.h: remap_pair_window) and stores 4 output bytes per group; a warp hands the stage back through
+// its "empty" mbarrier.  No CTA-wide barrier inside the frame loop.  W % 16 == 0.
 __global__ void __launch_bounds__(REMAP_THREADS, S3D_REMAP_CTAS) k_remap_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                 const short2* __restrict__ map_xy,
                                                                 const uint16_t* __restrict__ map_frac, int W, int H, int n_frames)

@@ -64,3 +64,40 @@ n = plane
 tp = timed(lambda: ctx.register_points_dev(src, dst, n, 36.0, 1.5, -2.0, 880.0))
 line("k_register_points", tp, n * 24, workload="12.3 M points")
 ctx.close()
+
+# ---- raw captures -> points: scan3d_reconstruct_raw_dev (remap + worklist + single-pass kernel chained on one stream),
+#      one context, then four contexts on four streams with one CTA slot per SM each for the persistent kernel: the
+#      remap of one scan (shared-memory / LSU bound) then runs beside the decode of another (FP64 / issue bound)
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+cfg = s3.make_config(W, H, W, H, 8, 10, 10, 4, 4, 2, flags=s3.FLAG_FAST_TRIANGULATION)
+stack, roi = s3.synth_stack(cfg, cal)
+d_stack = torch.from_numpy(stack).cuda()
+d_roi = torch.from_numpy(roi).cuda()
+del stack
+for n_ctx, limit in ((1, 0), (4, 1), (4, 0)):
+    streams = [torch.cuda.Stream() for _ in range(n_ctx)]
+    ctxs = [s3.Scan3D(cfg, 0, cal, stream=st.cuda_stream) for st in streams]
+    for c in ctxs:
+        if limit:
+            c.set_cta_limit(limit)
+        c.reconstruct_raw_dev(d_stack.data_ptr(), d_roi.data_ptr())     # builds the map, allocates
+    torch.cuda.synchronize()
+    n_scans = 48
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for st in streams:
+        st.wait_event(ev0)
+    for k in range(n_scans):
+        ctxs[k % n_ctx].reconstruct_raw_dev(d_stack.data_ptr(), d_roi.data_ptr())
+    for st in streams:
+        torch.cuda.current_stream().wait_stream(st)
+    ev1.record()
+    torch.cuda.synchronize()
+    sec = ev0.elapsed_time(ev1) * 1e-3 / n_scans
+    line("raw captures -> points (remap + worklist + k_fused7), %d context(s)%s" % (n_ctx, ", 1 CTA slot per SM each" if limit else ""),
+         sec, plane * (2 * NF + 6) + plane * 90, workload="4096x3000 x 56 raw frames per scan", mpix_per_s=round(plane / sec / 1e6, 1),
+         points=int(ctxs[0].point_count()))
+    for c in ctxs:
+        c.close()
