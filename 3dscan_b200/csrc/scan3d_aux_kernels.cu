@@ -426,7 +426,10 @@ cudaError_t launch_remap_frames(const uint8_t* src, uint8_t* dst, const short2* 
                                 int H, int n_frames, int sm_count, cudaStream_t st)
 {
     const size_t plane = (size_t)W * H;
-    if (W % 16 == 0 && (((uintptr_t)src | (uintptr_t)dst) % 16 == 0)) {
+    // a single frame (the capture loop's per-image call) does not amortise the tile set-up: 48.6 us through the
+    // per-tap gathers against 53.9 us staged at 12 MP; from two frames on the staged kernel wins (6 us per further frame
+    // against 23 us)
+    if (n_frames >= 2 && W % 16 == 0 && (((uintptr_t)src | (uintptr_t)dst) % 16 == 0)) {
         const int tiles = ((W + s3a::REMAP_TILE_W - 1) / s3a::REMAP_TILE_W) * ((H + s3a::REMAP_TILE_H - 1) / s3a::REMAP_TILE_H);
         static bool attr_set[64] = {};    // the attribute is per device
         int dev = 0;

@@ -45,6 +45,22 @@ def test_undistort_frames_match_oracle(W, H, dscale):
     ctx.close()
 
 
+@pytest.mark.parametrize("W,H,dscale,frames", [(640, 480, 5.0, 20), (2048, 104, 1.0, 14), (256, 8, 2.0, 13), (1024, 61, -3.0, 7)])
+def test_undistort_stack_longer_than_the_staging_ring(W, H, dscale, frames):
+    """k_remap_tiled's ring of staged boxes is 6 frames deep: stacks longer than that reuse every stage (both phases
+    of its mbarriers), with boxes that reach outside the image (strong distortion of either sign), partial tiles
+    (W % 256 != 0, H % 8 != 0) and a single-tile image."""
+    cal, _, c = calibs(W / 1600.0, 0.5, dc=None)
+    c["dc"] = c["dc"] * dscale
+    cal = s3.make_calib(*[c[k] for k in ("Kc", "dc", "Kp", "dp", "rc", "tc", "rp", "tp")])
+    ctx = _ctx(W, H, 640, 360, cal)
+    stack = np.random.default_rng(W * H + frames).integers(0, 256, (frames, H, W), dtype=np.uint8)
+    want = o.undistort_frames(stack, c["Kc"], c["dc"])
+    for _ in range(2):                                         # twice: the second launch starts from used barriers' memory
+        assert np.array_equal(ctx.undistort_frames(stack, 0), want)
+    ctx.close()
+
+
 def test_undistort_frames_match_cv2_golden():
     g = np.load(os.path.join(GOLDEN, "f4_kat.npz"))
     _, _, c = calibs()
