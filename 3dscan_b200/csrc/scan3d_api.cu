@@ -362,6 +362,18 @@ int scan3d_compute_wrapped_phase_dev(scan3d_ctx* ctx, int dir, const uint8_t* fr
     return SCAN3D_OK;
 }
 
+// The host-pointer entries stage their inputs in the context's own buffers (allocated on first use, sized for a whole
+// capture stack, kept until scan3d_destroy): no allocation or free per call.
+static int ensure_staging(scan3d_ctx* ctx)
+{
+    const size_t sb = (size_t)scan3d_stack_bytes(&ctx->cfg);
+    size_t rb;
+    roi_bytes(ctx, &rb);
+    if (!ctx->d_stack) CK(cudaMalloc((void**)&ctx->d_stack, sb));
+    if (!ctx->d_roi) CK(cudaMalloc((void**)&ctx->d_roi, rb));
+    return SCAN3D_OK;
+}
+
 int scan3d_compute_wrapped_phase(scan3d_ctx* ctx, int dir, const uint8_t* fringe_host, const uint8_t* roi_host)
 {
     if (!ctx || !fringe_host || !roi_host) return fail(ctx, SCAN3D_ERR_ARG, "null argument");
@@ -369,17 +381,12 @@ int scan3d_compute_wrapped_phase(scan3d_ctx* ctx, int dir, const uint8_t* fringe
     const size_t fb = (size_t)ctx->cfg.N * npix(ctx);
     size_t rb;
     roi_bytes(ctx, &rb);
-    uint8_t *d_f = nullptr, *d_r = nullptr;
-    CK(cudaMalloc((void**)&d_f, fb));
-    if (cudaMalloc((void**)&d_r, rb) != cudaSuccess) { cudaFree(d_f); return fail(ctx, SCAN3D_ERR_CUDA, "cudaMalloc roi"); }
-    int rc = SCAN3D_OK;
-    cudaError_t e = cudaMemcpyAsync(d_f, fringe_host, fb, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_r, roi_host, rb, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) rc = scan3d_compute_wrapped_phase_dev(ctx, dir, d_f, d_r);
-    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_f);
-    cudaFree(d_r);
-    if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, SCAN3D_ERR_CUDA, cudaGetErrorString(e != cudaSuccess ? e : e2));
+    int rc = ensure_staging(ctx);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_stack, fringe_host, fb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_roi, roi_host, rb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = scan3d_compute_wrapped_phase_dev(ctx, dir, ctx->d_stack, ctx->d_roi);
+    CK(cudaStreamSynchronize(ctx->stream));      // the caller may reuse its buffers, the next entry may restage
     return rc;
 }
 
@@ -406,15 +413,13 @@ int scan3d_unwrap_phase(scan3d_ctx* ctx, int dir, const uint8_t* gray_host, cons
     CK(cudaSetDevice(ctx->device));
     const int M = dir == 0 ? ctx->cfg.M_v : ctx->cfg.M_h;
     const size_t b = (size_t)M * npix(ctx);
-    uint8_t* d = nullptr;
-    CK(cudaMalloc((void**)&d, 2 * b));
-    cudaError_t e = cudaMemcpyAsync(d, gray_host, b, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d + b, inv_host, b, cudaMemcpyHostToDevice, ctx->stream);
-    int rc = SCAN3D_OK;
-    if (e == cudaSuccess) rc = scan3d_unwrap_phase_dev(ctx, dir, d, d + b);
-    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
-    if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, SCAN3D_ERR_CUDA, cudaGetErrorString(e != cudaSuccess ? e : e2));
+    int rc = ensure_staging(ctx);                // 2 M frames <= the stack's dirs * (N + 2 M)
+    if (rc) return rc;
+    uint8_t* d = ctx->d_stack;
+    CK(cudaMemcpyAsync(d, gray_host, b, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + b, inv_host, b, cudaMemcpyHostToDevice, ctx->stream));
+    rc = scan3d_unwrap_phase_dev(ctx, dir, d, d + b);
+    CK(cudaStreamSynchronize(ctx->stream));
     return rc;
 }
 
@@ -607,8 +612,7 @@ int scan3d_reconstruct(scan3d_ctx* ctx, const uint8_t* stack_host, const uint8_t
     const size_t sb = (size_t)scan3d_stack_bytes(&ctx->cfg);
     size_t rb;
     roi_bytes(ctx, &rb);
-    if (!ctx->d_stack) CK(cudaMalloc((void**)&ctx->d_stack, sb));
-    if (!ctx->d_roi) CK(cudaMalloc((void**)&ctx->d_roi, rb));
+    if (int rs = ensure_staging(ctx)) return rs;
     CK(cudaMemcpyAsync(ctx->d_stack, stack_host, sb, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_roi, roi_host, rb, cudaMemcpyHostToDevice, ctx->stream));
     int rc = scan3d_reconstruct_dev(ctx, ctx->d_stack, ctx->d_roi);
@@ -658,8 +662,7 @@ int scan3d_reconstruct_raw(scan3d_ctx* ctx, const uint8_t* raw_stack_host, const
     const size_t sb = (size_t)scan3d_stack_bytes(&ctx->cfg);
     size_t rb;
     roi_bytes(ctx, &rb);
-    if (!ctx->d_stack) CK(cudaMalloc((void**)&ctx->d_stack, sb));
-    if (!ctx->d_roi) CK(cudaMalloc((void**)&ctx->d_roi, rb));
+    if (int rs = ensure_staging(ctx)) return rs;
     CK(cudaMemcpyAsync(ctx->d_stack, raw_stack_host, sb, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_roi, roi_host, rb, cudaMemcpyHostToDevice, ctx->stream));
     int rc = scan3d_reconstruct_raw_dev(ctx, ctx->d_stack, ctx->d_roi);
@@ -1016,13 +1019,13 @@ int scan3d_debug_divcheck(scan3d_ctx* ctx, uint64_t* mismatches)
     CK(cudaSetDevice(ctx->device));
     unsigned long long* d = nullptr;
     CK(cudaMalloc((void**)&d, 8));
-    CK(cudaMemsetAsync(d, 0, 8, ctx->stream));
-    CK(launch_debug_divcheck(d, ctx->stream));
-    ctx->launches++;
     unsigned long long h = 0;
-    CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaMemsetAsync(d, 0, 8, ctx->stream);
+    if (e == cudaSuccess) e = launch_debug_divcheck(d, ctx->stream);
+    if (e == cudaSuccess) { ctx->launches++; e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream); }
+    const cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     cudaFree(d);
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, SCAN3D_ERR_CUDA, cudaGetErrorString(e != cudaSuccess ? e : e2));
     *mismatches = h;
     return SCAN3D_OK;
 }

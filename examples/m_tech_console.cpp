@@ -13,14 +13,28 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
 #include "scan3d_compat.h"
 #include "scan3d_host.h"
 
+// SCAN3D_CONSOLE_TIMES=1: wall clock of every reference-named stage on stderr (file reads, the [col][row]
+// transposes of the exported globals and the host<->device copies included: this is the drop-in path as linked)
+static bool g_times = false;
+template <class F>
+static void timed(const char* name, F&& f)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    f();
+    if (g_times)
+        fprintf(stderr, "  %-28s %9.2f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+}
+
 int main(int argc, char** argv)
 {
+    g_times = getenv("SCAN3D_CONSOLE_TIMES") != nullptr;
     if (argc < 2) {
         fprintf(stderr, "usage: %s <M_tech_project_console directory> [n_scans] [rot_step] [tx ty tz]\n", argv[0]);
         return 2;
@@ -38,8 +52,8 @@ int main(int argc, char** argv)
     number_of_patterns_binary_horizontal = 5;
     fringe_width_pixels_vertical = fringe_width_pixels_horizontal = 32;
 
-    generate_pattern();                       // STEP-1 (:300)
-    load_matrices();                          // STEP-2: the stored calibration (:310-330 run the calibration itself)
+    timed("generate_pattern", [] { generate_pattern(); });      // STEP-1 (:300)
+    timed("load_matrices", [] { load_matrices(); });            // STEP-2: the stored calibration (:310-330 run the calibration itself)
 
     unsigned t = 0;
     for (unsigned scan = 0; scan < n_scans; scan++) {
@@ -53,23 +67,23 @@ int main(int argc, char** argv)
               scan3d_read_bmp8(path.c_str(), &ow, &oh, outline.data(), (int64_t)outline.size()) == 0)) {
             for (int r = 1; r < H - 1; r++) outline[(size_t)r * W + 1] = outline[(size_t)r * W + W - 2] = 255;
         }
-        image_scissor_fill(outline.data());
+        timed("image_scissor_fill", [&] { image_scissor_fill(outline.data()); });
 
         printf("\nComputing wrapped phase...\n");
-        compute_wrapped_phase(0);             // :371
-        compute_wrapped_phase(1);             // :375
-        unwrap_phase(0);                      // :379
-        unwrap_phase(1);                      // :383
+        timed("compute_wrapped_phase(0)", [] { compute_wrapped_phase(0); });             // :371
+        timed("compute_wrapped_phase(1)", [] { compute_wrapped_phase(1); });             // :375
+        timed("unwrap_phase(0)", [] { unwrap_phase(0); });                               // :379
+        timed("unwrap_phase(1)", [] { unwrap_phase(1); });                               // :383
         printf("\nComputing correspondence...\n");
-        compute_c_p_map();                    // :388 (STEP-6)
+        timed("compute_c_p_map", [] { compute_c_p_map(); });                             // :388 (STEP-6)
         printf("\nTriangulating...\n");
-        triangulate();                        // :394 (STEP-7)
-        save_point_cloud(t);                  // :400 (STEP-8)
+        timed("triangulate", [] { triangulate(); });                                     // :394 (STEP-7)
+        timed("save_point_cloud", [&] { save_point_cloud(t); });                         // :400 (STEP-8)
         t++;
     }
     if (n_scans > 1) {
         printf("\nMerging view %u...", t);
-        register_point_clouds(n_scans, tx, ty, tz, rot_step);   // :408
+        timed("register_point_clouds", [&] { register_point_clouds(n_scans, tx, ty, tz, rot_step); });   // :408
     }
     scan3d_compat_shutdown();
     return 0;

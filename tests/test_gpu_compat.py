@@ -167,7 +167,17 @@ def test_reference_main_program(tmp_path):
                            os.path.join(repo, "examples", "m_tech_console.cpp"), "-L", LIBDIR, "-lscan3d_compat",
                            "-lscan3d_host", "-lscan3d", "-Wl,-rpath," + LIBDIR, "-o", exe])
     tx, ty, tz, step = 10.0, -5.0, 300.0, 36.0
-    subprocess.check_call([exe, root, "2", str(step), str(tx), str(ty), str(tz)], timeout=300)
+    # per-stage wall clock of the drop-in path as linked (BMP reads, [col][row] exports, copies included): kept as a
+    # measurement artefact when the run happens on a GPU box with a gpurun_out directory
+    run = subprocess.run([exe, root, "2", str(step), str(tx), str(ty), str(tz)], timeout=300, check=True,
+                         env=dict(os.environ, SCAN3D_CONSOLE_TIMES="1"), stderr=subprocess.PIPE, text=True)
+    times = [ln for ln in run.stderr.splitlines() if ln.rstrip().endswith(" ms")]
+    assert len(times) == 2 + 2 * 8 + 1, run.stderr          # generate + load, 8 stage calls per view, registration
+    out_dir = os.path.join(repo, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "main_program_times.log"), "w") as f:
+            f.write("examples/m_tech_console.cpp, 1600x1200 / 1280x720, 3-step 6/5 bits, two views + registration\n")
+            f.write("\n".join(times) + "\n")
 
     ref = run_oracle(cfg, ocal, stack, roi)
     assert ref.count > 50000
