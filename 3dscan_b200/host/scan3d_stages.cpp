@@ -73,13 +73,24 @@ T* plane(T*& p, size_t n)
     return p;
 }
 
-// row-major [H][W] -> the reference's [col][row]
+// row-major [H][W] (K values per pixel) <-> the reference's [col][row]: in 32 x 32 blocks, so that both sides stay in
+// the cache (the plain double loop strides one side by a whole column: 5-10x slower at 1600 x 1200)
+template <int K, class S, class D, class F>
+void transpose_blocks(const S* src, D* dst, int rows, int cols, F conv)
+{
+    constexpr int B = 32;
+    for (int r0 = 0; r0 < rows; r0 += B)
+        for (int c0 = 0; c0 < cols; c0 += B) {
+            const int r1 = r0 + B < rows ? r0 + B : rows, c1 = c0 + B < cols ? c0 + B : cols;
+            for (int c = c0; c < c1; c++)
+                for (int r = r0; r < r1; r++)
+                    for (int k = 0; k < K; k++) dst[((size_t)c * rows + r) * K + k] = conv(src[((size_t)r * cols + c) * K + k]);
+        }
+}
 template <class S, class D>
 void to_col_row(const S* src, D* dst)
 {
-    const int W = Camera_imagewidth, H = Camera_imageheight;
-    for (int r = 0; r < H; r++)
-        for (int c = 0; c < W; c++) dst[(size_t)c * H + r] = (D)src[(size_t)r * W + c];
+    transpose_blocks<1>(src, dst, Camera_imageheight, Camera_imagewidth, [](S v) { return (D)v; });
 }
 
 std::vector<uint8_t> roi_row_major()
@@ -87,8 +98,8 @@ std::vector<uint8_t> roi_row_major()
     if (!selected_region) die("compute_wrapped_phase", "selected_region is not set (image_scissor() fills it in the reference)");
     const int W = Camera_imagewidth, H = Camera_imageheight;
     std::vector<uint8_t> roi(npix());
-    for (int r = 0; r < H; r++)
-        for (int c = 0; c < W; c++) roi[(size_t)r * W + c] = selected_region[(size_t)c * H + r] == 1 ? 1 : 0;
+    // [col][row] -> row-major is the same block transpose with the roles of rows and columns exchanged
+    transpose_blocks<1>(selected_region, roi.data(), W, H, [](int v) { return (uint8_t)(v == 1 ? 1 : 0); });
     return roi;
 }
 
@@ -208,9 +219,7 @@ void triangulate()
     ck(scan3d_get_plane(g_ctx, SCAN3D_PLANE_XYZ, x.data()), "get xyz");
     double* dst = plane(intersection_points, 3 * n);
     const int W = Camera_imagewidth, H = Camera_imageheight;
-    for (int r = 0; r < H; r++)
-        for (int c = 0; c < W; c++)
-            for (int k = 0; k < 3; k++) dst[((size_t)c * H + r) * 3 + k] = x[((size_t)r * W + c) * 3 + k];
+    transpose_blocks<3>(x.data(), dst, H, W, [](double v) { return v; });
 }
 
 void save_point_cloud(unsigned cloud_index)
@@ -303,8 +312,7 @@ void image_scissor_fill(const unsigned char* internal_image)
     region.assign(npix(), 0);
     selected_region = region.data();
     const int W = Camera_imagewidth, H = Camera_imageheight;
-    for (int r = 0; r < H; r++)
-        for (int c = 0; c < W; c++) selected_region[(size_t)c * H + r] = roi[(size_t)r * W + c];
+    transpose_blocks<1>(roi.data(), selected_region, H, W, [](uint8_t v) { return (int)v; });
     if (scan3d_write_bmp8((g_root + "/i1.bmp").c_str(), W, H, filled.data()) != SCAN3D_OK)
         die("image_scissor_fill", scan3d_host_last_error());
 }
