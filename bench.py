@@ -575,7 +575,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "scans_per_s": world * args.steps * args.batch / (ms_max * 1e-3),
-                "points_last_scan": count, "gpu_launches": launches, "clocks": clocks,
+                "points_last_scan": count, "gpu_launches": launches * world, "gpu_launches_per_rank": launches, "clocks": clocks,
                 "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
         if rowshard is not None:
             line["rowshard"] = rowshard
