@@ -204,3 +204,9 @@ def test_raw_entry_and_folded_registration_equal_the_separate_calls(shape):
     b.reconstruct_raw(raw, roi)
     assert not np.array_equal(b.points().view(np.uint32), want.view(np.uint32))
     b.close()
+    # ... and the oracle's chain of the same three reference steps (exact triangulation order by default)
+    from gpu_common import run_oracle
+    _, _, c = calibs(W / 1600.0, PW / 1280.0)
+    ref = run_oracle(cfg, ocal, o.undistort_frames(raw, c["Kc"], c["dc"]), roi)
+    assert ref.count == n
+    assert np.array_equal(o.register_points(ref.pts, theta, *t).view(np.uint32), want.view(np.uint32))
