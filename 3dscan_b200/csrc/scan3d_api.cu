@@ -265,12 +265,14 @@ int scan3d_set_calibration(scan3d_ctx* ctx, const scan3d_calib* cal)
         if (ctx->undist_frac[k]) { cudaFree(ctx->undist_frac[k]); ctx->undist_frac[k] = nullptr; }
     }
     if (ctx->cfg.dirs == 2) {
-        if (d.cam_distorted) {
+        // a table also for an intrinsic matrix that is not [fx 0 cx; 0 fy cy; 0 0 1] (skew, ...): the kernels' table-free
+        // route then only ever sees the standard form (4 operations per coordinate, no division)
+        if (d.cam_distorted || !d.cam_std) {
             CK(dalloc(&ctx->cam_lut, npix(ctx)));
             CK(launch_undistort_lut(nullptr, d, false, ctx->cfg.W, ctx->cfg.H, ctx->cfg.row0, ctx->cam_lut, ctx->stream));
             ctx->launches++;
         }
-        if (d.proj_distorted) {
+        if (d.proj_distorted || !d.proj_std) {
             CK(dalloc(&ctx->proj_lut, (size_t)ctx->cfg.PW * ctx->cfg.PH));
             CK(launch_undistort_lut(nullptr, d, true, ctx->cfg.PW, ctx->cfg.PH, 0, ctx->proj_lut, ctx->stream));
             ctx->launches++;

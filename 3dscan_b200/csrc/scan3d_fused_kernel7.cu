@@ -583,13 +583,13 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     const double2 t = a.cam_lut[(size_t)p0 + lp0 + j];
                     uc = t.x; vc = t.y;
                 } else {
-                    undistorted_pixel_nodist(cal.Kc, cal.ifx_c, cal.ify_c, cal.cam_std != 0, (double)x, (double)y, &uc, &vc);
+                    undistorted_pixel_std(cal.Kc, cal.ifx_c, cal.ify_c, (double)x, (double)y, &uc, &vc);
                 }
                 if (a.proj_lut) {
                     const double2 t = a.proj_lut[(size_t)cpy * a.PW + cpx];
                     up = t.x; vp = t.y;
                 } else {
-                    undistorted_pixel_nodist(cal.Kp, cal.ifx_p, cal.ify_p, cal.proj_std != 0, (double)cpx, (double)cpy, &up, &vp);
+                    undistorted_pixel_std(cal.Kp, cal.ifx_p, cal.ify_p, (double)cpx, (double)cpy, &up, &vp);
                 }
                 if (EXACT) triangulate_point(cal.Ac, cal.Ap, uc, vc, up, vp, Xd);
                 else triangulate_point_fast(cal.Ac, cal.Ap, uc, vc, up, vp, Xd);

@@ -372,6 +372,13 @@ __device__ __forceinline__ double undist_coord_std(double u, double c, double in
 {
     return dadd(dmul(f, dmul(dsub(u, c), inv_f)), c);
 }
+// the same for callers that only run without a table when K has the standard form (the host builds a table otherwise)
+__device__ __forceinline__ void undistorted_pixel_std(const double* __restrict__ K, double ifx, double ify, double u, double v,
+                                                      double* ou, double* ov)
+{
+    *ou = undist_coord_std(u, K[2], ifx, K[0]);
+    *ov = undist_coord_std(v, K[5], ify, K[4]);
+}
 __device__ __forceinline__ void undistorted_pixel_nodist(const double* __restrict__ K, double ifx,
                                                          double ify, bool std_form, double u,
                                                          double v, double* ou, double* ov)

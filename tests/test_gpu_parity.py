@@ -224,6 +224,28 @@ def test_fused_undistorted_camera():
     ctx.close()
 
 
+def test_fused_skewed_intrinsics_without_distortion():
+    """Zero distortion but an intrinsic matrix outside the standard form (skew on both devices): the re-projection
+    of 7/triangulation.cpp:262-307 then is a full 3x3 product with a division (the oracle does it per pixel); the
+    library routes that case through the undistortion tables.  Points stay bit-identical in the exact mode."""
+    W, H, PW, PH = 1024, 128, 1024, 768
+    _, _, c = calibs(W / 1600.0, PW / 1280.0, dc=[0, 0, 0, 0, 0])
+    c["Kc"] = c["Kc"].copy(); c["Kp"] = c["Kp"].copy()
+    c["Kc"][1] = 0.75                   # K[0][1]: skew
+    c["Kp"][1] = -0.4
+    args = [c[k] for k in ("Kc", "dc", "Kp", "dp", "rc", "tc", "rp", "tp")]
+    cal, ocal = s3.make_calib(*args), o.make_calib(*args)
+    cfg = s3.make_config(W, H, PW, PH, 3, 10, 10, 1, 1, 2)
+    stack, roi = s3.synth_stack(cfg, cal)
+    ref = run_oracle(cfg, ocal, stack, roi)
+    assert ref.count > 10000
+    ctx = _ctx(cfg, cal)
+    ctx.reconstruct(stack, roi)
+    st = compare(cfg, ref, ctx)
+    assert st["pts_nonidentical"] == 0
+    ctx.close()
+
+
 @pytest.mark.parametrize("kind", ["empty", "full", "random", "border"])
 def test_fused_roi_edge_cases(kind):
     W, H, PW, PH = 1056, 40, 1024, 768
