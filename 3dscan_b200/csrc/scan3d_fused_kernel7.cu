@@ -115,7 +115,7 @@ constexpr int regs7(int cw, int minb)
 // has written one effective ROI plane per direction (a.roi = vertical, a.roi2 = horizontal); the mask recurrence runs
 // on each, so the two directions have their own masks (the reference's valid_map_vertical / _horizontal).
 // REG: register_point_clouds' turntable transform applied to every point where it is staged (scan3d_set_registration).
-template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false, bool REG = false>
+template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false, bool REG = false, int MV = 0, int MH = 0>
 __global__ void __launch_bounds__((CW + 1) * 32) __maxnreg__(regs7(CW, MINB))
 k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal, const __grid_constant__ CUtensorMap stack_map)
 {
@@ -126,7 +126,10 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
     constexpr bool fastdiv = true;   // host verified (else this kernel is not used)
 
     extern __shared__ __align__(128) uint8_t smem[];
-    const int NF = DIRS == 2 ? 2 * N + 2 * (a.M_v + a.M_h) : N + 2 * a.M_v;
+    // MV / MH != 0: the Gray depths as compile-time constants (the named configurations): plane loops without guards,
+    // frame offsets as immediates -- 4 % of the kernel time at 10 + 10 bits
+    const int M_v = MV ? MV : a.M_v, M_h = MH ? MH : a.M_h;
+    const int NF = DIRS == 2 ? 2 * N + 2 * (M_v + M_h) : N + 2 * M_v;
     uint8_t* slot = smem;
     uint8_t* sroi = smem + (size_t)NF * T;
     constexpr int NROI = (MOD && DIRS == 2) ? 2 : 1;                           // ROI windows: one per direction with MOD
@@ -436,11 +439,11 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
             mbits_h = NROI == 2 ? mask_of(sroi2) : mbits;
             if (mbits | mbits_h) {
                 fringe_terms<N>(sw, 0, WPF, tid, Tv);
-                gray_bits(sw, N, N + a.M_v, a.M_v, WPF, tid, gvA, gvB);
+                gray_bits(sw, N, N + M_v, M_v, WPF, tid, gvA, gvB);
                 if (DIRS == 2) {
-                    const int fh = N + 2 * a.M_v;
+                    const int fh = N + 2 * M_v;
                     fringe_terms<N>(sw, fh, WPF, tid, Th);
-                    gray_bits(sw, fh + N, fh + N + a.M_h, a.M_h, WPF, tid, ghA, ghB);
+                    gray_bits(sw, fh + N, fh + N + M_h, M_h, WPF, tid, ghA, ghB);
                 }
             }
         }
@@ -487,14 +490,14 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     const int x = xt + 2 * h + u;
                     const bool mv = (mb_v >> u) & 1u, mh = (mb_h >> u) & 1u;
                     const bool m = mv && mh;                                             // merge_valid_maps, 5/compute_correspondance.cpp:60-77
-                    const int cv = code_of_pair(gvA_h, gvB_h, u, a.M_v);
+                    const int cv = code_of_pair(gvA_h, gvB_h, u, M_v);
                     const float wv = add_pi(phase_of_pair<N>(Pv, u, tab));               // 4/phase_unwrap.cpp:290
                     float unwv = (x == 0 || x == W - 1) ? 0.0f : unwrap_abs(wv, cv, fastdiv);  // :285, :291
                     unwv = mv ? unwv : 0.0f;
                     bool v = mv;
                     r_cv[u] = mv ? cv : -1;
                     if (DIRS == 2) {
-                        const int ch = code_of_pair(ghA_h, ghB_h, u, a.M_h);
+                        const int ch = code_of_pair(ghA_h, ghB_h, u, M_h);
                         const float wh = add_pi(phase_of_pair<N>(Ph, u, tab));
                         float unwh = (y == 0 || y == a.H_total - 1) ? 0.0f : unwrap_abs(wh, ch, fastdiv);  // :304, :309
                         unwh = mh ? unwh : 0.0f;
@@ -635,10 +638,10 @@ static bool stack_tensor_map(CUtensorMap* map, const uint8_t* stack, size_t plan
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false, bool REG = false>
+template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false, bool REG = false, int MV = 0, int MH = 0>
 static cudaError_t launch7_t(const FusedArgs& a, const DeviceCalib& cal, int sm_count, const Plan7& p, cudaStream_t st)
 {
-    auto kern = k_fused7<N, DIRS, CW, MINB, EXACT, MOD, REG>;
+    auto kern = k_fused7<N, DIRS, CW, MINB, EXACT, MOD, REG, MV, MH>;
     // per instantiation, once per process and shared-memory size: attributes and occupancy (a scan of a small frame
     // is a few tens of microseconds: the host side of a launch must not cost as much)
     static size_t smem_cached = 0;
@@ -703,6 +706,20 @@ static cudaError_t launch7_nd(const FusedArgs& a, const DeviceCalib& cal, int sm
     if (p.cw == CWV && p.minb == MB) {                                                            \
         if (exact || DIRS == 1) return launch7_t<N, DIRS, CWV, MB, true>(a, cal, sm_count, p, st); \
         return launch7_t<N, DIRS, CWV, MB, (DIRS == 1)>(a, cal, sm_count, p, st);                  \
+    }
+    // The named configurations in the default shape get their Gray depths as compile-time constants:
+    // C3 / C4 / C5 (8-step, 10 + 10 bits), C1 (3-step, 6 + 5 bits), C2 (3-step, 8 bits, one direction).
+    if (p.cw == 7 && p.minb == 3) {
+        if (N == 8 && DIRS == 2 && a.M_v == 10 && a.M_h == 10) {
+            if (a.reg_on) return exact ? launch7_t<8, 2, 7, 3, true, false, true, 10, 10>(a, cal, sm_count, p, st)
+                                       : launch7_t<8, 2, 7, 3, false, false, true, 10, 10>(a, cal, sm_count, p, st);
+            return exact ? launch7_t<8, 2, 7, 3, true, false, false, 10, 10>(a, cal, sm_count, p, st)
+                         : launch7_t<8, 2, 7, 3, false, false, false, 10, 10>(a, cal, sm_count, p, st);
+        }
+        if (N == 3 && DIRS == 2 && a.M_v == 6 && a.M_h == 5 && !a.reg_on)
+            return exact ? launch7_t<3, 2, 7, 3, true, false, false, 6, 5>(a, cal, sm_count, p, st)
+                         : launch7_t<3, 2, 7, 3, false, false, false, 6, 5>(a, cal, sm_count, p, st);
+        if (N == 3 && DIRS == 1 && a.M_v == 8) return launch7_t<3, 1, 7, 3, true, false, false, 8, 0>(a, cal, sm_count, p, st);
     }
     // the variant that folds the turntable transform into the point store exists for the two default shapes
     if (DIRS == 2 && a.reg_on && p.cw == 7) {
