@@ -115,7 +115,7 @@ constexpr int regs7(int cw, int minb)
 // has written one effective ROI plane per direction (a.roi = vertical, a.roi2 = horizontal); the mask recurrence runs
 // on each, so the two directions have their own masks (the reference's valid_map_vertical / _horizontal).
 // REG: register_point_clouds' turntable transform applied to every point where it is staged (scan3d_set_registration).
-template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false, bool REG = false, int MV = 0, int MH = 0>
+template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false, bool REG = false, int MV = 0, int MH = 0, int LUTS = -1>
 __global__ void __launch_bounds__((CW + 1) * 32) __maxnreg__(regs7(CW, MINB))
 k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCalib cal, const __grid_constant__ CUtensorMap stack_map)
 {
@@ -129,6 +129,10 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
     // MV / MH != 0: the Gray depths as compile-time constants (the named configurations): plane loops without guards,
     // frame offsets as immediates -- 4 % of the kernel time at 10 + 10 bits
     const int M_v = MV ? MV : a.M_v, M_h = MH ? MH : a.M_h;
+    // LUTS >= 0: which undistortion tables exist is a compile-time fact (bit 0 camera, bit 1 projector; -1: look at the
+    // pointers).  LUTS = 1 is the reference's calibration class: distorted camera, distortion-free projector.
+    const bool has_cam_lut = LUTS < 0 ? a.cam_lut != nullptr : (LUTS & 1) != 0;
+    const bool has_proj_lut = LUTS < 0 ? a.proj_lut != nullptr : (LUTS & 2) != 0;
     const int NF = DIRS == 2 ? 2 * N + 2 * (M_v + M_h) : N + 2 * M_v;
     uint8_t* slot = smem;
     uint8_t* sroi = smem + (size_t)NF * T;
@@ -529,8 +533,8 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                     // the undistortion tables are gathered once per surviving pixel a few thousand
                     // cycles from now: pull the lines into L2 meanwhile (DRAM latency -> L2 latency)
                     if (vb) {
-                        if (a.cam_lut) prefetch_l2(a.cam_lut + gh);
-                        if (a.proj_lut) {
+                        if (has_cam_lut) prefetch_l2(a.cam_lut + gh);
+                        if (has_proj_lut) {
                             if (vb & 1u) prefetch_l2(a.proj_lut + (size_t)c4.y * a.PW + c4.x);
                             if (vb & 2u) prefetch_l2(a.proj_lut + (size_t)c4.w * a.PW + c4.z);
                         }
@@ -556,7 +560,7 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
             if (lane == 31) cnts[b * 16 + warp] = incl;
             // the camera-table entries of the thread's surviving pixels (64 contiguous bytes): into L1 while the warp
             // waits at the barrier -- the triangulation's first use of them was 5 % of all stall samples (-1 % time)
-            if (a.cam_lut && vbits) prefetch_l1(a.cam_lut + (size_t)p0 + lp0);
+            if (has_cam_lut && vbits) prefetch_l1(a.cam_lut + (size_t)p0 + lp0);
             cons_sync<NCONS>();
             uint32_t rank = incl - cnt, total = 0;
 #pragma unroll
@@ -582,13 +586,13 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 const int cpx = j == 0 ? cp01.x : j == 1 ? cp01.z : j == 2 ? cp23.x : cp23.z;
                 const int cpy = j == 0 ? cp01.y : j == 1 ? cp01.w : j == 2 ? cp23.y : cp23.w;
                 double uc, vc, up, vp, Xd[3];
-                if (a.cam_lut) {
+                if (has_cam_lut) {
                     const double2 t = a.cam_lut[(size_t)p0 + lp0 + j];
                     uc = t.x; vc = t.y;
                 } else {
                     undistorted_pixel_std(cal.Kc, cal.ifx_c, cal.ify_c, (double)x, (double)y, &uc, &vc);
                 }
-                if (a.proj_lut) {
+                if (has_proj_lut) {
                     const double2 t = a.proj_lut[(size_t)cpy * a.PW + cpx];
                     up = t.x; vp = t.y;
                 } else {
@@ -638,10 +642,10 @@ static bool stack_tensor_map(CUtensorMap* map, const uint8_t* stack, size_t plan
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false, bool REG = false, int MV = 0, int MH = 0>
+template <int N, int DIRS, int CW, int MINB, bool EXACT, bool MOD = false, bool REG = false, int MV = 0, int MH = 0, int LUTS = -1>
 static cudaError_t launch7_t(const FusedArgs& a, const DeviceCalib& cal, int sm_count, const Plan7& p, cudaStream_t st)
 {
-    auto kern = k_fused7<N, DIRS, CW, MINB, EXACT, MOD, REG, MV, MH>;
+    auto kern = k_fused7<N, DIRS, CW, MINB, EXACT, MOD, REG, MV, MH, LUTS>;
     // per instantiation, once per process and shared-memory size: attributes and occupancy (a scan of a small frame
     // is a few tens of microseconds: the host side of a launch must not cost as much)
     static size_t smem_cached = 0;
@@ -710,15 +714,22 @@ static cudaError_t launch7_nd(const FusedArgs& a, const DeviceCalib& cal, int sm
     // The named configurations in the default shape get their Gray depths as compile-time constants:
     // C3 / C4 / C5 (8-step, 10 + 10 bits), C1 (3-step, 6 + 5 bits), C2 (3-step, 8 bits, one direction).
     if (p.cw == 7 && p.minb == 3) {
+        // ... and with them the reference's calibration class (distorted camera, distortion-free projector: LUTS = 1)
+        const bool ref_class = a.cam_lut != nullptr && a.proj_lut == nullptr;
         if (N == 8 && DIRS == 2 && a.M_v == 10 && a.M_h == 10) {
-            if (a.reg_on) return exact ? launch7_t<8, 2, 7, 3, true, false, true, 10, 10>(a, cal, sm_count, p, st)
-                                       : launch7_t<8, 2, 7, 3, false, false, true, 10, 10>(a, cal, sm_count, p, st);
-            return exact ? launch7_t<8, 2, 7, 3, true, false, false, 10, 10>(a, cal, sm_count, p, st)
-                         : launch7_t<8, 2, 7, 3, false, false, false, 10, 10>(a, cal, sm_count, p, st);
+#define S3D_M10(EX, RG)                                                                                               \
+    (ref_class ? launch7_t<8, 2, 7, 3, EX, false, RG, 10, 10, 1>(a, cal, sm_count, p, st)                              \
+               : launch7_t<8, 2, 7, 3, EX, false, RG, 10, 10>(a, cal, sm_count, p, st))
+            if (a.reg_on) return exact ? S3D_M10(true, true) : S3D_M10(false, true);
+            return exact ? S3D_M10(true, false) : S3D_M10(false, false);
+#undef S3D_M10
         }
-        if (N == 3 && DIRS == 2 && a.M_v == 6 && a.M_h == 5 && !a.reg_on)
+        if (N == 3 && DIRS == 2 && a.M_v == 6 && a.M_h == 5 && !a.reg_on) {
+            if (ref_class) return exact ? launch7_t<3, 2, 7, 3, true, false, false, 6, 5, 1>(a, cal, sm_count, p, st)
+                                        : launch7_t<3, 2, 7, 3, false, false, false, 6, 5, 1>(a, cal, sm_count, p, st);
             return exact ? launch7_t<3, 2, 7, 3, true, false, false, 6, 5>(a, cal, sm_count, p, st)
                          : launch7_t<3, 2, 7, 3, false, false, false, 6, 5>(a, cal, sm_count, p, st);
+        }
         if (N == 3 && DIRS == 1 && a.M_v == 8) return launch7_t<3, 1, 7, 3, true, false, false, 8, 0>(a, cal, sm_count, p, st);
     }
     // the variant that folds the turntable transform into the point store exists for the two default shapes
