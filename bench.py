@@ -110,22 +110,29 @@ class ClockSampler:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        return self.window(t0, t1)
+
+    def window(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.05]
         window = "timed region"
         if not rows:     # region shorter than the sampling period: nearest samples either side
             rows = [r for t, r in self.rows if t0 - 0.1 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
             window = "nearest samples (region shorter than the 25 ms sampling period)"
-        sm, reasons, mx = [], set(), None
+        sm, reasons, mx, pw = [], set(), None, []
         for r in rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
+                pw.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window,
+                "power_w": float(np.median(pw)) if pw else None}
 
 
 def oracle_scan_seconds(cfg, ocal, stack, roi, threads, min_seconds, max_runs):
@@ -413,31 +420,35 @@ def main():
             k = b % args.ring
             ctxs[b % len(ctxs)].reconstruct_dev(ring[k].data_ptr(), rois[k].data_ptr())
 
-    # ---- burst figure first (GPU still cool, clocks at their maximum): the same schedule over 4 x 16 scans after
-    #      3 x 16 warm-up scans, ~20 ms -- what the kernel does before the power cap of a 1.4 s region pulls the SM
+    # ---- burst figure first (GPU still cool, clocks at their maximum): the same schedule over 8 x 16 scans after
+    #      3 x 16 warm-up scans, ~35 ms -- what the kernel does before the power cap of a 1.4 s region pulls the SM
     #      clock down (the kernel is SM-bound, so the long-region figure follows that clock)
     def small_step(n=16):
         for b in range(n):
             k = b % args.ring
             ctxs[b % len(ctxs)].reconstruct_dev(ring[k].data_ptr(), rois[k].data_ptr())
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(3):
         small_step()
     torch.cuda.synchronize()
+    sampler.wait_first_row()
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tb0 = time.time()
     b0.record(stream)
     for st in side_streams:
         st.wait_stream(stream)
-    for _ in range(4):
+    for _ in range(8):
         small_step()
     for st in side_streams:
         stream.wait_stream(st)
     b1.record(stream)
     torch.cuda.synchronize()
-    burst_us = b0.elapsed_time(b1) * 1e3 / 64
+    tb1 = time.time()
+    burst_us = b0.elapsed_time(b1) * 1e3 / 128
+    burst_clocks = sampler.window(tb0, tb1)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     for _ in range(args.warmup):
         step()
     sampler.wait_first_row()
@@ -477,8 +488,8 @@ def main():
                 "traffic": ncu_traffic(args.workload), "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
                 "kernel": ("s3d::k_fused<%d,%d>" if os.environ.get("SCAN3D_FUSED_IMPL") == "6" else "s3d::k_fused7<%d,%d,...>") % (N, dirs), "algorithmic_bytes_per_launch": bpp * npix,
                 "avg_launch_us": per_launch_s * 1e6, "launches_per_scan": launches / (args.steps * args.batch), "frac_of_8TBs_nominal": achieved / 8000.0,
-                "burst": {"avg_launch_us": burst_us, "frac": bpp * npix / (burst_us * 1e-6) / 1e9 / peak, "scans": 64,
-                          "note": "same schedule, 64 scans (~20 ms) before the long region: SM clock not yet pulled down by the power cap"}}
+                "burst": {"avg_launch_us": burst_us, "frac": bpp * npix / (burst_us * 1e-6) / 1e9 / peak, "scans": 128, "clocks": burst_clocks,
+                          "note": "same schedule, 128 scans (~35 ms) before the long region: what the kernel does before a sustained load's power cap pulls the SM clock down"}}
 
     # ---- e2e: host-buffer entry, pinned input, H2D + kernel + D2H of the point cloud per scan
     e2e = None
