@@ -589,14 +589,20 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 if (has_cam_lut) {
                     const double2 t = a.cam_lut[(size_t)p0 + lp0 + j];
                     uc = t.x; vc = t.y;
-                } else {
+                } else if (EXACT) {
                     undistorted_pixel_std(cal.Kc, cal.ifx_c, cal.ify_c, (double)x, (double)y, &uc, &vc);
+                } else {
+                    // fast mode: without distortion the normalise / re-project round trip f * ((u - c) / f) + c is the
+                    // identity up to two roundings (~1e-16 relative, against the mode's 1e-6 bound on the points)
+                    uc = (double)x; vc = (double)y;
                 }
                 if (has_proj_lut) {
                     const double2 t = a.proj_lut[(size_t)cpy * a.PW + cpx];
                     up = t.x; vp = t.y;
-                } else {
+                } else if (EXACT) {
                     undistorted_pixel_std(cal.Kp, cal.ifx_p, cal.ify_p, (double)cpx, (double)cpy, &up, &vp);
+                } else {
+                    up = (double)cpx; vp = (double)cpy;
                 }
                 if (EXACT) triangulate_point(cal.Ac, cal.Ap, uc, vc, up, vp, Xd);
                 else triangulate_point_fast(cal.Ac, cal.Ap, uc, vc, up, vp, Xd);
