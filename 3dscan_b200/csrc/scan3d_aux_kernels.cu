@@ -95,10 +95,6 @@ __device__ __forceinline__ void rm_bar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void rm_bar_expect(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void rm_bar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
@@ -108,12 +104,6 @@ __device__ __forceinline__ void rm_bar_wait(uint32_t bar, uint32_t parity)
         "@!p bra RM_WAIT_%=;\n\t}"
         ::"r"(bar), "r"(parity)
         : "memory");
-}
-__device__ __forceinline__ void rm_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
 }
 
 // the four words of a pair window: {base, base + 4} of the row and of the row below (immediate offsets: one address
@@ -127,16 +117,11 @@ __device__ __forceinline__ void rm_window(uint32_t addr, uint32_t& t0, uint32_t&
                  : "memory");
 }
 
-#ifndef S3D_REMAP_CTAS
-#define S3D_REMAP_CTAS 3
-#endif
-#ifndef S3D_REMAP_BULK
-#define S3D_REMAP_BULK 0     // 1: one cp.async.bulk per box row (measured: the copy engine's request rate, ~35 cycles per
-#endif                       //    request and SM, then bounds the kernel); 0: 16-byte cp.async vectors, one instruction per row
-#ifndef S3D_REMAP_STAGES
-#define S3D_REMAP_STAGES 6
-#endif
-constexpr int REMAP_STAGES = S3D_REMAP_STAGES;
+// Measured alternatives (profiles/r2_optimisation_log.md section 5): one cp.async.bulk per box row instead of cp.async
+// vectors 435 us (the copy engine serves ~1 small request per 35 cycles and SM); 4 / 8 stages 408 / 394 us; 2 / 4 CTAs
+// per SM 584 / 418 us (4: 56 registers, spills).
+constexpr int REMAP_STAGES = 6;
+constexpr int REMAP_CTAS_PER_SM = 3;
 constexpr int REMAP_CONSUMERS = 256;                                // 8 blending warps
 constexpr int REMAP_THREADS = REMAP_CONSUMERS + 32;                 // + 1 copy warp
 constexpr int REMAP_STAGE_BYTES = s3a::REMAP_BOX_H * s3a::REMAP_BOX_W + 128;   // + padding: a window's second word may lie past the last row
@@ -149,7 +134,7 @@ constexpr int REMAP_SMEM_BYTES = REMAP_STAGES * REMAP_STAGE_BYTES + 2 * REMAP_ST
 // columns), waits for the stage, cuts the taps of each pixel PAIR out of two aligned words per source row
 // (scan3d_aux_math.h: remap_pair_window) and stores 4 output bytes per group; a warp hands the stage back through
 // its "empty" mbarrier.  No CTA-wide barrier inside the frame loop.  W % 16 == 0.
-__global__ void __launch_bounds__(REMAP_THREADS, S3D_REMAP_CTAS) k_remap_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+__global__ void __launch_bounds__(REMAP_THREADS, REMAP_CTAS_PER_SM) k_remap_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                 const short2* __restrict__ map_xy,
                                                                 const uint16_t* __restrict__ map_frac, int W, int H, int n_frames)
 {
@@ -192,7 +177,7 @@ __global__ void __launch_bounds__(REMAP_THREADS, S3D_REMAP_CTAS) k_remap_tiled(c
     if (t == 0) {
         ext[0] = 0x7fffffff; ext[1] = -0x7fffffff; ext[2] = 0x7fffffff; ext[3] = -0x7fffffff;
         for (int s = 0; s < NS; s++) {
-            rm_bar_init(rm_smem(bars + s), S3D_REMAP_BULK ? 1 : 32);    // full: the copy warp's arrive(s) (+ the bytes)
+            rm_bar_init(rm_smem(bars + s), 32);                         // full: one arrival per lane of the copy warp
             rm_bar_init(rm_smem(bars + NS + s), REMAP_CONSUMERS / 32);  // empty: one arrival per blending warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -240,25 +225,6 @@ __global__ void __launch_bounds__(REMAP_THREADS, S3D_REMAP_CTAS) k_remap_tiled(c
         const int lane = t & 31;
         int s = 0;
         uint32_t ph = 1;      // parity of the "empty" phase that precedes the stage's first use: passes at once
-#if S3D_REMAP_BULK
-        // ---------------- copy warp: lane r owns box row r ----------------
-        int d_off = 0;
-        long long s_off = 0;
-        const int bytes = lane < s3a::REMAP_BOX_H ? s3a::remap_box_row_copy(b, lane, W, H, &d_off, &s_off) : 0;
-        int total = bytes;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-        const uint8_t* from = src + s_off;
-        for (int f = 0; f < n_frames; f++) {
-            const uint32_t full = rm_smem(bars + s), empty = rm_smem(bars + NS + s);
-            rm_bar_wait(empty, ph);
-            if (lane == 0) rm_bar_expect(full, (uint32_t)total);
-            __syncwarp();
-            if (bytes) rm_bulk_g2s(rm_smem(box + (size_t)s * REMAP_STAGE_BYTES + d_off), from, (uint32_t)bytes, full);
-            from += plane;
-            if (++s == NS) { s = 0; ph ^= 1u; }
-        }
-#else
         // ---------------- copy warp: lane c owns the box's 16-byte vector column c, one cp.async per box row ----------------
         // (rows and vector columns outside the image are never written: they hold the zero border)
         const int xv = b.x0 + 16 * lane;
@@ -287,7 +253,6 @@ __global__ void __launch_bounds__(REMAP_THREADS, S3D_REMAP_CTAS) k_remap_tiled(c
             if (++s == NS) { s = 0; ph ^= 1u; sbase = d0; }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
         return;
     }
 
