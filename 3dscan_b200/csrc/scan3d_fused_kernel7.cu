@@ -30,9 +30,8 @@
 
 #include "scan3d_fused_common.cuh"
 
-#ifndef S3D_IO_IDLE_NS
-#define S3D_IO_IDLE_NS 250   // the IO warp's back-off when an event-loop pass found nothing to do
-#endif
+// the IO warp's back-off when an event-loop pass found nothing to do (100 / 250 / 600 / 1500 ns measured: no difference)
+constexpr unsigned S3D_IO_IDLE_NS = 250;
 
 namespace s3d {
 
