@@ -186,9 +186,11 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
         bool resolving = false, published = false;
         int look = 0;
         uint32_t excl = 0;
-        uint32_t tot[2] = {0, 0};
-        int epos[2] = {0, 0};
-        bool skip[2] = {false, false};
+        // per staging buffer (0 / 1): count, list position, "empty tile" -- as scalars selected by the buffer index
+        // (arrays indexed by a run-time value live in local memory: ~2 M local accesses and 110 MB of L2 writes per scan)
+        uint32_t tot0 = 0, tot1 = 0;
+        int epos0 = 0, epos1 = 0;
+        bool skip0 = false, skip1 = false;
         while (!ended || (DIRS == 2 && epi_it < load_it)) {
             bool progressed = false;
             // ---- (1) the slot is free again: issue the next tile's loads (or the end marker) ----
@@ -260,10 +262,10 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
 #pragma unroll
                     for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
                     if (lane == 0) trace(a.trace, agg_it, 5);
-                    tot[b] = total;
-                    epos[b] = pos;
-                    skip[b] = total == 0 && pos != n_work - 1 && pos > 0;
-                    if (skip[b]) {
+                    const bool skip_b = total == 0 && pos != n_work - 1 && pos > 0;
+                    if (b) { tot1 = total; epos1 = pos; skip1 = skip_b; }
+                    else { tot0 = total; epos0 = pos; skip0 = skip_b; }
+                    if (skip_b) {
                         // empty tile: nothing to write, never waits; its count (0) is already out --
                         // upgrade it to a prefix if the predecessor's happens to be known
                         if (lane == 0) {
@@ -277,15 +279,18 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                 //      of the oldest pending tile ----
                 if (epi_it < agg_it) {
                     const int b = epi_it & 1;
-                    if (skip[b]) {
+                    const uint32_t tot_b = b ? tot1 : tot0;
+                    const int epos_b = b ? epos1 : epos0;
+                    const bool skip_b = b ? skip1 : skip0;
+                    if (skip_b) {
                         if (__any_sync(0xffffffffu, mbar_try(bar_staged + 8 * b, (epi_it >> 1) & 1))) {
                             if (lane == 0) mbar_arrive(bar_cxfree + 8 * b);
                             epi_it++;
                             progressed = true;
                         }
                     } else {
-                        if (!resolving) { resolving = true; published = false; excl = 0; look = epos[b] - 1; }
-                        bool resolved = published || epos[b] == 0;
+                        if (!resolving) { resolving = true; published = false; excl = 0; look = epos_b - 1; }
+                        bool resolved = published || epos_b == 0;
                         if (!resolved) {
                             // Walk back window after window while the words are there.  The distance
                             // to the nearest known prefix is (count->prefix latency) x (tile rate of
@@ -318,16 +323,16 @@ k_fused7(const __grid_constant__ FusedArgs a, const __grid_constant__ DeviceCali
                             published = true;
                             progressed = true;
                             if (lane == 0) {
-                                st_state(a.tile_state + epos[b], tag | (2ull << 32) | (excl + tot[b]));
-                                if (epos[b] == n_work - 1) *a.d_count = excl + tot[b];
+                                st_state(a.tile_state + epos_b, tag | (2ull << 32) | (excl + tot_b));
+                                if (epos_b == n_work - 1) *a.d_count = excl + tot_b;
                                 trace(a.trace, epi_it, 6);
                             }
                         }
                         resolved = published && __any_sync(0xffffffffu, mbar_try(bar_staged + 8 * b, (epi_it >> 1) & 1));
                         if (resolved) {
                             progressed = true;
-                            const uint32_t total = tot[b];
-                            const int pos = epos[b];
+                            const uint32_t total = tot_b;
+                            const int pos = epos_b;
                             if (total) {
                                 // stream the tile's compacted points as one contiguous block
                                 const float* cx = cxb + b * 3 * T;
